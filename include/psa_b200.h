@@ -1,0 +1,160 @@
+/*
+ * psa_b200.h -- C ABI of the B200-native mutant-offset search.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * GuyKabiri/Parallel-Sequence-Alignment: everything behind
+ *     double gpu_run_program(ProgramData*, Mutant*, int first, int last)   (cuda_funcs.h:33)
+ * i.e. cuda_funcs.cu:6-278 (driver + 3 kernels) and the per-pair primitives it runs on the
+ * device (cuda_funcs.cu:290-502), plus the orchestration around it that north_star replaces:
+ * the rank/CPU/GPU offset split of divide_execute_tasks (cpu_funcs.c:123-218) and the
+ * MPI MAXLOC/MINLOC reduce of initiate_program (cpu_funcs.c:64-94).
+ *
+ * Plain C: pointers and sizes only, no torch / CUDA types in any signature
+ * (a CUDA stream, where one is accepted, is passed as void*).
+ * All entry points are thread-compatible (one call at a time per context).
+ * There is NO CPU fallback: every search entry point fails with PSA_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef PSA_B200_H
+#define PSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSA_ABI_VERSION 1
+
+/* ---- status codes (the reference has none: it exit()s, cuda_funcs.cu:44-48) ------------- */
+enum {
+    PSA_OK            = 0,
+    PSA_ERR_ARG       = -1,  /* NULL pointer, nq < 0, len2 < 1, len2 > len1, empty offset range */
+    PSA_ERR_ALPHABET  = -2,  /* a symbol outside [A-Z-] (undefined behaviour in the reference)  */
+    PSA_ERR_WEIGHTS   = -3,  /* NaN / Inf weight                                               */
+    PSA_ERR_CUDA      = -4,  /* no device / CUDA runtime failure (see psa_last_error)          */
+    PSA_ERR_NOMEM     = -5,
+    PSA_ERR_STATE     = -6,  /* psa_batch_run / psa_batch_fetch without a prepared batch       */
+    PSA_ERR_IO        = -7   /* input.txt / output.txt could not be read / written             */
+};
+
+/* ---- records ---------------------------------------------------------------------------- */
+
+/* Same layout as the reference's Mutant {int offset; int char_offset; char ch;} (mutant.h:6-10). */
+typedef struct psa_mutant {
+    int32_t offset;        /* absolute offset n of Seq2 under Seq1; -1 if no mutation exists */
+    int32_t char_offset;   /* index i in Seq2 of the replaced character; -1 if none          */
+    char    ch;            /* replacement letter; '\0' if none                               */
+} psa_mutant;
+
+/* One result per query. score is the reference's double (cpu_funcs.c:297-299):
+   sum_i w(sign(Seq1[n+i],Seq2[i])) + best single-substitution difference; +-INFINITY if none. */
+typedef struct psa_result {
+    psa_mutant mutant;
+    int32_t    rank;        /* internal: dense rank of the winning substitution difference     */
+    double     score;
+    int64_t    counts[4];   /* N('*'), N(':'), N('.'), N('_') at the winning offset, unmutated */
+} psa_result;
+
+/* Host-resolved 27x27 pair table (replaces fill_hash cpu_funcs.c:304-318 and the per-pair
+   get_substitute search cuda_funcs.cu:310-421).  Row = Seq2 symbol, column = Seq1 symbol;
+   symbol index 0..25 = 'A'..'Z', 26 = '-'. */
+typedef struct psa_pair_table {
+    char    sign[27][27];      /* '*' ':' '.' '_'                                        */
+    char    substitute[27][27];/* best replacement for the Seq2 symbol, '\0' if none      */
+    double  diff[27][27];      /* w(sign(c1,substitute)) - w(sign(c1,c2)) as the reference computes it */
+    uint8_t rank[27][27];      /* 0 = no substitute; 1..nranks, higher = better for the goal */
+    int32_t nranks;
+    int32_t exact;             /* 1: every partial sum is exact in double and int64 fixed point */
+    int32_t frac_bits;         /* fixed-point scale 2^frac_bits used for device score keys      */
+    int64_t key_slack;         /* candidate window (key units) re-scored in reference double order; 0 if exact */
+} psa_pair_table;
+
+typedef struct psa_context psa_context;
+
+/* ---- library / context ------------------------------------------------------------------ */
+
+int         psa_abi_version(void);
+const char* psa_strerror(int status);
+
+/* Number of visible CUDA devices of compute capability 10.x (0 on a CPU-only host). */
+int psa_device_count(void);
+
+/* Create a context over `ndevices` GPUs (device ordinals in devices[], or 0..ndevices-1 when
+   devices == NULL).  Replaces MPI_Init + cudaMalloc-per-call (cuda_funcs.cu:43-69): buffers
+   and streams persist across calls.  Fails with PSA_ERR_CUDA on a host without a usable GPU. */
+int  psa_create(psa_context** ctx, const int* devices, int ndevices);
+void psa_destroy(psa_context* ctx);
+const char* psa_last_error(const psa_context* ctx);
+
+/* Tuning knobs (for tests / benchmarks). name: "engine" 0 = auto, 1 = exact scalar kernel only,
+   2 = bit-sliced scan kernel; "rank_planes" = -1 auto / 0..8. Unknown name -> PSA_ERR_ARG. */
+int psa_set_option(psa_context* ctx, const char* name, long long value);
+/* Counters of the last run. name: "kernel_launches", "candidate_tiles", "tiles",
+   "fallback_queries", "engine". Unknown -> -1. */
+long long psa_get_stat(const psa_context* ctx, const char* name);
+
+/* ---- host-side table resolution (no GPU needed) ------------------------------------------ */
+
+/* max_len2 sizes the exactness analysis (longest query in the batch). */
+int psa_build_pair_table(const double weights[4], int is_max, long long max_len2, psa_pair_table* out);
+
+/* ---- the search ---------------------------------------------------------------------------- */
+
+/* Batched search: nq queries against one Seq1 under one (weights, goal).
+   Query q is seq2s[q_off[q] .. q_off[q+1]) (ASCII, not NUL-terminated); every query is searched
+   over all offsets 0 .. len1-len2(q).  Work is partitioned over the context's GPUs by contiguous
+   query blocks (or by offset range when nq == 1) and merged on the host under the reference
+   order: best score, then lowest offset, then lowest char_offset (cuda_funcs.cu:290-307).
+   Host pointers may be pageable or pinned. */
+int psa_search_batch(psa_context* ctx, const double weights[4], int is_max,
+                     const char* seq1, int64_t len1,
+                     const char* seq2s, const int64_t* q_off, int32_t nq,
+                     psa_result* out);
+
+/* One query restricted to absolute offsets [first,last) -- the gpu_run_program contract. */
+int psa_search_range(psa_context* ctx, const double weights[4], int is_max,
+                     const char* seq1, int64_t len1, const char* seq2, int64_t len2,
+                     int64_t first, int64_t last, psa_result* out);
+
+/* Split-phase form of psa_search_batch, for callers that keep a batch resident in HBM:
+   prepare = validate + H2D + table/profile resolution; run = the kernels only (returns the
+   device time in ms measured with CUDA events on the library's streams, max over the
+   context's GPUs); fetch = D2H of the per-query records + host scoring. */
+int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max,
+                      const char* seq1, int64_t len1,
+                      const char* seq2s, const int64_t* q_off, int32_t nq);
+int psa_batch_run(psa_context* ctx, float* device_ms);
+int psa_batch_fetch(psa_context* ctx, psa_result* out);
+
+/* Pinned host memory for callers that want true async H2D (bench e2e leg). */
+void* psa_alloc_pinned(size_t bytes);
+void  psa_free_pinned(void* p);
+
+/* ---- drop-in for the reference entry point --------------------------------------------------
+ * psa_gpu_run_program is the extern "C" spelling of
+ *     double gpu_run_program(ProgramData* cpu_data, Mutant* returned_mutant,
+ *                            int first_offset, int last_offset);           (cuda_funcs.h:33)
+ * program_data points at the reference's ProgramData {int is_max; double weights[4];
+ * char seq1[10001]; char seq2[5001];} (program_data.h:6-11), returned_mutant at its Mutant.
+ * Returns the best score over absolute offsets [first,last), or -INFINITY/+INFINITY (goal
+ * max/min) when no mutation exists (cuda_funcs.cu:143-145).  Like the reference it prints to
+ * stderr and exit(EXIT_FAILURE)s on any CUDA error.  The library also exports the C++-mangled
+ * symbol _Z15gpu_run_programP5_dataP7_mutantii that the reference's cpu_funcs.c links against.
+ */
+double psa_gpu_run_program(void* program_data, void* returned_mutant, int first_offset, int last_offset);
+
+/* input.txt / output.txt in the reference's format (cpu_funcs.c:353-378): four weights, Seq1,
+   Seq2, "maximum"|"minimum" (anything else = minimum), whitespace separated; output
+   "<mutant>\n<offset> <score %g>" without trailing newline.  seq buffers are malloc()ed. */
+int psa_read_input_file(const char* path, double weights[4], int* is_max, char** seq1, char** seq2);
+int psa_write_output_file(const char* path, const char* mutant, int offset, double score);
+
+/* The whole reference program for one input file: read, search on the context's GPUs, write. */
+int psa_run_files(psa_context* ctx, const char* input_path, const char* output_path, psa_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSA_B200_H */

@@ -1,0 +1,155 @@
+// psa_capi.cpp -- the reference-facing surface: gpu_run_program drop-in, input.txt / output.txt,
+// and psa_run_files (what initiate_program does around the hot path, cpu_funcs.c:25-121).
+#include "psa_host.h"
+#include "psa_reference_abi.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cctype>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static_assert(offsetof(ProgramData, weights) == 8, "ProgramData layout (program_data.h:6-11)");
+static_assert(offsetof(ProgramData, seq1) == 40, "ProgramData layout (program_data.h:6-11)");
+static_assert(offsetof(ProgramData, seq2) == 40 + PSA_SEQ1_CAPACITY + 1, "ProgramData layout");
+static_assert(sizeof(Mutant) == 12 && offsetof(Mutant, ch) == 8, "Mutant layout (mutant.h:6-10)");
+static_assert(sizeof(psa_mutant) == sizeof(Mutant), "psa_mutant mirrors Mutant");
+
+namespace {
+
+// gpu_run_program has no context argument: keep one per CUDA device, created on first use and
+// kept for the life of the process (the reference allocates and frees per call instead).
+std::mutex g_mu;
+std::map<int, psa_context*> g_ctx;
+
+[[noreturn]] void die(const char* what, const char* detail)
+{
+    // the reference's convention for every CUDA failure (cuda_funcs.cu:44-48)
+    std::fprintf(stderr, "%s - %s\n", what, detail);
+    std::exit(EXIT_FAILURE);
+}
+
+psa_context* context_for_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) die("Failed to query the CUDA device", cudaGetErrorString(cudaGetLastError()));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(dev);
+    if (it != g_ctx.end()) return it->second;
+    psa_context* ctx = nullptr;
+    int rc = psa_create(&ctx, &dev, 1);
+    if (rc) die("Failed to create the GPU context", psa_strerror(rc));
+    g_ctx[dev] = ctx;
+    return ctx;
+}
+
+} // namespace
+
+// C++ linkage on purpose: this is the symbol cpu_funcs.c:180 resolves.
+double gpu_run_program(ProgramData* cpu_data, Mutant* returned_mutant, int first_offset, int last_offset)
+{
+    if (!cpu_data || !returned_mutant) die("gpu_run_program", "null argument");
+    const double none = cpu_data->is_max ? -INFINITY : INFINITY;
+    returned_mutant->offset = -1;
+    returned_mutant->char_offset = -1;
+    returned_mutant->ch = '\0';
+    if (last_offset <= first_offset) return none;         // the reference's caller never does this (cpu_funcs.c:178)
+    psa_context* ctx = context_for_current_device();
+    psa_result r;
+    int rc = psa_search_range(ctx, cpu_data->weights, cpu_data->is_max, cpu_data->seq1,
+                              (int64_t)std::strlen(cpu_data->seq1), cpu_data->seq2,
+                              (int64_t)std::strlen(cpu_data->seq2), first_offset, last_offset, &r);
+    if (rc) die("Failed to run the mutant-offset search on the GPU", psa_last_error(ctx));
+    returned_mutant->offset = r.mutant.offset;
+    returned_mutant->char_offset = r.mutant.char_offset;
+    returned_mutant->ch = r.mutant.ch;
+    return r.mutant.ch == '\0' ? none : r.score;           // cuda_funcs.cu:143-145
+}
+
+extern "C" {
+
+double psa_gpu_run_program(void* program_data, void* returned_mutant, int first_offset, int last_offset)
+{
+    return gpu_run_program((ProgramData*)program_data, (Mutant*)returned_mutant, first_offset, last_offset);
+}
+
+// Whitespace-separated tokens, like the reference's fscanf("%lf %lf %lf %lf") + three fscanf("%s")
+// (cpu_funcs.c:353-368), but without its fixed-size buffers.
+int psa_read_input_file(const char* path, double weights[4], int* is_max, char** seq1, char** seq2)
+{
+    if (!path || !weights || !is_max || !seq1 || !seq2) return PSA_ERR_ARG;
+    *seq1 = *seq2 = nullptr;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return PSA_ERR_IO;
+    int rc = PSA_ERR_IO;
+    std::string tok[3];
+    if (std::fscanf(f, "%lf %lf %lf %lf", &weights[0], &weights[1], &weights[2], &weights[3]) == 4) {
+        int got = 0;
+        for (; got < 3; got++) {
+            int c;
+            while ((c = std::fgetc(f)) != EOF && std::isspace(c)) {}
+            if (c == EOF) break;
+            do { tok[got].push_back((char)c); } while ((c = std::fgetc(f)) != EOF && !std::isspace(c));
+        }
+        if (got == 3) {
+            *is_max = tok[2] == "maximum" ? 1 : 0;        // anything else is a minimum (cpu_funcs.c:365)
+            *seq1 = (char*)std::malloc(tok[0].size() + 1);
+            *seq2 = (char*)std::malloc(tok[1].size() + 1);
+            if (*seq1 && *seq2) {
+                std::memcpy(*seq1, tok[0].c_str(), tok[0].size() + 1);
+                std::memcpy(*seq2, tok[1].c_str(), tok[1].size() + 1);
+                rc = PSA_OK;
+            } else {
+                std::free(*seq1); std::free(*seq2);
+                *seq1 = *seq2 = nullptr;
+                rc = PSA_ERR_NOMEM;
+            }
+        }
+    }
+    std::fclose(f);
+    return rc;
+}
+
+int psa_write_output_file(const char* path, const char* mutant, int offset, double score)
+{
+    if (!path || !mutant) return PSA_ERR_ARG;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return PSA_ERR_IO;
+    // "<mutant>\n<offset> <score>" with %g and no trailing newline (cpu_funcs.c:377)
+    int ok = std::fprintf(f, "%s\n%d %g", mutant, offset, score) > 0;
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? PSA_OK : PSA_ERR_IO;
+}
+
+int psa_run_files(psa_context* ctx, const char* input_path, const char* output_path, psa_result* out)
+{
+    if (!ctx || !input_path || !output_path) return PSA_ERR_ARG;
+    double w[4];
+    int is_max = 0;
+    char *seq1 = nullptr, *seq2 = nullptr;
+    int rc = psa_read_input_file(input_path, w, &is_max, &seq1, &seq2);
+    if (rc) return rc;
+    const int64_t len1 = (int64_t)std::strlen(seq1), len2 = (int64_t)std::strlen(seq2);
+    const int64_t q_off[2] = { 0, len2 };
+    psa_result r;
+    rc = psa_search_batch(ctx, w, is_max, seq1, len1, seq2, q_off, 1, &r);
+    if (rc == PSA_OK) {
+        // the mutant string: Seq2 with one character replaced (cpu_funcs.c:96-98); if no mutation
+        // exists the reference indexes with -1 (undefined) -- here Seq2 is written unchanged
+        std::string mut(seq2);
+        if (r.mutant.char_offset >= 0) mut[(size_t)r.mutant.char_offset] = r.mutant.ch;
+        rc = psa_write_output_file(output_path, mut.c_str(), r.mutant.offset, r.score);
+        if (out) *out = r;
+    }
+    std::free(seq1); std::free(seq2);
+    return rc;
+}
+
+} // extern "C"

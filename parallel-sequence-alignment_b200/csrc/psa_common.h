@@ -1,0 +1,70 @@
+// psa_common.h -- structures shared by the host resolver and the sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+namespace psa {
+
+constexpr int kSymbols   = 27;   // 'A'..'Z', '-'
+constexpr int kGap       = 26;
+constexpr int kRowPad    = 32;   // table rows padded to 32 columns (one shared-memory bank line)
+constexpr int kZeroRow   = 27;   // bit-plane row of zeros used to pad Seq2 to a multiple of 32 steps
+constexpr int kPlaneRows = 28;
+constexpr int kMaxRanks  = 15;   // rank field is 4 bits; 0 = "no substitute"
+constexpr uint8_t kBadSymbol = 0xFF;
+
+// Packed per-pair payload, code[c2][c1]:
+//   bits 0-1  sign class   0 '*'  1 ':'  2 '.'  3 '_'
+//   bits 2-5  rank of the best substitution difference (0 none, 1..nranks; higher = better for the goal)
+// The reference evaluates get_hashtable_sign + get_substitute + get_weight for every pair of every
+// offset (cpu_funcs.c:277-285, cuda_funcs.cu:183-193); all three are pure functions of (c1,c2) for a
+// given (weights, goal), so they are resolved once on the host into this table.
+struct DeviceTable {
+    uint8_t code[kSymbols][kRowPad];
+    uint8_t sub[kSymbols][kRowPad];   // ASCII replacement letter (0 = none)
+    int64_t kcls[4];                  // goal-signed fixed-point pair weight per class (key units)
+    int64_t kdiff[kMaxRanks + 1];     // goal-signed fixed-point substitution difference per rank
+    double  wcls[4];                  // +W1, -W2, -W3, -W4 exactly as get_weight returns them
+    double  wdiff[kMaxRanks + 1];     // the reference's double difference per rank
+    int64_t key_slack;                // 0 in exact mode
+    int32_t nranks;
+    int32_t is_max;
+    int32_t exact;
+    int32_t has_none;                 // some pair has no substitute (never observed; handled anyway)
+};
+
+constexpr int64_t kKeyNone = INT64_MIN;       // key of an offset with no possible mutation / no data
+
+// One record per (query, tile of offsets), written by the scan / exact kernels.
+struct TileRec {
+    int64_t key;        // best resolved key in the tile (kKeyNone if none)
+    int64_t ub_key;     // best upper bound among offsets the scan could not resolve (kKeyNone if none)
+    double  score;      // exact kernel, re-score mode: reference double score of the tile winner
+    int32_t offset;     // absolute offset of `key` / `score`
+    int32_t ub_offset;
+    int32_t flags;      // bit0: written by the exact kernel
+    int32_t pad;
+};
+constexpr int kTileExact = 1;
+
+// One record per query, written by the final kernel and copied back to the host.
+struct QueryRec {
+    int64_t key;
+    double  score;        // valid when !exact (re-score mode); host derives it from counts otherwise
+    int32_t offset;
+    int32_t char_offset;
+    int32_t ch;
+    int32_t rank;
+    int32_t counts[4];
+};
+
+// Launch geometry shared by all kernels of one batch.
+struct BatchGeom {
+    int64_t len1;
+    int64_t first;          // single-query range mode: absolute first offset (else 0)
+    int64_t last;           // single-query range mode: absolute last offset (exclusive), else -1 = all
+    int32_t nq;
+    int32_t tile;           // offsets per tile
+    int32_t total_tiles;
+};
+
+} // namespace psa

@@ -1,0 +1,566 @@
+// psa_engine.cu -- context, persistent buffers, (query | offset-range) partitioning over GPUs,
+// and the C ABI declared in include/psa_b200.h.
+//
+// Replaces the host side of the reference's GPU path and the orchestration around it:
+//   gpu_run_program            cuda_funcs.cu:6-146   (cudaMalloc x3 + copies + cudaFree x3 per call)
+//   divide_execute_tasks       cpu_funcs.c:123-218   (rank x CPU/GPU x thread split of offsets)
+//   initiate_program's reduce  cpu_funcs.c:64-94     (MPI_Allreduce MAXLOC/MINLOC + Send/Recv)
+// with one process driving 1..8 GPUs: buffers and streams persist in a context, every GPU gets a
+// contiguous block of queries (or, for a single query, a contiguous range of offsets -- the same
+// split as cpu_funcs.c:128-133 with GPUs in place of ranks), all GPUs are enqueued before any is
+// waited for, and the <= 8 candidates per query are merged on the host under the reference order
+// (best score, then lowest offset: MAXLOC/MINLOC ties go to the lowest rank = lowest offsets).
+#include "psa_host.h"
+#include "psa_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace psa;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct DeviceState {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, cand_list, flags, cls_planes, rank_planes;
+    PinBuf h_qoff, h_tile_start, h_out, h_flags;
+    // slice of the current batch owned by this GPU
+    int q_begin = 0, q_end = 0;
+    BatchGeom G{};
+    BatchPtrs P{};
+    bool active = false;
+};
+
+} // namespace
+
+struct psa_context {
+    std::vector<DeviceState> devs;
+    std::string err;
+    // options
+    int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
+    int opt_rank_planes = -1;  // -1 auto
+    // current batch
+    bool prepared = false, ran = false;
+    bool range_split = false;  // single query split by offset range over the GPUs
+    DeviceTable table{};
+    double weights[4] = { 0, 0, 0, 0 };
+    int is_max = 0;
+    int nq = 0;
+    int engine = 1;
+    int rank_planes = 0;
+    int64_t max_len2 = 0;
+    std::vector<int64_t> len2s;
+    // stats of the last run
+    long long st_launches = 0, st_cand = 0, st_tiles = 0;
+};
+
+namespace {
+
+int fail(psa_context* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define PSA_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, PSA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+int ensure_dev(psa_context* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return PSA_OK;
+    if (b.p) PSA_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    PSA_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return PSA_OK;
+}
+
+int ensure_pin(psa_context* ctx, PinBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return PSA_OK;
+    if (b.p) PSA_CUDA(ctx, cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    PSA_CUDA(ctx, cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return PSA_OK;
+}
+
+void release(DeviceState& d)
+{
+    cudaSetDevice(d.dev);
+    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.cand_list, &d.flags,
+                       &d.cls_planes, &d.rank_planes })
+        if (b->p) cudaFree(b->p);
+    for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out, &d.h_flags })
+        if (b->p) cudaFreeHost(b->p);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+inline int64_t offsets_of(int64_t len1, int64_t len2) { return len1 - len2 + 1; }
+
+int pick_rank_planes(const psa_context* ctx)
+{
+    int avail = ctx->table.nranks - (ctx->table.has_none ? 0 : 1);   // planes needed to resolve everything
+    if (avail < 0) avail = 0;
+    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : 2;
+    if (want > 2) want = want >= 4 ? 4 : 2;                          // supported widths: 0,1,2,4
+    return std::min(want, std::max(avail, 0));
+}
+
+// Enqueue H2D copies and geometry for one GPU's slice. first/last >= 0 selects range mode (nq == 1).
+int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t len1, const char* seq2s,
+                   const int64_t* q_off, int q_begin, int q_end, int64_t first, int64_t last)
+{
+    PSA_CUDA(ctx, cudaSetDevice(d.dev));
+    const int nq = q_end - q_begin;
+    d.q_begin = q_begin; d.q_end = q_end;
+    d.active = nq > 0;
+    if (!d.active) return PSA_OK;
+
+    const bool scan = ctx->engine == 2;
+    const int tile = scan ? kScanTile : kExactTile;
+    int rc;
+    if ((rc = ensure_pin(ctx, d.h_qoff, sizeof(int64_t) * (nq + 1)))) return rc;
+    if ((rc = ensure_pin(ctx, d.h_tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
+    if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq))) return rc;
+    if ((rc = ensure_pin(ctx, d.h_flags, sizeof(int32_t) * 4))) return rc;
+    int64_t* hq = (int64_t*)d.h_qoff.p;
+    int32_t* ht = (int32_t*)d.h_tile_start.p;
+    const int64_t byte0 = q_off[q_begin];
+    int64_t tiles = 0;
+    for (int k = 0; k < nq; k++) {
+        hq[k] = q_off[q_begin + k] - byte0;
+        const int64_t len2 = q_off[q_begin + k + 1] - q_off[q_begin + k];
+        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, len2);
+        ht[k] = (int32_t)tiles;
+        tiles += (l - tile_base(f) + tile - 1) / tile;
+        if (tiles > 0x7FFFFF00) return fail(ctx, PSA_ERR_ARG, "batch too large: more than 2^31 tiles on one GPU");
+    }
+    hq[nq] = q_off[q_end] - byte0;
+    ht[nq] = (int32_t)tiles;
+    const int64_t seq2_bytes = hq[nq];
+
+    const int64_t pad_bits = kScanTile + 2048 + 64;
+    const int64_t plane_words = (len1 + pad_bits + 31) / 32;
+    if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.qoff, sizeof(int64_t) * (nq + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, d.tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, d.tiles, sizeof(TileRec) * (size_t)tiles))) return rc;
+    if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq))) return rc;
+    if ((rc = ensure_dev(ctx, d.cand_list, sizeof(int32_t) * (size_t)tiles))) return rc;
+    if ((rc = ensure_dev(ctx, d.flags, sizeof(int32_t) * 4))) return rc;
+    if (scan) {
+        if ((rc = ensure_dev(ctx, d.cls_planes, sizeof(uint2) * (size_t)plane_words * kPlaneRows))) return rc;
+        if ((rc = ensure_dev(ctx, d.rank_planes,
+                             sizeof(uint32_t) * (size_t)plane_words * kPlaneRows * std::max(ctx->rank_planes, 1))))
+            return rc;
+    }
+
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2s + byte0, (size_t)seq2_bytes, cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.qoff.p, hq, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.tile_start.p, ht, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
+
+    d.G.len1 = len1;
+    d.G.first = last >= 0 ? first : 0;
+    d.G.last = last >= 0 ? last : -1;
+    d.G.nq = nq;
+    d.G.tile = tile;
+    d.G.total_tiles = (int32_t)tiles;
+    d.P.seq1 = (const uint8_t*)d.seq1.p;
+    d.P.seq2s = (const uint8_t*)d.seq2s.p;
+    d.P.qoff = (const int64_t*)d.qoff.p;
+    d.P.tile_start = (const int32_t*)d.tile_start.p;
+    d.P.tiles = (TileRec*)d.tiles.p;
+    d.P.out = (QueryRec*)d.out.p;
+    d.P.cand_list = (int32_t*)d.cand_list.p;
+    d.P.cand_count = (int32_t*)d.flags.p;
+    d.P.err_flag = (int32_t*)d.flags.p + 1;
+    d.P.cls_planes = (uint2*)d.cls_planes.p;
+    d.P.rank_planes = (uint32_t*)d.rank_planes.p;
+    d.P.plane_words = plane_words;
+    return PSA_OK;
+}
+
+int run_device(psa_context* ctx, DeviceState& d)
+{
+    if (!d.active) return PSA_OK;
+    PSA_CUDA(ctx, cudaSetDevice(d.dev));
+    PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    PSA_CUDA(ctx, cudaMemsetAsync(d.flags.p, 0, sizeof(int32_t) * 4, d.stream));
+    if (ctx->engine == 2) {
+        launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
+        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, d.stream);
+        launch_select(ctx->table, d.G, d.P, d.stream);
+        launch_exact_tiles(ctx->table, d.G, d.P, true, d.sm_count, d.stream);
+        ctx->st_launches += 4;
+    } else {
+        launch_exact_tiles(ctx->table, d.G, d.P, false, d.sm_count, d.stream);
+        ctx->st_launches += 1;
+    }
+    launch_final(ctx->table, d.G, d.P, d.stream);
+    ctx->st_launches += 1;
+    PSA_CUDA(ctx, cudaGetLastError());
+    PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    ctx->st_tiles += d.G.total_tiles;
+    return PSA_OK;
+}
+
+// reference order on (score, offset): strictly better score, or equal score and lower offset
+inline bool swapable(int is_max, double s_old, int off_old, double s_new, int off_new)
+{
+    if (is_max ? s_new > s_old : s_new < s_old) return true;
+    return s_new == s_old && off_new < off_old;
+}
+
+double score_from_counts(const psa_context* ctx, const QueryRec& r)
+{
+    // exact mode: every product and partial sum below is exactly representable, so this equals the
+    // reference's sequential sum + difference bit for bit
+    const double* w = ctx->table.wcls;
+    double s = 0.0;
+    for (int c = 0; c < 4; c++) s += double(r.counts[c]) * w[c];
+    return s + ctx->table.wdiff[r.rank] + 0.0;
+}
+
+void to_result(const psa_context* ctx, const QueryRec& r, psa_result* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    if (r.offset < 0 || r.rank <= 0) {
+        out->mutant.offset = -1; out->mutant.char_offset = -1; out->mutant.ch = '\0';
+        out->score = ctx->is_max ? -INFINITY : INFINITY;
+        return;
+    }
+    out->mutant.offset = r.offset;
+    out->mutant.char_offset = r.char_offset;
+    out->mutant.ch = (char)r.ch;
+    out->rank = r.rank;
+    for (int c = 0; c < 4; c++) out->counts[c] = r.counts[c];
+    out->score = ctx->table.exact ? score_from_counts(ctx, r) : r.score + 0.0;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int psa_abi_version(void) { return PSA_ABI_VERSION; }
+
+const char* psa_strerror(int status)
+{
+    switch (status) {
+    case PSA_OK: return "ok";
+    case PSA_ERR_ARG: return "invalid argument";
+    case PSA_ERR_ALPHABET: return "sequence symbol outside [A-Z-]";
+    case PSA_ERR_WEIGHTS: return "weights must be finite";
+    case PSA_ERR_CUDA: return "CUDA error or no usable sm_100 GPU";
+    case PSA_ERR_NOMEM: return "out of memory";
+    case PSA_ERR_STATE: return "no batch prepared";
+    case PSA_ERR_IO: return "file I/O error";
+    }
+    return "unknown status";
+}
+
+int psa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int psa_create(psa_context** out, const int* devices, int ndevices)
+{
+    if (!out || ndevices < 1) return PSA_ERR_ARG;
+    *out = nullptr;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) { cudaGetLastError(); return PSA_ERR_CUDA; }
+    psa_context* ctx = new (std::nothrow) psa_context();
+    if (!ctx) return PSA_ERR_NOMEM;
+    ctx->devs.resize(ndevices);
+    for (int i = 0; i < ndevices; i++) {
+        DeviceState& d = ctx->devs[i];
+        d.dev = devices ? devices[i] : i;
+        int major = 0;
+        if (d.dev < 0 || d.dev >= visible || cudaSetDevice(d.dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d.dev) != cudaSuccess || major != 10 ||
+            cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.dev) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
+            cudaGetLastError();
+            for (DeviceState& x : ctx->devs) release(x);
+            delete ctx;
+            return PSA_ERR_CUDA;     // the kernels are sm_100a only: no other device can run them
+        }
+    }
+    *out = ctx;
+    return PSA_OK;
+}
+
+void psa_destroy(psa_context* ctx)
+{
+    if (!ctx) return;
+    for (DeviceState& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        release(d);
+    }
+    delete ctx;
+}
+
+const char* psa_last_error(const psa_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int psa_set_option(psa_context* ctx, const char* name, long long value)
+{
+    if (!ctx || !name) return PSA_ERR_ARG;
+    if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    return PSA_ERR_ARG;
+}
+
+long long psa_get_stat(const psa_context* ctx, const char* name)
+{
+    if (!ctx || !name) return -1;
+    if (!std::strcmp(name, "kernel_launches")) return ctx->st_launches;
+    if (!std::strcmp(name, "candidate_tiles")) return ctx->st_cand;
+    if (!std::strcmp(name, "tiles")) return ctx->st_tiles;
+    if (!std::strcmp(name, "engine")) return ctx->engine;
+    if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
+    if (!std::strcmp(name, "exact")) return ctx->table.exact;
+    return -1;
+}
+
+static int prepare_common(psa_context* ctx, const double* weights, int is_max, const char* seq1, int64_t len1,
+                          const char* seq2s, const int64_t* q_off, int32_t nq, int64_t first, int64_t last)
+{
+    if (!ctx) return PSA_ERR_ARG;
+    ctx->prepared = ctx->ran = false;
+    if (!weights || !seq1 || !seq2s || !q_off || nq < 0) return fail(ctx, PSA_ERR_ARG, "null argument or nq < 0");
+    if (len1 < 1 || len1 > 0x7FFF0000ll) return fail(ctx, PSA_ERR_ARG, "len1 out of range");
+    int64_t max_len2 = 0;
+    ctx->len2s.resize(nq);
+    for (int q = 0; q < nq; q++) {
+        const int64_t len2 = q_off[q + 1] - q_off[q];
+        if (len2 < 1 || len2 > len1) return fail(ctx, PSA_ERR_ARG, "query %d: len2=%lld must be in [1, len1]", q, (long long)len2);
+        ctx->len2s[q] = len2;
+        max_len2 = std::max(max_len2, len2);
+    }
+    if (max_len2 > kExactMaxLen2) return fail(ctx, PSA_ERR_ARG, "len2 > %lld is not supported", (long long)kExactMaxLen2);
+    if (last >= 0) {
+        if (nq != 1 || first < 0 || first >= last || last > offsets_of(len1, max_len2))
+            return fail(ctx, PSA_ERR_ARG, "offset range [%lld,%lld) invalid", (long long)first, (long long)last);
+    }
+    int rc = build_tables(weights, is_max, std::max<int64_t>(max_len2, 1), nullptr, &ctx->table);
+    if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
+    std::memcpy(ctx->weights, weights, sizeof(ctx->weights));
+    ctx->is_max = is_max ? 1 : 0;
+    ctx->nq = nq;
+    ctx->max_len2 = max_len2;
+    ctx->engine = ctx->opt_engine ? ctx->opt_engine : kDefaultEngine;
+    if (ctx->engine == 2 && max_len2 > kScanMaxLen2) ctx->engine = 1;
+    ctx->rank_planes = ctx->engine == 2 ? pick_rank_planes(ctx) : 0;
+
+    const int ndev = (int)ctx->devs.size();
+    ctx->range_split = false;
+    for (DeviceState& d : ctx->devs) d.active = false;
+    if (nq == 0) { ctx->prepared = true; return PSA_OK; }
+
+    if (nq == 1) {
+        // one query: contiguous offset ranges per GPU (cpu_funcs.c:128-133 with GPUs as ranks),
+        // rounded to whole tiles so no GPU gets a sliver
+        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, max_len2);
+        const int64_t tile = ctx->engine == 2 ? kScanTile : kExactTile;
+        const int64_t ntiles = (l - tile_base(f) + tile - 1) / tile;
+        const int use = (int)std::min<int64_t>(ndev, ntiles);
+        ctx->range_split = use > 1;
+        int64_t t0 = 0;
+        for (int g = 0; g < use; g++) {
+            const int64_t t1 = ntiles * (g + 1) / use;
+            const int64_t gf = std::max(f, tile_base(f) + t0 * tile), gl = std::min(l, tile_base(f) + t1 * tile);
+            t0 = t1;
+            if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, 0, 1, gf, gl))) return rc;
+        }
+    } else {
+        // many queries: contiguous blocks balanced by pair evaluations
+        std::vector<double> work(nq + 1, 0.0);
+        for (int q = 0; q < nq; q++) work[q + 1] = work[q] + double(offsets_of(len1, ctx->len2s[q])) * double(ctx->len2s[q]);
+        int qb = 0;
+        for (int g = 0; g < ndev; g++) {
+            int qe;
+            if (g == ndev - 1) qe = nq;
+            else {
+                const double target = work[nq] * double(g + 1) / double(ndev);
+                qe = int(std::lower_bound(work.begin(), work.end(), target) - work.begin());
+                qe = std::max(qb, std::min(qe, nq));
+            }
+            if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, qb, qe, -1, -1))) return rc;
+            qb = qe;
+        }
+    }
+    ctx->prepared = true;
+    return PSA_OK;
+}
+
+int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
+                      const char* seq2s, const int64_t* q_off, int32_t nq)
+{
+    int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
+    if (rc) return rc;
+    // the split-phase form promises a resident batch: wait for the copies here
+    for (DeviceState& d : ctx->devs)
+        if (d.active) { PSA_CUDA(ctx, cudaSetDevice(d.dev)); PSA_CUDA(ctx, cudaStreamSynchronize(d.stream)); }
+    return PSA_OK;
+}
+
+static int run_async(psa_context* ctx)
+{
+    if (!ctx || !ctx->prepared) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch prepared") : PSA_ERR_ARG;
+    ctx->st_launches = ctx->st_cand = ctx->st_tiles = 0;
+    for (DeviceState& d : ctx->devs) {
+        int rc = run_device(ctx, d);
+        if (rc) return rc;
+    }
+    ctx->ran = true;
+    return PSA_OK;
+}
+
+int psa_batch_run(psa_context* ctx, float* device_ms)
+{
+    int rc = run_async(ctx);
+    if (rc) return rc;
+    float worst = 0.f;
+    for (DeviceState& d : ctx->devs) {
+        if (!d.active) continue;
+        PSA_CUDA(ctx, cudaSetDevice(d.dev));
+        PSA_CUDA(ctx, cudaEventSynchronize(d.ev1));
+        float ms = 0.f;
+        PSA_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        worst = std::max(worst, ms);
+    }
+    if (device_ms) *device_ms = worst;
+    return PSA_OK;
+}
+
+int psa_batch_fetch(psa_context* ctx, psa_result* out)
+{
+    if (!ctx || !ctx->prepared || !ctx->ran) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch has run") : PSA_ERR_ARG;
+    if (ctx->nq == 0) return PSA_OK;
+    if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
+    for (DeviceState& d : ctx->devs) {
+        if (!d.active) continue;
+        PSA_CUDA(ctx, cudaSetDevice(d.dev));
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, sizeof(QueryRec) * d.G.nq, cudaMemcpyDeviceToHost, d.stream));
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_flags.p, d.flags.p, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, d.stream));
+    }
+    bool bad_symbol = false;
+    for (DeviceState& d : ctx->devs) {
+        if (!d.active) continue;
+        PSA_CUDA(ctx, cudaSetDevice(d.dev));
+        PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        const int32_t* fl = (const int32_t*)d.h_flags.p;
+        ctx->st_cand += fl[0];
+        if (fl[1]) bad_symbol = true;
+    }
+    if (bad_symbol) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
+
+    if (ctx->range_split || (ctx->nq == 1)) {
+        // merge the per-GPU candidates of the single query in ascending offset order
+        psa_result best;
+        bool have = false;
+        for (DeviceState& d : ctx->devs) {
+            if (!d.active) continue;
+            psa_result cur;
+            to_result(ctx, ((const QueryRec*)d.h_out.p)[0], &cur);
+            if (cur.mutant.offset < 0) continue;
+            if (!have || swapable(ctx->is_max, best.score, best.mutant.offset, cur.score, cur.mutant.offset)) {
+                best = cur; have = true;
+            }
+        }
+        if (!have) { QueryRec none{}; none.offset = -1; to_result(ctx, none, &best); }
+        out[0] = best;
+        return PSA_OK;
+    }
+    for (DeviceState& d : ctx->devs) {
+        if (!d.active) continue;
+        const QueryRec* recs = (const QueryRec*)d.h_out.p;
+        for (int k = 0; k < d.G.nq; k++) to_result(ctx, recs[k], &out[d.q_begin + k]);
+    }
+    return PSA_OK;
+}
+
+int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
+                     const char* seq2s, const int64_t* q_off, int32_t nq, psa_result* out)
+{
+    int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
+    if (rc) return rc;
+    if ((rc = run_async(ctx))) return rc;
+    return psa_batch_fetch(ctx, out);
+}
+
+int psa_search_range(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
+                     const char* seq2, int64_t len2, int64_t first, int64_t last, psa_result* out)
+{
+    if (first < 0 || last < 0) return ctx ? fail(ctx, PSA_ERR_ARG, "negative offset") : PSA_ERR_ARG;
+    const int64_t q_off[2] = { 0, len2 };
+    int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2, q_off, 1, first, last);
+    if (rc) return rc;
+    if ((rc = run_async(ctx))) return rc;
+    return psa_batch_fetch(ctx, out);
+}
+
+void* psa_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void psa_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

@@ -1,0 +1,346 @@
+// psa_kernels.cu -- exact scalar kernel, candidate selection and per-query finalisation (sm_100a).
+//
+// Together with psa_scan.cu these replace the reference's calc_mutants_scores / reduction /
+// reduce_last_results kernels (cuda_funcs.cu:149-264).  Differences in kind, not in result:
+//   * no per-pair substitution search on the device: one byte of a host-resolved table per pair;
+//   * no global-memory scratch of offsets x block_size records (the reference allocates
+//     offsets*B*32 bytes per call, cuda_funcs.cu:57-64): partial results live in registers and
+//     are reduced with warp shuffles, one 40-byte record per tile of offsets reaches HBM;
+//   * integer sign counts and an int64 key instead of tree-summed doubles, so the order of
+//     offsets does not depend on the reduction shape (the reference's GPU path differs from its
+//     own CPU path there, and races across blocks, cuda_funcs.cu:239-264);
+//   * when the weights are not exactly summable, candidate tiles are re-scored with a double
+//     accumulated in the reference's CPU order (cpu_funcs.c:271-299) so the winner is the CPU
+//     reference's winner.
+#include "psa_kernels.cuh"
+
+namespace psa {
+
+namespace {
+
+constexpr int kExactThreads = 256;
+constexpr int kExactChunk = 2048;       // Seq2 symbols staged per pass
+
+__device__ __forceinline__ uint32_t symbol_of(uint8_t c)
+{
+    uint32_t d = uint32_t(c) - uint32_t('A');
+    return d < 26u ? d : (c == uint8_t('-') ? uint32_t(kGap) : 0xFFu);
+}
+
+// (key, offset) ordering used everywhere: larger key wins, ties go to the lower offset
+// (is_swapable, cuda_funcs.cu:290-307, with the score already goal-signed into the key).
+struct Cand {
+    int64_t key;
+    int32_t off;
+};
+
+__device__ __forceinline__ bool better(int64_t k2, int32_t o2, int64_t k1, int32_t o1)
+{
+    return k2 > k1 || (k2 == k1 && o2 < o1);
+}
+
+__device__ __forceinline__ Cand warp_best(Cand c)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        int64_t k = __shfl_xor_sync(0xFFFFFFFFu, c.key, d);
+        int32_t o = __shfl_xor_sync(0xFFFFFFFFu, c.off, d);
+        if (better(k, o, c.key, c.off)) { c.key = k; c.off = o; }
+    }
+    return c;
+}
+
+template <int THREADS>
+__device__ __forceinline__ Cand block_best(Cand c, Cand* s_part)
+{
+    c = warp_best(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_part[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        Cand v = lane < THREADS / 32 ? s_part[lane] : Cand{ kKeyNone, 0x7FFFFFFF };
+        v = warp_best(v);
+        if (lane == 0) s_part[0] = v;
+    }
+    __syncthreads();
+    return s_part[0];
+}
+
+// Order-preserving map double -> int64 (after -0.0 has been folded into +0.0).
+__device__ __forceinline__ int64_t sortable_from_double(double v)
+{
+    int64_t b = __double_as_longlong(v + 0.0);
+    return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFFll);
+}
+__device__ __forceinline__ double double_from_sortable(int64_t k)
+{
+    return __longlong_as_double(k ^ ((k >> 63) & 0x7FFFFFFFFFFFFFFFll));
+}
+
+// query that owns global tile id `tile` (tile_start is a non-decreasing prefix sum, nq+1 entries)
+__device__ __forceinline__ int query_of_tile(const int32_t* __restrict__ tile_start, int nq, int tile)
+{
+    int lo = 0, hi = nq;            // invariant: tile_start[lo] <= tile < tile_start[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_start[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Exact scalar kernel: one thread per offset, all of Seq2 in ascending i.
+//   EXACT = true : integer sign counts -> int64 fixed-point key
+//   EXACT = false: double accumulated sequentially in i exactly like find_best_mutant_offset
+//                  (cpu_funcs.c:271-299); the key is the goal-signed double mapped to a sortable int64
+// -------------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kExactThreads)
+k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int use_list)
+{
+    __shared__ uint64_t s_tab[kSymbols * kRowPad];
+    __shared__ __align__(16) uint8_t s_win[kExactThreads + kExactChunk];
+    __shared__ __align__(16) uint8_t s_q[kExactChunk];
+    __shared__ double s_w[4];
+    __shared__ Cand s_part[kExactThreads / 32];
+
+    const int tid = threadIdx.x;
+    for (int k = tid; k < kSymbols * kRowPad; k += kExactThreads) {
+        uint32_t code = T.code[k / kRowPad][k % kRowPad];
+        uint32_t cls = code & 3u, rank = code >> 2;
+        uint64_t e = uint64_t(rank) << 60;
+        if (EXACT) { if (cls) e |= 1ull << (20 * (cls - 1)); }
+        else e |= cls;
+        s_tab[k] = e;
+    }
+    if (tid < 4) s_w[tid] = T.wcls[tid];
+    __syncthreads();
+
+    const int nitems = use_list ? *P.cand_count : G.total_tiles;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile_id = use_list ? P.cand_list[item] : item;
+        const int q = query_of_tile(P.tile_start, G.nq, tile_id);
+        const int t = tile_id - P.tile_start[q];
+        const int64_t qbeg = P.qoff[q];
+        const int len2 = int(P.qoff[q + 1] - qbeg);
+        const int64_t first = G.last >= 0 ? G.first : 0;
+        const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
+        const int64_t tb = tile_base(first) + int64_t(t) * G.tile;
+        const int64_t n0 = tb > first ? tb : first;
+        const int64_t n1 = (tb + G.tile) < last ? (tb + G.tile) : last;
+
+        Cand mine{ kKeyNone, 0x7FFFFFFF };
+        for (int64_t sub = n0; sub < n1; sub += kExactThreads) {
+            const int64_t n = sub + tid;
+            const bool valid = n < n1;
+            uint64_t acc = 0;          // EXACT: three 20-bit counts (':' '.' '_')
+            double total = 0.0;        // !EXACT: the reference's running sum
+            uint32_t best_hi = 0;      // rank in bits 28-31
+            for (int c0 = 0; c0 < len2; c0 += kExactChunk) {
+                const int cl = (len2 - c0) < kExactChunk ? (len2 - c0) : kExactChunk;
+                __syncthreads();
+                for (int k = tid; k < cl; k += kExactThreads) {
+                    uint32_t s = symbol_of(P.seq2s[qbeg + c0 + k]);
+                    if (s == 0xFFu) { atomicOr(P.err_flag, 1); s = 0; }
+                    s_q[k] = uint8_t(s);
+                }
+                for (int k = tid; k < kExactThreads + cl - 1; k += kExactThreads) {
+                    const int64_t p = sub + c0 + k;
+                    uint32_t s = 0;
+                    if (p < G.len1) {
+                        s = symbol_of(P.seq1[p]);
+                        if (s == 0xFFu) { atomicOr(P.err_flag, 1); s = 0; }
+                    }
+                    s_win[k] = uint8_t(s);
+                }
+                __syncthreads();
+                if (valid) {
+                    const uint8_t* w = s_win + tid;
+                    if (EXACT) {
+#pragma unroll 4
+                        for (int i = 0; i < cl; i++) {
+                            uint64_t e = s_tab[uint32_t(s_q[i]) * kRowPad + w[i]];
+                            acc += e & 0x0FFFFFFFFFFFFFFFull;
+                            best_hi = max(best_hi, uint32_t(e >> 32));
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = 0; i < cl; i++) {
+                            uint64_t e = s_tab[uint32_t(s_q[i]) * kRowPad + w[i]];
+                            total += s_w[uint32_t(e) & 3u];
+                            best_hi = max(best_hi, uint32_t(e >> 32));
+                        }
+                    }
+                }
+            }
+            if (valid) {
+                const uint32_t rank = best_hi >> 28;
+                int64_t key = kKeyNone;
+                if (rank) {
+                    if (EXACT) {
+                        const int64_t c1 = int64_t(acc & 0xFFFFF), c2 = int64_t((acc >> 20) & 0xFFFFF),
+                                      c3 = int64_t((acc >> 40) & 0xFFFFF);
+                        const int64_t c0n = int64_t(len2) - c1 - c2 - c3;
+                        key = c0n * T.kcls[0] + c1 * T.kcls[1] + c2 * T.kcls[2] + c3 * T.kcls[3] + T.kdiff[rank];
+                    } else {
+                        const double score = total + T.wdiff[rank];       // cpu_funcs.c:299
+                        key = sortable_from_double(T.is_max ? score : -score);
+                    }
+                }
+                if (better(key, int32_t(n), mine.key, mine.off)) { mine.key = key; mine.off = int32_t(n); }
+            }
+        }
+        const Cand win = block_best<kExactThreads>(mine, s_part);
+        if (tid == 0) {
+            TileRec r;
+            r.key = win.key;
+            r.ub_key = kKeyNone;
+            r.score = EXACT ? 0.0 : (win.key == kKeyNone ? 0.0 : (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key));
+            r.offset = win.off;
+            r.ub_offset = 0x7FFFFFFF;
+            r.flags = kTileExact;
+            r.pad = 0;
+            P.tiles[tile_id] = r;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Candidate selection (scan engine only): after the bit-sliced scan every tile holds its best
+// resolved key and the best upper bound of its unresolved offsets.  A tile must be evaluated by the
+// exact kernel iff something in it could still be the reference's winner:
+//   exact mode   : an unresolved offset whose bound reaches the best resolved key
+//   re-score mode: any key or bound within key_slack of the best key
+// -------------------------------------------------------------------------------------------------
+constexpr int kSelectThreads = 128;
+
+__global__ void __launch_bounds__(kSelectThreads)
+k_select(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
+{
+    __shared__ Cand s_part[kSelectThreads / 32];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int t0 = P.tile_start[q], t1 = P.tile_start[q + 1];
+    Cand mine{ kKeyNone, 0x7FFFFFFF };
+    for (int t = t0 + tid; t < t1; t += kSelectThreads) {
+        const TileRec r = P.tiles[t];
+        // in re-score mode bounds count too: they are valid upper estimates of real keys only, so the
+        // threshold must come from resolved keys (a lower bound of the true best)
+        if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
+    }
+    const Cand best = block_best<kSelectThreads>(mine, s_part);
+    for (int t = t0 + tid; t < t1; t += kSelectThreads) {
+        const TileRec r = P.tiles[t];
+        bool need;
+        if (T.exact) {
+            need = r.ub_key != kKeyNone && !better(best.key, best.off, r.ub_key, r.ub_offset);
+        } else {
+            const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
+            // best.key - slack cannot underflow: |key| < 2^61
+            need = top != kKeyNone && (best.key == kKeyNone || top >= best.key - T.key_slack);
+        }
+        if (need) P.cand_list[atomicAdd(P.cand_count, 1)] = t;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Finalisation: per query, the winning tile record, then one pass over the winning alignment for
+// the sign counts, the first position carrying the best rank (cpu_funcs.c:287-294: strict compare,
+// so the lowest i wins ties) and its replacement letter.
+// -------------------------------------------------------------------------------------------------
+constexpr int kFinalThreads = 128;
+
+__global__ void __launch_bounds__(kFinalThreads)
+k_final(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
+{
+    __shared__ Cand s_part[kFinalThreads / 32];
+    __shared__ unsigned long long s_pos;
+    __shared__ int s_cnt[4];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int t0 = P.tile_start[q], t1 = P.tile_start[q + 1];
+    Cand mine{ kKeyNone, 0x7FFFFFFF };
+    for (int t = t0 + tid; t < t1; t += kFinalThreads) {
+        const TileRec r = P.tiles[t];
+        if (!T.exact && !(r.flags & kTileExact)) continue;   // only reference-order doubles may compete
+        if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
+    }
+    const Cand win = block_best<kFinalThreads>(mine, s_part);
+
+    QueryRec out;
+    out.key = win.key; out.score = 0.0;
+    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
+    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
+    if (win.key == kKeyNone) {            // no mutation possible at any offset (never seen in practice)
+        if (tid == 0) P.out[q] = out;
+        return;
+    }
+    if (tid == 0) s_pos = 0ull;
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+
+    const int64_t qbeg = P.qoff[q];
+    const int len2 = int(P.qoff[q + 1] - qbeg);
+    const uint8_t* a = P.seq1 + win.off;
+    const uint8_t* b = P.seq2s + qbeg;
+    int cnt[4] = { 0, 0, 0, 0 };
+    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
+    for (int i = tid; i < len2; i += kFinalThreads) {
+        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }      // flagged by the kernels before us
+        const uint32_t code = T.code[c2][c1];
+        cnt[code & 3u]++;
+        const unsigned long long p = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
+        pos = p > pos ? p : pos;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
+        pos = o > pos ? o : pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
+    }
+    if ((tid & 31) == 0) {
+        atomicMax(&s_pos, pos);
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int rank = int(s_pos >> 32);
+        const int i = int(~uint32_t(s_pos));
+        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        out.offset = win.off;
+        out.char_offset = i;
+        out.ch = T.sub[c2][c1];
+        out.rank = rank;
+        for (int c = 0; c < 4; c++) out.counts[c] = s_cnt[c];
+        if (!T.exact) out.score = (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key);
+        P.out[q] = out;
+    }
+}
+
+} // namespace
+
+void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool cand, int sm_count,
+                        cudaStream_t stream)
+{
+    int grid = cand ? sm_count * 4 : G.total_tiles;
+    if (grid < 1) return;
+    if (T.exact) k_exact_tiles<true><<<grid, kExactThreads, 0, stream>>>(T, G, P, cand ? 1 : 0);
+    else k_exact_tiles<false><<<grid, kExactThreads, 0, stream>>>(T, G, P, cand ? 1 : 0);
+}
+
+void launch_select(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
+{
+    if (G.nq < 1) return;
+    k_select<<<G.nq, kSelectThreads, 0, stream>>>(T, G, P);
+}
+
+void launch_final(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
+{
+    if (G.nq < 1) return;
+    k_final<<<G.nq, kFinalThreads, 0, stream>>>(T, G, P);
+}
+
+} // namespace psa

@@ -1,0 +1,56 @@
+// psa_kernels.cuh -- device-side contract between the engine and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "psa_common.h"
+
+namespace psa {
+
+// Device pointers of one batch on one GPU.
+struct BatchPtrs {
+    const uint8_t* seq1;        // ASCII, len1 bytes (+ padding readable up to seq1_alloc)
+    const uint8_t* seq2s;       // ASCII, all queries concatenated
+    const int64_t* qoff;        // nq+1 byte offsets into seq2s
+    const int32_t* tile_start;  // nq+1 prefix sum of tiles per query
+    TileRec*       tiles;       // total_tiles records
+    QueryRec*      out;         // nq records
+    int32_t*       cand_list;   // tile ids that must be evaluated by the exact kernel
+    int32_t*       cand_count;  // [0] = number of entries in cand_list
+    int32_t*       err_flag;    // bit0: symbol outside [A-Z-]
+    // bit-plane profile of Seq1 (scan engine): [row][word] of 64-bit (class planes) and
+    // [row][word][rank_planes] of 32-bit words; rows = 28 (27 symbols + zero row)
+    uint2*         cls_planes;
+    uint32_t*      rank_planes;
+    int64_t        plane_words; // words per row
+};
+
+// Offsets of a query are tiled from `base` = first rounded down to a multiple of 32 so that bit-plane
+// words line up; a tile covers [base + t*tile, base + (t+1)*tile) intersected with [first, last).
+__host__ __device__ inline int64_t tile_base(int64_t first) { return first & ~int64_t(31); }
+
+// ---- launchers (all asynchronous on `stream`) -------------------------------------------------
+// exact scalar kernel over every tile (cand == false) or over the candidate list (cand == true)
+void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool cand, int sm_count,
+                        cudaStream_t stream);
+// per-query winner + char_offset + counts
+void launch_final(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
+// bit-plane profile of Seq1 for the scan engine
+void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
+                    cudaStream_t stream);
+// bit-sliced scan of every tile
+void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
+                 cudaStream_t stream);
+// per-query candidate selection between scan and exact
+void launch_select(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
+
+// scan engine limits
+constexpr int kDefaultEngine = 1;                   // engine picked by "auto" (1 scalar, 2 bit-sliced scan)
+constexpr int kScanWarps = 4;                       // warps per block
+constexpr int kScanTile = kScanWarps * 1024;        // offsets per tile (32 lanes x 32 offsets per warp)
+constexpr int kScanMaxLen2 = 32767;                 // 15 counter planes
+constexpr int kExactTile = 256;                     // tile of the scalar engine when used alone
+constexpr int64_t kExactMaxLen2 = (1 << 20) - 1;    // 20-bit count fields
+
+int scan_chunk_steps(int rank_planes, int64_t max_len2);   // i-steps staged per shared-memory window
+size_t scan_smem_bytes(int rank_planes, int chunk);
+
+} // namespace psa

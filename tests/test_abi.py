@@ -1,0 +1,115 @@
+"""The C ABI: the library loads, exports every symbol include/psa_b200.h declares (plus the
+reference's C++-mangled entry point), has the reference's record layouts, reads and writes the
+reference's file formats, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "psa_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(psa_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(psa):
+    names = declared_functions()
+    assert len(names) >= 20
+    lib = C.CDLL(psa.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/psa_b200.h but not exported"
+
+
+def test_reference_mangled_entry_point(psa):
+    """cpu_funcs.c (built as C++) imports _Z15gpu_run_programP5_dataP7_mutantii (cuda_funcs.h:33)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", psa.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert re.search(r" T _Z15gpu_run_programP5_dataP7_mutantii$", out, flags=re.M)
+    assert re.search(r" T psa_gpu_run_program$", out, flags=re.M)
+
+
+def test_library_contains_sm100a_code_only(psa):
+    out = subprocess.run(["cuobjdump", "-lelf", psa.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_record_layouts(psa):
+    assert C.sizeof(psa.ProgramData) == 15048           # program_data.h:6-11
+    assert psa.ProgramData.weights.offset == 8 and psa.ProgramData.seq1.offset == 40
+    assert psa.ProgramData.seq2.offset == 10041
+    assert C.sizeof(psa.Mutant) == 12 and psa.Mutant.ch.offset == 8     # mutant.h:6-10
+    assert psa.abi_version() == 1
+
+
+def test_layouts_agree_with_reference_build(psa, ref):
+    assert ref.lib.ref_sizeof_program_data() == C.sizeof(psa.ProgramData)
+    assert ref.lib.ref_sizeof_mutant() == C.sizeof(psa.Mutant)
+
+
+def test_input_output_formats(psa, tmp_path, input_blocks):
+    b = input_blocks[1]
+    p = tmp_path / "input.txt"
+    p.write_text("  ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n\n1 1 1 1\nAAA\nA\nminimum\n")
+    w, is_max, s1, s2 = psa.read_seq_and_weights_from_file(str(p))
+    assert (w, is_max, s1, s2) == (b["weights"], True, b["seq1"], b["seq2"])
+    p.write_text("1 2 3 4 ABC AB maximal")                 # anything but "maximum" is a minimum
+    assert psa.read_seq_and_weights_from_file(str(p)) == ([1, 2, 3, 4], False, "ABC", "AB")
+    for broken in ("1 2 3", "1 2 3 4 ABC", "x 2 3 4 A B maximum"):
+        p.write_text(broken)
+        with pytest.raises(psa.PsaError) as e:
+            psa.read_seq_and_weights_from_file(str(p))
+        assert e.value.status == psa.PSA_ERR_IO
+    with pytest.raises(psa.PsaError):
+        psa.read_seq_and_weights_from_file(str(tmp_path / "missing.txt"))
+    o = tmp_path / "output.txt"
+    psa.write_results_to_file(str(o), "HELLO", 4505, -4879.0)
+    assert o.read_bytes() == b"HELLO\n4505 -4879"           # "%s\n%d %g", no trailing newline
+    psa.write_results_to_file(str(o), "X", 21, 41.7)
+    assert o.read_bytes() == b"X\n21 41.7"
+    psa.write_results_to_file(str(o), "X", 9, -191.79999999999998)
+    assert o.read_bytes() == b"X\n9 -191.8"
+
+
+def test_io_matches_reference_io(psa, ref, tmp_path, input_blocks):
+    b = input_blocks[3]
+    p = tmp_path / "input.txt"
+    p.write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"])
+    w = (C.c_double * 4)()
+    mx = C.c_int()
+    s1, s2 = C.create_string_buffer(10001), C.create_string_buffer(5001)
+    assert ref.lib.ref_read_input(str(p).encode(), w, C.byref(mx), s1, s2) == 0
+    assert psa.read_seq_and_weights_from_file(str(p)) == (list(w), bool(mx.value), s1.value.decode(), s2.value.decode())
+    for score in (-4879.0, 30.9, 1e21, -0.000123456789, 5.0):
+        ref.lib.ref_write_output(str(tmp_path / "r.txt").encode(), b"MUTANT", 17, score)
+        psa.write_results_to_file(str(tmp_path / "o.txt"), "MUTANT", 17, score)
+        assert (tmp_path / "r.txt").read_bytes() == (tmp_path / "o.txt").read_bytes()
+
+
+def test_no_cpu_fallback(psa):
+    """On a host without a B200 the product must fail loudly, not compute on the CPU."""
+    if psa.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(psa.PsaError) as e:
+        psa.Context(1)
+    assert e.value.status == psa.PSA_ERR_CUDA
+
+
+def test_product_does_not_link_the_oracle(psa):
+    out = subprocess.run(["ldd", psa.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "psa_ref" not in out
+    syms = subprocess.run(["nm", "-D", psa.LIB_PATH], capture_output=True, text=True).stdout
+    assert "psa_oracle" not in syms and "ref_search" not in syms
+    src = os.path.join(ROOT, "parallel-sequence-alignment_b200")
+    for dirpath, _, files in os.walk(src):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "oracle/" not in text and "psa_oracle" not in text, f

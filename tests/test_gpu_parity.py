@@ -1,0 +1,201 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (run with -m gpu on a B200).
+
+Bit-exact bar: offset, char_offset, substitute letter and the score double must equal the
+oracle's (== the reference's 1-thread CPU path, see tests/test_oracle.py)."""
+import random
+
+import pytest
+
+from conftest import same_answer
+
+pytestmark = pytest.mark.gpu
+ALPHA = [chr(65 + i) for i in range(26)] + ["-"]
+ENGINES = [1, 2]
+
+
+def _set_engine(ctx, engine, planes=-1):
+    ctx.set_option("engine", engine)
+    ctx.set_option("rank_planes", planes)
+
+
+@pytest.fixture(params=ENGINES, ids=["scalar", "scan"])
+def engine(request, ctx):
+    _set_engine(ctx, request.param)
+    yield request.param
+    _set_engine(ctx, 0)
+
+
+def test_library_is_native_and_gpu_visible(psa):
+    assert psa.device_count() >= 1
+
+
+def test_input_blocks(ctx, engine, input_blocks):
+    """The 10 problems of the reference's input.txt (block 0 is pinned by its output.txt)."""
+    for b in input_blocks:
+        r = ctx.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"])
+        assert same_answer(r, b["expect"]), (b["weights_text"], r)
+        assert "%g" % r.score == b["expect"]["score_g"]
+    b = input_blocks[0]
+    r = ctx.search(b["weights"], False, b["seq1"], b["seq2"])
+    assert r.mutant(b["seq2"]) + "\n%d %g" % (r.offset, r.score) == b["output_txt"]
+
+
+def test_synthetic_golden(ctx, engine, synthetic_cases):
+    for c in synthetic_cases:
+        r = ctx.search(c["weights"], c["is_max"], c["seq1"], c["seq2"])
+        assert same_answer(r, c["expect"]), (c["tag"], c["weights"], c["is_max"], r, c["expect"])
+
+
+def test_counts_and_rank_reported(ctx, engine, port, input_blocks):
+    b = input_blocks[0]
+    r = ctx.search(b["weights"], False, b["seq1"], b["seq2"])
+    o = port.search(b["weights"], False, b["seq1"], b["seq2"])
+    assert r.counts == o.counts == (60, 312, 240, 1519) and sum(r.counts) == len(b["seq2"])
+
+
+@pytest.mark.parametrize("w", [[1, 1, 1, 1], [1, 3, 4, 2], [2, 1.5, 1.1, 1.3], [1.5, 2.6, 0.1, 0.2], [0.8, 0.54, 2.6, 13.7]])
+def test_config2_tie_breaking(ctx, engine, port, synth, w):
+    """BASELINE config 2: 3000/2000, MIN (and MAX), tie-rich integer weights and FP weights."""
+    wl = synth.workload("c2", weights=w)
+    for is_max in (False, True):
+        r = ctx.search(w, is_max, wl.seq1, wl.queries[0])
+        assert same_answer(r, port.search(w, is_max, wl.seq1, wl.queries[0]))
+
+
+def test_planted_exact_ties(ctx, engine, port, synth):
+    """Seq2 planted at several offsets: equal best scores, the lowest offset must win."""
+    core = synth.letters(77, 400)
+    s1 = synth.letters(78, 1500) + core + synth.letters(79, 900) + core + synth.letters(80, 5000) + core
+    for w in ([1, 3, 4, 2], [1.5, 2.6, 0.1, 0.2]):
+        for is_max in (True, False):
+            r = ctx.search(w, is_max, s1, core)
+            assert same_answer(r, port.search(w, is_max, s1, core))
+            if is_max:
+                assert r.offset == 1500
+
+
+def test_random_shapes(ctx, engine, port):
+    rng = random.Random(99)
+    wsets = [[1, 3, 4, 2], [1, 1, 1, 1], [2, 1.5, 1.1, 1.3], [0.1, 0.7, 0.3, 0.9], [7, 0, 2, 0.5], [0, 0, 0, 0]]
+    for trial in range(120):
+        w = rng.choice(wsets)
+        is_max = trial % 2
+        n1 = rng.choice([1, 2, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 4095, 4097, rng.randint(1, 9000)])
+        n2 = rng.choice([1, n1, max(1, n1 - 1), rng.randint(1, n1), rng.randint(1, min(n1, 70))])
+        alpha = ALPHA if trial % 5 == 0 else ALPHA[:26] if trial % 3 else "ACDG"
+        s1 = "".join(rng.choice(alpha) for _ in range(n1))
+        s2 = "".join(rng.choice(alpha) for _ in range(n2))
+        r = ctx.search(w, is_max, s1, s2)
+        assert same_answer(r, port.search(w, is_max, s1, s2)), (trial, w, is_max, n1, n2)
+
+
+def test_ragged_batch(ctx, engine, port, synth):
+    """Queries of very different lengths in one batch, incl. len2 == len1 and len2 == 1."""
+    s1 = synth.letters(5, 5000)
+    lens = [1, 2, 31, 32, 33, 64, 500, 777, 1024, 2047, 4999, 5000, 3, 64, 64, 1999]
+    qs = [synth.letters(100 + k, n) for k, n in enumerate(lens)]
+    for w, is_max in (([1, 3, 4, 2], False), ([1.5, 2.6, 0.1, 0.2], True)):
+        got = ctx.search_batch(w, is_max, s1, qs)
+        exp = port.search_batch(w, is_max, s1, qs)
+        for k, (g, e) in enumerate(zip(got, exp)):
+            assert same_answer(g, e), (k, lens[k], g, e)
+            assert g.counts == e.counts
+    assert ctx.search_batch([1, 1, 1, 1], True, s1, []) == []
+
+
+def test_offset_ranges(ctx, engine, port, synth):
+    """psa_search_range == the reference's [first,last) contract of gpu_run_program."""
+    s1, s2 = synth.letters(8, 7000), synth.letters(9, 300)
+    for w in ([1, 3, 4, 2], [2, 1.5, 1.1, 1.3]):
+        for (f, l) in ((0, 6701), (0, 1), (6700, 6701), (17, 4113), (4096, 4097), (31, 33), (1000, 6000)):
+            for is_max in (True, False):
+                r = ctx.search_range(w, is_max, s1, s2, f, l)
+                assert same_answer(r, port.search(w, is_max, s1, s2, f, l)), (w, f, l, is_max)
+
+
+def test_gpu_run_program_dropin(psa, port, input_blocks):
+    """The reference entry point (cuda_funcs.h:33) on the reference's own records."""
+    for b in input_blocks[:4]:
+        is_max = b["goal"] == "maximum"
+        d = psa.make_program_data(b["weights"], is_max, b["seq1"], b["seq2"])
+        total = len(b["seq1"]) - len(b["seq2"]) + 1
+        score, m = psa.gpu_run_program(d, 0, total)
+        e = b["expect"]
+        assert (score, m.offset, m.char_offset, m.ch.decode()) == (e["score"], e["offset"], e["char_offset"], e["ch"])
+        # two "ranks" splitting the offsets like cpu_funcs.c:128-133, merged with MAXLOC/MINLOC (ties -> rank 0)
+        half = total // 2
+        if half:
+            s0, m0 = psa.gpu_run_program(d, 0, half)
+            s1_, m1 = psa.gpu_run_program(d, half, total)
+            win = (s1_, m1) if ((s1_ > s0) if is_max else (s1_ < s0)) else (s0, m0)
+            assert (win[0], win[1].offset, win[1].char_offset) == (e["score"], e["offset"], e["char_offset"])
+
+
+def test_rejects_bad_input(psa, ctx):
+    with pytest.raises(psa.PsaError) as e:
+        ctx.search([1, 1, 1, 1], True, "ABCDEFGH", "ABc")
+    assert e.value.status == psa.PSA_ERR_ALPHABET
+    with pytest.raises(psa.PsaError) as e:
+        ctx.search([1, 1, 1, 1], True, "ABC*EFGH", "ABC")
+    assert e.value.status == psa.PSA_ERR_ALPHABET
+    with pytest.raises(psa.PsaError) as e:
+        ctx.search([1, 1, 1, 1], True, "AB", "ABC")
+    assert e.value.status == psa.PSA_ERR_ARG
+    with pytest.raises(psa.PsaError) as e:
+        ctx.search([1, float("nan"), 1, 1], True, "ABC", "AB")
+    assert e.value.status == psa.PSA_ERR_WEIGHTS
+    assert ctx.search([1, 1, 1, 1], True, "ABCDEFGH", "ABC").offset == 0      # context still usable
+
+
+def test_run_files_and_cli(psa, ctx, tmp_path, input_blocks):
+    import subprocess
+    b = input_blocks[0]
+    (tmp_path / "input.txt").write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n")
+    r = ctx.run_files(str(tmp_path / "input.txt"), str(tmp_path / "out_api.txt"))
+    assert (tmp_path / "out_api.txt").read_text() == b["output_txt"] and r.offset == 4505
+    p = subprocess.run([psa.CLI_PATH], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert (tmp_path / "output.txt").read_text() == b["output_txt"]
+    assert "CUDA percentage set to 100" in p.stdout and "total time:" in p.stdout
+
+
+def test_config3_sample_and_full_properties(ctx, port, synth):
+    """BASELINE config 3 (1024 x 500 vs 3000, MAX): a 64-query sample bit-exact against the oracle,
+    the full batch through size-independent properties."""
+    _set_engine(ctx, 0)
+    wl = synth.workload("c3")
+    got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:64])
+    for g, e in zip(got, exp):
+        assert same_answer(g, e)
+    for q, g in zip(wl.queries, got):
+        assert 0 <= g.offset <= 2500 and 0 <= g.char_offset < 500 and sum(g.counts) == 500
+        n = port.offset_naive(wl.weights, wl.is_max, wl.seq1, q, g.offset)       # the reported score is the true score there
+        assert (n.score, n.char_offset, n.ch, n.counts) == (g.score, g.char_offset, g.ch, g.counts)
+    # batching must be invisible: same answers one query at a time and in reverse order
+    again = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[::-1][:50])
+    assert [(a.offset, a.score) for a in again] == [(g.offset, g.score) for g in got[::-1][:50]]
+
+
+def test_config5_sample_and_properties(ctx, port, synth):
+    """BASELINE config 5 (65536 x 64 vs 10000, MIN): 4096-query slice; 256 bit-exact vs the oracle."""
+    _set_engine(ctx, 0)
+    wl = synth.workload("c5", nq=4096)
+    got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:256])
+    for g, e in zip(got, exp):
+        assert same_answer(g, e)
+    for q, g in list(zip(wl.queries, got))[::16]:
+        n = port.offset_naive(wl.weights, wl.is_max, wl.seq1, q, g.offset)
+        assert (n.score, n.char_offset, n.ch) == (g.score, g.char_offset, g.ch)
+
+
+def test_config4_long_seq1(ctx, port, synth):
+    """BASELINE config 4 (len1 = 1e6, len2 = 2000, non-dyadic weights): beyond the reference's static
+    capacity, so the checker is the oracle port (multi-threaded)."""
+    _set_engine(ctx, 0)
+    wl = synth.workload("c4")
+    r = ctx.search(wl.weights, wl.is_max, wl.seq1, wl.queries[0])
+    assert same_answer(r, port.search(wl.weights, wl.is_max, wl.seq1, wl.queries[0], nthreads=8))
+    r2 = ctx.search([1, 3, 4, 2], False, wl.seq1, wl.queries[0])
+    assert same_answer(r2, port.search([1, 3, 4, 2], False, wl.seq1, wl.queries[0], nthreads=8))
