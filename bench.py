@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- pair-evals/s of the mutant-offset search on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c5|c4|c2|c1] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic queries of the named BASELINE.json
+shape.  Weak scaling: every rank owns a full batch (different seed per rank), no data-path collective;
+`value` = pair-evals of all ranks / max-over-ranks device time.
+
+  value      batch resident in HBM (psa_batch_prepare), per-step device time from CUDA events recorded
+             by the library on the stream it launches on (psa_batch_run), L2 flushed between steps
+  e2e        the public call psa_search_batch with HOST (pinned) buffers: H2D + kernels + D2H + host
+             scoring, wall clock per step
+  roofline   the dominant kernel alone (its own CUDA events) against the integer-issue roofline of
+             SURVEY.md section 8(d); HBM is shown to be non-binding
+  cpu_baseline / --impl reference
+             the reference's own CPU loop (oracle/_ref, compiled from /root/reference) on a bounded
+             sample of the same workload, all host threads
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "parallel-sequence-alignment_b200"
+
+METRIC = "pair-evals/sec"
+UNIT = "pair-evals/s"
+# 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM issue, 148 SMs at the measured max SM clock
+SM_COUNT = 148
+LANE_OPS_PER_PAIR_EVAL = 2.0
+HBM_BYTES_PER_QUERY_FIXED = 48 + 8 + 4      # result record + offsets
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def golden_c1():
+    with open(os.path.join(ROOT, "tests", "golden", "input_blocks.json")) as f:
+        b = json.load(f)[0]
+    return b["weights"], b["goal"] == "maximum", b["seq1"].encode(), [b["seq2"].encode()]
+
+
+def make_workload(synth, name, rank, nq=None):
+    if name == "c1":
+        w, is_max, s1, qs = golden_c1()
+        return synth.Workload("c1", w, is_max, s1, qs, "reference input.txt block 1 (9711/2131 MIN)")
+    return synth.workload(name, nq=nq, seed_shift=1000 * rank)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU loop on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def reference_sample(synth, name, seconds=12.0):
+    """Pick a sample (number of queries) of workload `name` worth ~`seconds` of reference CPU time."""
+    import oracle
+    threads = os.cpu_count() or 1
+    kind = "reference" if oracle.ref_available() else "port"
+    eng = oracle.Ref() if kind == "reference" else oracle.Port()
+    wl = make_workload(synth, name, 0, nq=None if name in ("c1", "c2", "c4") else (1024 if name == "c3" else 8192))
+    seq1 = wl.seq1
+    cap_note = ""
+    if kind == "reference" and len(seq1) > eng.cap1:          # c4: beyond the reference's static buffers
+        seq1 = seq1[: eng.cap1]
+        cap_note = f" (Seq1 truncated to the reference's capacity {eng.cap1})"
+
+    def run(queries):
+        t0 = time.perf_counter()
+        for q in queries:
+            if kind == "reference":
+                eng.search_omp(wl.weights, wl.is_max, seq1, q, threads)
+            else:
+                eng.search(wl.weights, wl.is_max, seq1, q, nthreads=threads)
+        return time.perf_counter() - t0
+
+    pe = lambda qs: sum((len(seq1) - len(q) + 1) * len(q) for q in qs)
+    probe = wl.queries[:1]
+    dt = max(run(probe), 1e-4)
+    n = max(1, min(len(wl.queries), int(seconds / dt)))
+    sample = wl.queries[:n]
+    return {"kind": kind, "threads": threads, "run": run, "sample": sample, "pair_evals": pe(sample),
+            "desc": f"{n} of the workload's queries, {kind} find_best_mutant_cpu split over {threads} threads "
+                    f"(-O3 build, table filled single-threaded){cap_note}", "wl": wl}
+
+
+def run_reference_arm(args, synth, rank, world):
+    if rank != 0:
+        return
+    s = reference_sample(synth, args.workload, seconds=max(2.0, 40.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        s["run"](s["sample"])
+    t = 0.0
+    for _ in range(args.steps):
+        t += s["run"](s["sample"])
+    value = s["pair_evals"] * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, s["wl"]), "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": s["threads"], "kind": s["kind"], "sample": s["desc"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+FULL_NOTE = {"c1": "reference input.txt block 1 (9711/2131 MIN)", "c2": "single pair len1=3000 len2=2000 MIN",
+             "c3": "1024 queries len2=500 vs len1=3000 MAX", "c4": "len1=1000000 len2=2000 MAX",
+             "c5": "65536 queries len2=64 vs len1=10000 MIN"}
+
+
+def workload_name(name, wl):
+    return f"{name}: {FULL_NOTE[name]}, weights {wl.weights}, uniform A-Z (splitmix64)"
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, synth, rank, local_rank, world):
+    import torch
+    psa = importlib.import_module(PKG)
+    if not torch.cuda.is_available() or psa.device_count() < 1:
+        raise SystemExit("bench.py: no B200 visible; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peaks = load_peaks()
+    wl = make_workload(synth, args.workload, rank)
+    ctx = psa.Context(devices=[local_rank])
+    if args.engine:
+        ctx.set_option("engine", args.engine)
+    batch = psa.Batch(wl.seq1, wl.queries, pinned=True)
+    pair_evals = batch.pair_evals
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- value: resident batch, device time --------------------------------------------------------
+    ctx.prepare(wl.weights, wl.is_max, batch)
+    for _ in range(args.warmup):
+        flush_l2()
+        ctx.run()
+    results = ctx.fetch()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms, main_ns, launches = 0.0, 0, 0
+    for _ in range(args.steps):
+        flush_l2()
+        dev_ms += ctx.run()
+        main_ns += ctx.stat("main_kernel_ns")
+        launches += ctx.stat("kernel_launches")
+    barrier()
+    dev_ms_max = max_over_ranks(dev_ms)
+    total_pe = sum_over_ranks(float(pair_evals))
+
+    # ---- e2e: host buffers through the public call -------------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        ctx.search_batch(wl.weights, wl.is_max, None, batch=batch)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        r2 = ctx.search_batch(wl.weights, wl.is_max, None, batch=batch)
+        e2e_s += time.perf_counter() - t0
+        launches += ctx.stat("kernel_launches")
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_s_max = max_over_ranks(e2e_s)
+    assert [(a.offset, a.char_offset, a.score) for a in r2] == [(a.offset, a.char_offset, a.score) for a in results]
+
+    if rank == 0:
+        value = total_pe * args.steps / (dev_ms_max * 1e-3)
+        e2e_value = total_pe * args.steps / e2e_s_max
+        # roofline of the dominant kernel on this rank (its own events), per GPU
+        k_s = main_ns * 1e-9 / args.steps
+        achieved = pair_evals / k_s if k_s > 0 else 0.0
+        clk = peaks["sm_max_mhz"] * 1e6
+        peak = SM_COUNT * 128 * clk / LANE_OPS_PER_PAIR_EVAL
+        alg_bytes = batch.len1 + sum(batch.lens) + batch.nq * HBM_BYTES_PER_QUERY_FIXED
+        engine = ctx.stat("engine")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, wl), "pair_evals_per_gpu_step": pair_evals,
+                       "l2": "flushed between timed steps (512 MiB write)", "engine": {1: "scalar", 2: "bitsliced-scan"}.get(engine, engine),
+                       "exact_integer_keys": bool(ctx.stat("exact")), "sharding": "one full batch per rank, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes,
+                    "d2h_bytes_per_step": 48 * batch.nq + 16, "ms_per_step": 1e3 * e2e_s_max / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "int-issue", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
+                         "traffic": None,
+                         "kernel": "k_scan" if engine == 2 else "k_exact_tiles", "kernel_ms": k_s * 1e3,
+                         "kernel_share_of_step": (main_ns * 1e-6) / dev_ms if dev_ms else None,
+                         "model": "SURVEY 8(d): 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM x 148 SMs x "
+                                  f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} clock); not HBM, not tensor",
+                         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / k_s / 1e9 if k_s else 0.0,
+                                 "peak_gbs": peaks["hbm_gbs"], "frac": (alg_bytes / k_s / 1e9) / peaks["hbm_gbs"] if k_s else 0.0,
+                                 "peak_source": peaks["source"]}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            s = reference_sample(synth, args.workload, seconds=args.cpu_seconds)
+            t = s["run"](s["sample"])
+            line["cpu_baseline"] = {"value": s["pair_evals"] / t, "unit": UNIT, "cores": s["threads"], "kind": s["kind"],
+                                    "sample": s["desc"], "seconds": t}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 scalar, 2 bit-sliced scan")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, local_rank, world = dist_env()
+    synth = importlib.import_module(PKG + ".synth")
+    if args.impl == "reference":
+        run_reference_arm(args, synth, rank, world)
+    else:
+        run_ours(args, synth, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,7 +43,7 @@ struct DeviceState {
     int dev = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
     DevBuf seq1, seq2s, qoff, tile_start, tiles, out, cand_list, flags, cls_planes, rank_planes;
     PinBuf h_qoff, h_tile_start, h_out, h_flags;
     // slice of the current batch owned by this GPU
@@ -61,6 +61,7 @@ struct psa_context {
     // options
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
+    int opt_scan_warps = 0;    // 0 auto, 1..4
     // current batch
     bool prepared = false, ran = false;
     bool range_split = false;  // single query split by offset range over the GPUs
@@ -70,10 +71,11 @@ struct psa_context {
     int nq = 0;
     int engine = 1;
     int rank_planes = 0;
+    int scan_tile = kScanTile;   // offsets per scan tile = 1024 x warps per block
     int64_t max_len2 = 0;
     std::vector<int64_t> len2s;
     // stats of the last run
-    long long st_launches = 0, st_cand = 0, st_tiles = 0;
+    long long st_launches = 0, st_cand = 0, st_tiles = 0, st_main_ns = 0;
 };
 
 namespace {
@@ -129,6 +131,8 @@ void release(DeviceState& d)
         if (b->p) cudaFreeHost(b->p);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.evk0) cudaEventDestroy(d.evk0);
+    if (d.evk1) cudaEventDestroy(d.evk1);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -154,7 +158,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     if (!d.active) return PSA_OK;
 
     const bool scan = ctx->engine == 2;
-    const int tile = scan ? kScanTile : kExactTile;
+    const int tile = scan ? ctx->scan_tile : kExactTile;
     int rc;
     if ((rc = ensure_pin(ctx, d.h_qoff, sizeof(int64_t) * (nq + 1)))) return rc;
     if ((rc = ensure_pin(ctx, d.h_tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
@@ -227,12 +231,16 @@ int run_device(psa_context* ctx, DeviceState& d)
     PSA_CUDA(ctx, cudaMemsetAsync(d.flags.p, 0, sizeof(int32_t) * 4, d.stream));
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
+        PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, d.stream);
+        PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         launch_select(ctx->table, d.G, d.P, d.stream);
         launch_exact_tiles(ctx->table, d.G, d.P, true, d.sm_count, d.stream);
         ctx->st_launches += 4;
     } else {
+        PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_exact_tiles(ctx->table, d.G, d.P, false, d.sm_count, d.stream);
+        PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 1;
     }
     launch_final(ctx->table, d.G, d.P, d.stream);
@@ -329,7 +337,8 @@ int psa_create(psa_context** out, const int* devices, int ndevices)
             cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d.dev) != cudaSuccess || major != 10 ||
             cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
+            cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
+            cudaEventCreate(&d.evk0) != cudaSuccess || cudaEventCreate(&d.evk1) != cudaSuccess) {
             cudaGetLastError();
             for (DeviceState& x : ctx->devs) release(x);
             delete ctx;
@@ -358,6 +367,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
     return PSA_ERR_ARG;
 }
 
@@ -367,8 +377,10 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "kernel_launches")) return ctx->st_launches;
     if (!std::strcmp(name, "candidate_tiles")) return ctx->st_cand;
     if (!std::strcmp(name, "tiles")) return ctx->st_tiles;
+    if (!std::strcmp(name, "main_kernel_ns")) return ctx->st_main_ns;   // dominant kernel of the last psa_batch_run
     if (!std::strcmp(name, "engine")) return ctx->engine;
     if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
+    if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
     if (!std::strcmp(name, "exact")) return ctx->table.exact;
     return -1;
 }
@@ -402,6 +414,20 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
     ctx->engine = ctx->opt_engine ? ctx->opt_engine : kDefaultEngine;
     if (ctx->engine == 2 && max_len2 > kScanMaxLen2) ctx->engine = 1;
     ctx->rank_planes = ctx->engine == 2 ? pick_rank_planes(ctx) : 0;
+    if (ctx->engine == 2) {
+        // warps per block (1024 offsets each): the count that wastes the fewest idle warp-tiles, larger on ties
+        double best_cost = 0;
+        int best_w = kScanWarps;
+        for (int w = kScanWarps; w >= 1; w--) {
+            double cost = 0;
+            for (int q = 0; q < nq; q++) {
+                const int64_t n = last >= 0 ? last - tile_base(first) : offsets_of(len1, ctx->len2s[q]);
+                cost += double((n + 1024 * w - 1) / (1024 * w)) * w;
+            }
+            if (w == kScanWarps || cost < best_cost) { best_cost = cost; best_w = w; }
+        }
+        ctx->scan_tile = ctx->opt_scan_warps > 0 ? 1024 * ctx->opt_scan_warps : 1024 * best_w;
+    }
 
     const int ndev = (int)ctx->devs.size();
     ctx->range_split = false;
@@ -412,7 +438,7 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
         // one query: contiguous offset ranges per GPU (cpu_funcs.c:128-133 with GPUs as ranks),
         // rounded to whole tiles so no GPU gets a sliver
         const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, max_len2);
-        const int64_t tile = ctx->engine == 2 ? kScanTile : kExactTile;
+        const int64_t tile = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
         const int64_t ntiles = (l - tile_base(f) + tile - 1) / tile;
         const int use = (int)std::min<int64_t>(ndev, ntiles);
         ctx->range_split = use > 1;
@@ -458,7 +484,7 @@ int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, con
 static int run_async(psa_context* ctx)
 {
     if (!ctx || !ctx->prepared) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch prepared") : PSA_ERR_ARG;
-    ctx->st_launches = ctx->st_cand = ctx->st_tiles = 0;
+    ctx->st_launches = ctx->st_cand = ctx->st_tiles = ctx->st_main_ns = 0;
     for (DeviceState& d : ctx->devs) {
         int rc = run_device(ctx, d);
         if (rc) return rc;
@@ -479,6 +505,9 @@ int psa_batch_run(psa_context* ctx, float* device_ms)
         float ms = 0.f;
         PSA_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         worst = std::max(worst, ms);
+        float kms = 0.f;
+        PSA_CUDA(ctx, cudaEventElapsedTime(&kms, d.evk0, d.evk1));
+        ctx->st_main_ns = std::max(ctx->st_main_ns, (long long)(kms * 1e6));
     }
     if (device_ms) *device_ms = worst;
     return PSA_OK;

@@ -13,6 +13,7 @@
 //     accumulated in the reference's CPU order (cpu_funcs.c:271-299) so the winner is the CPU
 //     reference's winner.
 #include "psa_kernels.cuh"
+#include "psa_device.cuh"
 
 namespace psa {
 
@@ -20,74 +21,6 @@ namespace {
 
 constexpr int kExactThreads = 256;
 constexpr int kExactChunk = 2048;       // Seq2 symbols staged per pass
-
-__device__ __forceinline__ uint32_t symbol_of(uint8_t c)
-{
-    uint32_t d = uint32_t(c) - uint32_t('A');
-    return d < 26u ? d : (c == uint8_t('-') ? uint32_t(kGap) : 0xFFu);
-}
-
-// (key, offset) ordering used everywhere: larger key wins, ties go to the lower offset
-// (is_swapable, cuda_funcs.cu:290-307, with the score already goal-signed into the key).
-struct Cand {
-    int64_t key;
-    int32_t off;
-};
-
-__device__ __forceinline__ bool better(int64_t k2, int32_t o2, int64_t k1, int32_t o1)
-{
-    return k2 > k1 || (k2 == k1 && o2 < o1);
-}
-
-__device__ __forceinline__ Cand warp_best(Cand c)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        int64_t k = __shfl_xor_sync(0xFFFFFFFFu, c.key, d);
-        int32_t o = __shfl_xor_sync(0xFFFFFFFFu, c.off, d);
-        if (better(k, o, c.key, c.off)) { c.key = k; c.off = o; }
-    }
-    return c;
-}
-
-template <int THREADS>
-__device__ __forceinline__ Cand block_best(Cand c, Cand* s_part)
-{
-    c = warp_best(c);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) s_part[warp] = c;
-    __syncthreads();
-    if (warp == 0) {
-        Cand v = lane < THREADS / 32 ? s_part[lane] : Cand{ kKeyNone, 0x7FFFFFFF };
-        v = warp_best(v);
-        if (lane == 0) s_part[0] = v;
-    }
-    __syncthreads();
-    return s_part[0];
-}
-
-// Order-preserving map double -> int64 (after -0.0 has been folded into +0.0).
-__device__ __forceinline__ int64_t sortable_from_double(double v)
-{
-    int64_t b = __double_as_longlong(v + 0.0);
-    return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFFll);
-}
-__device__ __forceinline__ double double_from_sortable(int64_t k)
-{
-    return __longlong_as_double(k ^ ((k >> 63) & 0x7FFFFFFFFFFFFFFFll));
-}
-
-// query that owns global tile id `tile` (tile_start is a non-decreasing prefix sum, nq+1 entries)
-__device__ __forceinline__ int query_of_tile(const int32_t* __restrict__ tile_start, int nq, int tile)
-{
-    int lo = 0, hi = nq;            // invariant: tile_start[lo] <= tile < tile_start[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (tile_start[mid] <= tile) lo = mid; else hi = mid;
-    }
-    return lo;
-}
 
 // -------------------------------------------------------------------------------------------------
 // Exact scalar kernel: one thread per offset, all of Seq2 in ascending i.

@@ -43,14 +43,14 @@ void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, i
 void launch_select(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
 
 // scan engine limits
-constexpr int kDefaultEngine = 1;                   // engine picked by "auto" (1 scalar, 2 bit-sliced scan)
-constexpr int kScanWarps = 4;                       // warps per block
-constexpr int kScanTile = kScanWarps * 1024;        // offsets per tile (32 lanes x 32 offsets per warp)
+constexpr int kDefaultEngine = 2;                   // engine picked by "auto" (1 scalar, 2 bit-sliced scan)
+constexpr int kScanWarps = 4;                       // max warps per block; a warp owns 1024 offsets
+constexpr int kScanTile = kScanWarps * 1024;        // largest tile (the engine picks 1..4 warps per batch)
 constexpr int kScanMaxLen2 = 32767;                 // 15 counter planes
 constexpr int kExactTile = 256;                     // tile of the scalar engine when used alone
 constexpr int64_t kExactMaxLen2 = (1 << 20) - 1;    // 20-bit count fields
 
 int scan_chunk_steps(int rank_planes, int64_t max_len2);   // i-steps staged per shared-memory window
-size_t scan_smem_bytes(int rank_planes, int chunk);
+size_t scan_smem_bytes(int rank_planes, int chunk, int warps);
 
 } // namespace psa

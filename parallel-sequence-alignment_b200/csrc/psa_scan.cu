@@ -1,11 +1,373 @@
-// psa_scan.cu -- bit-sliced scan engine (placeholder until the kernel lands; engine 2 is not selectable yet)
+// psa_scan.cu -- the hot kernels of the scan engine (sm_100a): Seq1 bit-plane profile + bit-sliced scan.
+//
+// What the reference does per pair per offset (cuda_funcs.cu:171-198: two table signs, a substitution
+// search, two weights, a global-memory FP64 read-modify-write) becomes here:
+//
+//   k_profile  once per batch: for every Seq2 symbol a (27 rows) and every Seq1 position j, three facts
+//              about the pair (a, Seq1[j]) as bit planes over j:
+//                 b0, b1  the 2-bit sign class ('*'=0 ':'=1 '.'=2 '_'=3)
+//                 r_p     "the best substitution here has the p-th best rank" for the top K ranks
+//   k_scan     a lane owns 32 consecutive offsets as the 32 bits of a register; a warp owns 1024.
+//              Step i of the alignment needs, for all 32 offsets at once, bits [n+i, n+i+32) of row
+//              Seq2[i] -- two aligned shared-memory words and one funnel shift per plane.  The sign
+//              counts N(b0), N(b1), N(b0&b1) are kept as vertical (bit-sliced) counters updated with
+//              carry-save adders: ~2 LOP3 per plane per step for 32 offsets, i.e. ~0.3 integer
+//              lane-ops per pair evaluation instead of the >= 2 of a scalar formulation.  The best rank
+//              is the OR of the rank planes.  Counts are exact integers; the score key is formed once
+//              per offset in the epilogue (after a 32x32 bit transpose) as an int64.
+//
+// Offsets whose best rank is below the K tracked planes are "unresolved": the tile record carries an
+// upper bound for them and k_select sends the tile to the exact kernel only if that bound could win.
 #include "psa_kernels.cuh"
+#include "psa_device.cuh"
+#include "psa_bitslice.h"
 
 namespace psa {
 
-int scan_chunk_steps(int, int64_t) { return 512; }
-size_t scan_smem_bytes(int, int) { return 0; }
-void launch_profile(const DeviceTable&, const BatchGeom&, const BatchPtrs&, int, int, cudaStream_t) {}
-void launch_scan(const DeviceTable&, const BatchGeom&, const BatchPtrs&, int, int64_t, cudaStream_t) {}
+namespace {
+
+constexpr int kProfileThreads = 256;
+constexpr int kScanChunkMax = 1024;     // alignment steps staged per shared-memory window
+
+// -------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kProfileThreads)
+k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
+{
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    for (int k = threadIdx.x; k < kSymbols * kRowPad; k += kProfileThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    __syncthreads();
+    const int64_t total = int64_t(kPlaneRows) * P.plane_words;
+    for (int64_t idx = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * kProfileThreads) {
+        const int row = int(idx / P.plane_words);
+        const int64_t w = idx - int64_t(row) * P.plane_words;
+        const int64_t base = w * 32;
+        uint32_t b0 = 0, b1 = 0, r[K > 0 ? K : 1] = {};
+        if (row < kSymbols && base < G.len1) {
+            // 32 bytes of Seq1; the buffer is padded so the vector loads stay inside the allocation
+            const uint4 v0 = *reinterpret_cast<const uint4*>(P.seq1 + base);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(P.seq1 + base + 16);
+            const uint32_t words[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+            const int n = (G.len1 - base) < 32 ? int(G.len1 - base) : 32;
+#pragma unroll
+            for (int t = 0; t < 32; t++) {
+                if (t < n) {
+                    uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
+                    if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
+                    const uint32_t code = s_code[row * kRowPad + c];
+                    b0 |= (code & 1u) << t;
+                    b1 |= ((code >> 1) & 1u) << t;
+                    const int rank = int(code >> 2);
+#pragma unroll
+                    for (int k = 0; k < K; k++) r[k] |= uint32_t(rank != 0 && rank == T.nranks - k) << t;
+                }
+            }
+        }
+        P.cls_planes[idx] = make_uint2(b0, b1);
+#pragma unroll
+        for (int k = 0; k < K; k++) P.rank_planes[idx * K + k] = r[k];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// One group = 32 alignment steps with compile-time shift amounts 0..31.
+//   pc / pr : this lane's low word in the class / rank window for step 0 of the group
+//   ro      : 32 byte offsets (row * nwords * 8), one per step, warp-uniform
+// -------------------------------------------------------------------------------------------------
+template <int NUP, int K, bool RANK>
+__device__ __forceinline__ void scan_group(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C,
+                                           uint32_t (&racc)[K > 0 ? K : 1], const char* pc, const char* pr,
+                                           const uint32_t* ro)
+{
+    uint32_t pa[5], pb[5], pn[5];
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s4 + u;
+            const uint32_t off = offs[u];
+            const uint2 lo = *reinterpret_cast<const uint2*>(pc + off);
+            uint32_t x0 = lo.x, x1 = lo.y;
+            if (s != 0) {
+                const uint2 hi = *reinterpret_cast<const uint2*>(pc + off + 8);
+                x0 = __funnelshift_r(lo.x, hi.x, s);
+                x1 = __funnelshift_r(lo.y, hi.y, s);
+            }
+            vc_feed(A, pa, x0, s);
+            vc_feed(B, pb, x1, s);
+            vc_feed(C, pn, x0 & x1, s);
+            if (RANK) {
+                if (K == 1) {
+                    const uint32_t l = *reinterpret_cast<const uint32_t*>(pr + (off >> 1));
+                    uint32_t x = l;
+                    if (s != 0) x = __funnelshift_r(l, *reinterpret_cast<const uint32_t*>(pr + (off >> 1) + 4), s);
+                    racc[0] |= x;
+                } else if (K == 2) {
+                    const uint2 l = *reinterpret_cast<const uint2*>(pr + off);
+                    uint2 h = l;
+                    if (s != 0) h = *reinterpret_cast<const uint2*>(pr + off + 8);
+                    racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
+                    racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
+                } else if (K == 4) {
+                    const uint4 l = *reinterpret_cast<const uint4*>(pr + (off << 1));
+                    uint4 h = l;
+                    if (s != 0) h = *reinterpret_cast<const uint4*>(pr + (off << 1) + 16);
+                    racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
+                    racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
+                    racc[K > 2 ? 2 : 0] |= s ? __funnelshift_r(l.z, h.z, s) : l.z;
+                    racc[K > 3 ? 3 : 0] |= s ? __funnelshift_r(l.w, h.w, s) : l.w;
+                }
+            }
+        }
+    }
+}
+
+// per-lane result of the epilogue
+struct LaneBest {
+    Cand res;   // best resolved (key, offset)
+    Cand ub;    // best upper bound among unresolved offsets
+};
+
+__device__ __forceinline__ void take(Cand& c, int64_t key, int32_t off)
+{
+    if (better(key, off, c.key, c.off)) { c.key = key; c.off = off; }
+}
+
+// -------------------------------------------------------------------------------------------------
+// NB : counter planes (len2 < 2^NB), K : rank planes tracked
+// block = warps x 32 threads, tile = warps x 1024 offsets, one block per tile
+// dynamic shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | [chunk] uint32 row offsets
+// -------------------------------------------------------------------------------------------------
+template <int NB, int K>
+__global__ void __launch_bounds__(128)
+k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk)
+{
+    constexpr int NUP = NB - 5;
+    constexpr bool kSingle = 3 * NB + K <= 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint2* s_cls = reinterpret_cast<uint2*>(smem);
+    uint32_t* s_rnk = reinterpret_cast<uint32_t*>(s_cls + size_t(kPlaneRows) * nwords);
+    uint32_t* s_ro = s_rnk + size_t(kPlaneRows) * nwords * K;
+    __shared__ Cand s_res[4], s_ub[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
+    const int tile_id = blockIdx.x;
+    const int q = query_of_tile(P.tile_start, G.nq, tile_id);
+    const int t = tile_id - P.tile_start[q];
+    const int64_t qbeg = P.qoff[q];
+    const int len2 = int(P.qoff[q + 1] - qbeg);
+    const int64_t first = G.last >= 0 ? G.first : 0;
+    const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
+    const int64_t tb = tile_base(first) + int64_t(t) * G.tile;      // multiple of 32
+    const int64_t ln0 = tb + warp * 1024 + lane * 32;               // this lane's first offset
+
+    // valid offsets of this lane as a bit mask
+    uint32_t vmask = 0;
+    {
+        const int64_t lo = first > ln0 ? first - ln0 : 0;
+        const int64_t hi = (last - ln0) < 32 ? (last - ln0) : 32;
+        if (hi > lo) {
+            const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << int(hi)) - 1u);
+            const uint32_t below_lo = (1u << int(lo)) - 1u;
+            vmask = upto_hi & ~below_lo;
+        }
+    }
+    const bool warp_active = __any_sync(0xFFFFFFFFu, vmask != 0);
+
+    VCounter<NUP> A, B, C;
+    A.clear(); B.clear(); C.clear();
+    uint32_t racc[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
+    racc[0] = ~vmask;                       // offsets outside the range count as saturated
+    bool rank_on = K > 0;
+
+    const int steps_total = (len2 + 31) & ~31;
+    for (int c0 = 0; c0 < steps_total; c0 += chunk) {
+        const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
+        const int need = warps * 32 + (cl >> 5);                    // window words actually read
+        __syncthreads();
+        {
+            const int64_t g0 = (tb + c0) >> 5;
+            const uint2* gc = P.cls_planes + g0;
+            for (int idx = tid; idx < kPlaneRows * need; idx += nthreads) {
+                const int row = idx / need, w = idx - row * need;
+                s_cls[row * nwords + w] = gc[int64_t(row) * P.plane_words + w];
+            }
+            if (K > 0) {
+                const uint32_t* gr = P.rank_planes + g0 * K;
+                for (int idx = tid; idx < kPlaneRows * need * K; idx += nthreads) {
+                    const int row = idx / (need * K), w = idx - row * (need * K);
+                    s_rnk[row * nwords * K + w] = gr[int64_t(row) * P.plane_words * K + w];
+                }
+            }
+            for (int s = tid; s < cl; s += nthreads) {
+                const int i = c0 + s;
+                uint32_t row = kZeroRow;
+                if (i < len2) {
+                    row = symbol_of(P.seq2s[qbeg + i]);
+                    if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
+                }
+                s_ro[s] = row * uint32_t(nwords) * 8u;
+            }
+        }
+        __syncthreads();
+        if (warp_active) {
+            const int groups = cl >> 5;
+            for (int g = 0; g < groups; g++) {
+                const char* pc = reinterpret_cast<const char*>(s_cls + warp * 32 + lane + g);
+                const char* pr = reinterpret_cast<const char*>(s_rnk + size_t(warp * 32 + lane + g) * K);
+                const uint32_t* ro = s_ro + g * 32;
+                if (rank_on) {
+                    scan_group<NUP, K, true>(A, B, C, racc, pc, pr, ro);
+                    // every offset of the warp already carries the top rank: the lower planes are moot
+                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) rank_on = false;
+                } else {
+                    scan_group<NUP, K, false>(A, B, C, racc, pc, pr, ro);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: per-offset keys ---------------------------------------------------------------
+    LaneBest mine{ { kKeyNone, 0x7FFFFFFF }, { kKeyNone, 0x7FFFFFFF } };
+    if (warp_active && vmask) {
+        // key = len2*k0 + N(b0)*(k1-k0) + N(b1)*(k2-k0) + N(b0&b1)*(k3-k1-k2+k0) + kdiff[rank]
+        const int64_t ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
+        const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
+        const int64_t kbase = int64_t(len2) * T.kcls[0];
+        // ranks nranks, nranks-1, .. nranks-K+1 are tracked; anything else is <= floor
+        const int floor_rank = T.nranks - K;
+        const bool floor_none = floor_rank <= 0;                        // nothing below the planes but "no substitute"
+        const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+        const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
+        int64_t ktop[K > 0 ? K : 1];
+#pragma unroll
+        for (int k = 0; k < K; k++) ktop[k] = T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0];
+
+        uint32_t m[32], m2[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) { m[k] = 0; m2[k] = 0; }
+#pragma unroll
+        for (int k = 0; k < NB; k++) { m[k] = A.plane(k); m[NB + k] = B.plane(k); }
+        if (kSingle) {
+#pragma unroll
+            for (int k = 0; k < NB; k++) m[2 * NB + k] = C.plane(k);
+#pragma unroll
+            for (int k = 0; k < K; k++) m[3 * NB + k] = racc[k];
+            transpose32(m);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NB; k++) m2[k] = C.plane(k);
+#pragma unroll
+            for (int k = 0; k < K; k++) m2[NB + k] = racc[k];
+            transpose32(m);
+            transpose32(m2);
+        }
+        constexpr uint32_t kMask = (1u << NB) - 1u;
+#pragma unroll
+        for (int tt = 0; tt < 32; tt++) {
+            if (!((vmask >> tt) & 1u)) continue;
+            const uint32_t v = m[tt];
+            const uint32_t na = v & kMask, nb = (v >> NB) & kMask;
+            uint32_t nc, rb;
+            if (kSingle) { nc = (v >> (kSingle ? 2 * NB : 0)) & kMask; rb = K > 0 ? (v >> (kSingle ? 3 * NB : 0)) & ((1u << K) - 1u) : 0u; }
+            else { nc = m2[tt] & kMask; rb = K > 0 ? (m2[tt] >> NB) & ((1u << K) - 1u) : 0u; }
+            int64_t key = kbase + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
+            const int32_t off = int32_t(ln0 + tt);
+            if (K > 0 && rb) {
+                // lowest set plane = best rank present
+                int64_t d = ktop[K > 0 ? K - 1 : 0];
+#pragma unroll
+                for (int k = K - 2; k >= 0; k--)
+                    if (rb & (1u << k)) d = ktop[k];
+                take(mine.res, key + d, off);
+            } else if (floor_exact) {
+                if (!floor_none) take(mine.res, key + kfloor, off);
+            } else {
+                take(mine.ub, key + kfloor, off);
+            }
+        }
+    }
+    mine.res = warp_best(mine.res);
+    mine.ub = warp_best(mine.ub);
+    if (lane == 0) { s_res[warp] = mine.res; s_ub[warp] = mine.ub; }
+    __syncthreads();
+    if (tid == 0) {
+        Cand r = s_res[0], u = s_ub[0];
+        for (int w = 1; w < warps; w++) {
+            take(r, s_res[w].key, s_res[w].off);
+            take(u, s_ub[w].key, s_ub[w].off);
+        }
+        TileRec rec;
+        rec.key = r.key; rec.offset = r.off;
+        rec.ub_key = u.key; rec.ub_offset = u.off;
+        rec.score = 0.0; rec.flags = 0; rec.pad = 0;
+        P.tiles[tile_id] = rec;
+    }
+}
+
+template <int NB, int K>
+void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, cudaStream_t stream)
+{
+    const int warps = G.tile / 1024;
+    const int nwords = warps * 32 + chunk / 32;
+    const size_t smem = scan_smem_bytes(K, chunk, warps);
+    cudaFuncSetAttribute(k_scan<NB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_scan<NB, K><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
+}
+
+template <int NB>
+void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, cudaStream_t stream)
+{
+    switch (K) {
+    case 0: launch_scan_inst<NB, 0>(T, G, P, chunk, stream); break;
+    case 1: launch_scan_inst<NB, 1>(T, G, P, chunk, stream); break;
+    case 2: launch_scan_inst<NB, 2>(T, G, P, chunk, stream); break;
+    default: launch_scan_inst<NB, 4>(T, G, P, chunk, stream); break;
+    }
+}
+
+} // namespace
+
+int scan_chunk_steps(int, int64_t max_len2)
+{
+    const int64_t padded = (max_len2 + 31) & ~int64_t(31);
+    return int(padded < kScanChunkMax ? padded : kScanChunkMax);
+}
+
+size_t scan_smem_bytes(int rank_planes, int chunk, int warps)
+{
+    const size_t nwords = size_t(warps) * 32 + chunk / 32;
+    return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(chunk) * 4;
+}
+
+void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
+                    cudaStream_t stream)
+{
+    const int64_t total = int64_t(kPlaneRows) * P.plane_words;
+    int64_t blocks = (total + kProfileThreads - 1) / kProfileThreads;
+    const int64_t cap = int64_t(sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    switch (rank_planes) {
+    case 0: k_profile<0><<<(int)blocks, kProfileThreads, 0, stream>>>(T, G, P); break;
+    case 1: k_profile<1><<<(int)blocks, kProfileThreads, 0, stream>>>(T, G, P); break;
+    case 2: k_profile<2><<<(int)blocks, kProfileThreads, 0, stream>>>(T, G, P); break;
+    default: k_profile<4><<<(int)blocks, kProfileThreads, 0, stream>>>(T, G, P); break;
+    }
+}
+
+void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
+                 cudaStream_t stream)
+{
+    if (G.total_tiles < 1) return;
+    const int chunk = scan_chunk_steps(rank_planes, max_len2);
+    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, stream);
+    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, stream);
+    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, stream);
+}
 
 } // namespace psa
