@@ -131,6 +131,10 @@ _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
 
+def c_weights(weights) -> C.Array:
+    return (C.c_double * 4)(*[float(x) for x in weights])
+
+
 def _w(weights) -> C.Array:
     return (C.c_double * 4)(*[float(x) for x in weights])
 
@@ -271,6 +275,20 @@ class Context:
         self._check(_lib.psa_search_batch(self._h, _w(weights), int(bool(is_max)), b.seq1_ptr, b.len1,
                                           b.seq2s_ptr, b.q_off_ptr, b.nq, out))
         return [_py(out[i]) for i in range(b.nq)]
+
+    def search_batch_raw(self, weights_c, is_max: bool, batch: Batch, out):
+        """The bare C call (psa_search_batch) on preallocated buffers: `weights_c` a c_double[4], `out` a
+        result array from new_result_array().  No Python objects are created per result."""
+        self._check(_lib.psa_search_batch(self._h, weights_c, int(bool(is_max)), batch.seq1_ptr, batch.len1,
+                                          batch.seq2s_ptr, batch.q_off_ptr, batch.nq, out))
+
+    @staticmethod
+    def new_result_array(nq: int):
+        return (_CResult * max(nq, 1))()
+
+    @staticmethod
+    def result_from_array(out, i: int) -> Result:
+        return _py(out[i])
 
     def search(self, weights, is_max: bool, seq1, seq2) -> Result:
         return self.search_batch(weights, is_max, seq1, [seq2])[0]

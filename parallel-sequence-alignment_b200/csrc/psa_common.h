@@ -36,12 +36,12 @@ constexpr int64_t kKeyNone = INT64_MIN;       // key of an offset with no possib
 
 // One record per (query, tile of offsets), written by the scan / exact kernels.
 struct TileRec {
-    int64_t key;        // best resolved key in the tile (kKeyNone if none)
-    int64_t ub_key;     // best upper bound among offsets the scan could not resolve (kKeyNone if none)
-    double  score;      // exact kernel, re-score mode: reference double score of the tile winner
-    int32_t offset;     // absolute offset of `key` / `score`
+    int64_t key;        // best key in the tile (kKeyNone if none); exact integer order in exact mode
+    int64_t ub_key;     // scan engine, re-score mode: upper estimate of every key in the tile
+    double  score;      // unused (kept for layout)
+    int32_t offset;     // absolute offset of `key`
     int32_t ub_offset;
-    int32_t flags;      // bit0: written by the exact kernel
+    int32_t flags;      // bit0: written by the exact kernel (key is a sortable reference double when !exact)
     int32_t pad;
 };
 constexpr int kTileExact = 1;

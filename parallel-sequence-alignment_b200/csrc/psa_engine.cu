@@ -44,7 +44,7 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, cand_list, flags, cls_planes, rank_planes;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, flags, cls_planes, rank_planes;
     PinBuf h_qoff, h_tile_start, h_out, h_flags;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
@@ -124,7 +124,7 @@ int ensure_pin(psa_context* ctx, PinBuf& b, size_t bytes)
 void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
-    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.cand_list, &d.flags,
+    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.flags,
                        &d.cls_planes, &d.rank_planes })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out, &d.h_flags })
@@ -142,8 +142,10 @@ int pick_rank_planes(const psa_context* ctx)
 {
     int avail = ctx->table.nranks - (ctx->table.has_none ? 0 : 1);   // planes needed to resolve everything
     if (avail < 0) avail = 0;
-    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : 2;
-    if (want > 2) want = want >= 4 ? 4 : 2;                          // supported widths: 0,1,2,4
+    // offsets the planes leave unresolved are settled inside the scan kernel, so the plane count is a pure
+    // speed knob: long queries saturate the top rank within a few dozen steps, short ones benefit from two
+    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : (ctx->max_len2 >= 128 ? 1 : 2);
+    if (want > 2) want = 4;                                          // supported widths: 0,1,2,4
     return std::min(want, std::max(avail, 0));
 }
 
@@ -180,15 +182,15 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     ht[nq] = (int32_t)tiles;
     const int64_t seq2_bytes = hq[nq];
 
-    const int64_t pad_bits = kScanTile + 2048 + 64;
-    const int64_t plane_words = (len1 + pad_bits + 31) / 32;
+    const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.qoff, sizeof(int64_t) * (nq + 1)))) return rc;
     if ((rc = ensure_dev(ctx, d.tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
     if ((rc = ensure_dev(ctx, d.tiles, sizeof(TileRec) * (size_t)tiles))) return rc;
     if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq))) return rc;
-    if ((rc = ensure_dev(ctx, d.cand_list, sizeof(int32_t) * (size_t)tiles))) return rc;
+    if (scan && !ctx->table.exact)
+        if ((rc = ensure_dev(ctx, d.lane_keys, sizeof(int64_t) * (size_t)tiles * (tile / 32)))) return rc;
     if ((rc = ensure_dev(ctx, d.flags, sizeof(int32_t) * 4))) return rc;
     if (scan) {
         if ((rc = ensure_dev(ctx, d.cls_planes, sizeof(uint2) * (size_t)plane_words * kPlaneRows))) return rc;
@@ -214,7 +216,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.tile_start = (const int32_t*)d.tile_start.p;
     d.P.tiles = (TileRec*)d.tiles.p;
     d.P.out = (QueryRec*)d.out.p;
-    d.P.cand_list = (int32_t*)d.cand_list.p;
+    d.P.lane_keys = (int64_t*)d.lane_keys.p;
     d.P.cand_count = (int32_t*)d.flags.p;
     d.P.err_flag = (int32_t*)d.flags.p + 1;
     d.P.cls_planes = (uint2*)d.cls_planes.p;
@@ -234,16 +236,14 @@ int run_device(psa_context* ctx, DeviceState& d)
         PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
-        launch_select(ctx->table, d.G, d.P, d.stream);
-        launch_exact_tiles(ctx->table, d.G, d.P, true, d.sm_count, d.stream);
-        ctx->st_launches += 4;
+        ctx->st_launches += 2;
     } else {
         PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
-        launch_exact_tiles(ctx->table, d.G, d.P, false, d.sm_count, d.stream);
+        launch_exact_tiles(ctx->table, d.G, d.P, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 1;
     }
-    launch_final(ctx->table, d.G, d.P, d.stream);
+    launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
     ctx->st_launches += 1;
     PSA_CUDA(ctx, cudaGetLastError());
     PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));

@@ -30,7 +30,7 @@ constexpr int kExactChunk = 2048;       // Seq2 symbols staged per pass
 // -------------------------------------------------------------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(kExactThreads)
-k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int use_list)
+k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
 {
     __shared__ uint64_t s_tab[kSymbols * kRowPad];
     __shared__ __align__(16) uint8_t s_win[kExactThreads + kExactChunk];
@@ -50,9 +50,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
     if (tid < 4) s_w[tid] = T.wcls[tid];
     __syncthreads();
 
-    const int nitems = use_list ? *P.cand_count : G.total_tiles;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int tile_id = use_list ? P.cand_list[item] : item;
+    for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {
         const int q = query_of_tile(P.tile_start, G.nq, tile_id);
         const int t = tile_id - P.tile_start[q];
         const int64_t qbeg = P.qoff[q];
@@ -140,64 +138,82 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 }
 
 // -------------------------------------------------------------------------------------------------
-// Candidate selection (scan engine only): after the bit-sliced scan every tile holds its best
-// resolved key and the best upper bound of its unresolved offsets.  A tile must be evaluated by the
-// exact kernel iff something in it could still be the reference's winner:
-//   exact mode   : an unresolved offset whose bound reaches the best resolved key
-//   re-score mode: any key or bound within key_slack of the best key
+// Finish: one block per query.
+//  (1) winner over the query's tile records under (key desc, offset asc);
+//  (2) only when the weights are not exactly summable and the records come from the bit-sliced scan:
+//      the integer keys order offsets like the reference only up to key_slack, so every 32-offset word
+//      whose key estimate is within key_slack of the best key is re-scored here with a double
+//      accumulated over i = 0..len2-1 in the reference's order (cpu_funcs.c:271-299), and the winner is
+//      chosen among those doubles under is_swapable's order (cuda_funcs.cu:290-307);
+//  (3) one pass over the winning alignment for the sign counts, the first position carrying the best
+//      rank (cpu_funcs.c:287-294: strict compare, so the lowest i wins ties) and its replacement letter.
 // -------------------------------------------------------------------------------------------------
-constexpr int kSelectThreads = 128;
+constexpr int kFinishThreads = 128;
 
-__global__ void __launch_bounds__(kSelectThreads)
-k_select(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
+__global__ void __launch_bounds__(kFinishThreads)
+k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int scan_records)
 {
-    __shared__ Cand s_part[kSelectThreads / 32];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int t0 = P.tile_start[q], t1 = P.tile_start[q + 1];
-    Cand mine{ kKeyNone, 0x7FFFFFFF };
-    for (int t = t0 + tid; t < t1; t += kSelectThreads) {
-        const TileRec r = P.tiles[t];
-        // in re-score mode bounds count too: they are valid upper estimates of real keys only, so the
-        // threshold must come from resolved keys (a lower bound of the true best)
-        if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
-    }
-    const Cand best = block_best<kSelectThreads>(mine, s_part);
-    for (int t = t0 + tid; t < t1; t += kSelectThreads) {
-        const TileRec r = P.tiles[t];
-        bool need;
-        if (T.exact) {
-            need = r.ub_key != kKeyNone && !better(best.key, best.off, r.ub_key, r.ub_offset);
-        } else {
-            const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
-            // best.key - slack cannot underflow: |key| < 2^61
-            need = top != kKeyNone && (best.key == kKeyNone || top >= best.key - T.key_slack);
-        }
-        if (need) P.cand_list[atomicAdd(P.cand_count, 1)] = t;
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// Finalisation: per query, the winning tile record, then one pass over the winning alignment for
-// the sign counts, the first position carrying the best rank (cpu_funcs.c:287-294: strict compare,
-// so the lowest i wins ties) and its replacement letter.
-// -------------------------------------------------------------------------------------------------
-constexpr int kFinalThreads = 128;
-
-__global__ void __launch_bounds__(kFinalThreads)
-k_final(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
-{
-    __shared__ Cand s_part[kFinalThreads / 32];
+    __shared__ Cand s_part[kFinishThreads / 32];
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ double s_w[4];
     __shared__ unsigned long long s_pos;
     __shared__ int s_cnt[4];
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = P.tile_start[q], t1 = P.tile_start[q + 1];
+    for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    if (tid < 4) s_w[tid] = T.wcls[tid];
+
+    const int64_t qbeg = P.qoff[q];
+    const int len2 = int(P.qoff[q + 1] - qbeg);
+    const int64_t first = G.last >= 0 ? G.first : 0;
+    const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
+    const uint8_t* b = P.seq2s + qbeg;
+
     Cand mine{ kKeyNone, 0x7FFFFFFF };
-    for (int t = t0 + tid; t < t1; t += kFinalThreads) {
+    for (int t = t0 + tid; t < t1; t += kFinishThreads) {
         const TileRec r = P.tiles[t];
-        if (!T.exact && !(r.flags & kTileExact)) continue;   // only reference-order doubles may compete
         if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
     }
-    const Cand win = block_best<kFinalThreads>(mine, s_part);
+    Cand win = block_best<kFinishThreads>(mine, s_part);     // also orders the s_code / s_w writes
+
+    if (!T.exact && scan_records) {
+        const int64_t threshold = win.key == kKeyNone ? kKeyNone : win.key - T.key_slack;   // |key| < 2^61: no wrap
+        const int tile_words = G.tile >> 5;
+        Cand mine2{ kKeyNone, 0x7FFFFFFF };
+        int words = 0;
+        for (int t = t0; t < t1; t++) {
+            const TileRec r = P.tiles[t];
+            const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
+            if (top == kKeyNone || top < threshold) continue;
+            const int64_t* lk = P.lane_keys + int64_t(t) * tile_words;
+            const int64_t tb = tile_base(first) + int64_t(t - t0) * G.tile;
+            for (int w = warp; w < tile_words; w += kFinishThreads / 32) {
+                const int64_t k = lk[w];
+                if (k == kKeyNone || k < threshold) continue;
+                words++;
+                const int64_t n = tb + 32 * w + lane;
+                if (n < first || n >= last) continue;
+                const uint8_t* a = P.seq1 + n;
+                double total = 0.0;
+                uint32_t best_rank = 0;
+#pragma unroll 4
+                for (int i = 0; i < len2; i++) {
+                    uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+                    if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }      // flagged by the kernels before us
+                    const uint32_t code = s_code[c2 * kRowPad + c1];
+                    total += s_w[code & 3u];
+                    best_rank = max(best_rank, code >> 2);
+                }
+                if (best_rank) {
+                    const double score = total + T.wdiff[best_rank];                       // cpu_funcs.c:299
+                    const int64_t key = sortable_from_double(T.is_max ? score : -score);
+                    if (better(key, int32_t(n), mine2.key, mine2.off)) { mine2.key = key; mine2.off = int32_t(n); }
+                }
+            }
+        }
+        if (lane == 0 && words) atomicAdd(P.cand_count, words);
+        win = block_best<kFinishThreads>(mine2, s_part);
+    }
 
     QueryRec out;
     out.key = win.key; out.score = 0.0;
@@ -211,16 +227,13 @@ k_final(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtr
     if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
 
-    const int64_t qbeg = P.qoff[q];
-    const int len2 = int(P.qoff[q + 1] - qbeg);
     const uint8_t* a = P.seq1 + win.off;
-    const uint8_t* b = P.seq2s + qbeg;
     int cnt[4] = { 0, 0, 0, 0 };
     unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
-    for (int i = tid; i < len2; i += kFinalThreads) {
+    for (int i = tid; i < len2; i += kFinishThreads) {
         uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
-        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }      // flagged by the kernels before us
-        const uint32_t code = T.code[c2][c1];
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        const uint32_t code = s_code[c2 * kRowPad + c1];
         cnt[code & 3u]++;
         const unsigned long long p = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
         pos = p > pos ? p : pos;
@@ -232,7 +245,7 @@ k_final(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtr
 #pragma unroll
         for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
     }
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         atomicMax(&s_pos, pos);
 #pragma unroll
         for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
@@ -248,32 +261,25 @@ k_final(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtr
         out.ch = T.sub[c2][c1];
         out.rank = rank;
         for (int c = 0; c < 4; c++) out.counts[c] = s_cnt[c];
-        if (!T.exact) out.score = (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key);
+        const bool key_is_double = !T.exact;     // engine 1 tile keys and re-scored keys are sortable doubles
+        if (key_is_double) out.score = (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key);
         P.out[q] = out;
     }
 }
 
 } // namespace
 
-void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool cand, int sm_count,
-                        cudaStream_t stream)
+void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
 {
-    int grid = cand ? sm_count * 4 : G.total_tiles;
-    if (grid < 1) return;
-    if (T.exact) k_exact_tiles<true><<<grid, kExactThreads, 0, stream>>>(T, G, P, cand ? 1 : 0);
-    else k_exact_tiles<false><<<grid, kExactThreads, 0, stream>>>(T, G, P, cand ? 1 : 0);
+    if (G.total_tiles < 1) return;
+    if (T.exact) k_exact_tiles<true><<<G.total_tiles, kExactThreads, 0, stream>>>(T, G, P);
+    else k_exact_tiles<false><<<G.total_tiles, kExactThreads, 0, stream>>>(T, G, P);
 }
 
-void launch_select(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
+void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream)
 {
     if (G.nq < 1) return;
-    k_select<<<G.nq, kSelectThreads, 0, stream>>>(T, G, P);
-}
-
-void launch_final(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
-{
-    if (G.nq < 1) return;
-    k_final<<<G.nq, kFinalThreads, 0, stream>>>(T, G, P);
+    k_finish<<<G.nq, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
 }
 
 } // namespace psa

@@ -13,8 +13,8 @@ struct BatchPtrs {
     const int32_t* tile_start;  // nq+1 prefix sum of tiles per query
     TileRec*       tiles;       // total_tiles records
     QueryRec*      out;         // nq records
-    int32_t*       cand_list;   // tile ids that must be evaluated by the exact kernel
-    int32_t*       cand_count;  // [0] = number of entries in cand_list
+    int64_t*       lane_keys;   // scan engine, re-score mode: per (tile, 32-offset word) upper estimate of its keys
+    int32_t*       cand_count;  // [0] = number of 32-offset words re-scored in reference order (statistic)
     int32_t*       err_flag;    // bit0: symbol outside [A-Z-]
     // bit-plane profile of Seq1 (scan engine): [row][word] of 64-bit (class planes) and
     // [row][word][rank_planes] of 32-bit words; rows = 28 (27 symbols + zero row)
@@ -23,24 +23,23 @@ struct BatchPtrs {
     int64_t        plane_words; // words per row
 };
 
-// Offsets of a query are tiled from `base` = first rounded down to a multiple of 32 so that bit-plane
-// words line up; a tile covers [base + t*tile, base + (t+1)*tile) intersected with [first, last).
-__host__ __device__ inline int64_t tile_base(int64_t first) { return first & ~int64_t(31); }
+// Offsets of a query are tiled from `base` = first rounded down to a multiple of 128 so that bit-plane
+// rows line up on 16 bytes (TMA bulk copies); a tile covers [base + t*tile, base + (t+1)*tile) intersected
+// with [first, last).
+__host__ __device__ inline int64_t tile_base(int64_t first) { return first & ~int64_t(127); }
 
 // ---- launchers (all asynchronous on `stream`) -------------------------------------------------
-// exact scalar kernel over every tile (cand == false) or over the candidate list (cand == true)
-void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool cand, int sm_count,
-                        cudaStream_t stream);
-// per-query winner + char_offset + counts
-void launch_final(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
+// exact scalar kernel over every tile (engine 1)
+void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
+// per-query finish: winner over the tile records (re-scored in reference order when the weights are not
+// exactly summable and the records come from the scan), then char_offset + counts + substitute letter
+void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream);
 // bit-plane profile of Seq1 for the scan engine
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
                     cudaStream_t stream);
 // bit-sliced scan of every tile
 void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
                  cudaStream_t stream);
-// per-query candidate selection between scan and exact
-void launch_select(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
 
 // scan engine limits
 constexpr int kDefaultEngine = 2;                   // engine picked by "auto" (1 scalar, 2 bit-sliced scan)
@@ -50,7 +49,8 @@ constexpr int kScanMaxLen2 = 32767;                 // 15 counter planes
 constexpr int kExactTile = 256;                     // tile of the scalar engine when used alone
 constexpr int64_t kExactMaxLen2 = (1 << 20) - 1;    // 20-bit count fields
 
-int scan_chunk_steps(int rank_planes, int64_t max_len2);   // i-steps staged per shared-memory window
+int scan_chunk_steps(int rank_planes, int64_t max_len2);   // i-steps staged per shared-memory window (multiple of 128)
+int64_t scan_plane_words(int64_t len1);                    // words per bit-plane row incl. zero padding (multiple of 4)
 size_t scan_smem_bytes(int rank_planes, int chunk, int warps);
 
 } // namespace psa

@@ -125,21 +125,20 @@ __device__ __forceinline__ void scan_group(VCounter<NUP>& A, VCounter<NUP>& B, V
     }
 }
 
-// per-lane result of the epilogue
-struct LaneBest {
-    Cand res;   // best resolved (key, offset)
-    Cand ub;    // best upper bound among unresolved offsets
-};
-
 __device__ __forceinline__ void take(Cand& c, int64_t key, int32_t off)
 {
     if (better(key, off, c.key, c.off)) { c.key = key; c.off = off; }
 }
 
+__host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
+
 // -------------------------------------------------------------------------------------------------
 // NB : counter planes (len2 < 2^NB), K : rank planes tracked
 // block = warps x 32 threads, tile = warps x 1024 offsets, one block per tile
-// dynamic shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | [chunk] uint32 row offsets
+// dynamic shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | [chunk] uint32 row offsets;
+// after the main loop the front of it is reused as per-warp scratch (1024 x int64) by the epilogue.
+// The window is filled by TMA bulk copies (one per plane row) that complete on an mbarrier while the
+// block converts its slice of Seq2 into row offsets.
 // -------------------------------------------------------------------------------------------------
 template <int NB, int K>
 __global__ void __launch_bounds__(128)
@@ -147,11 +146,14 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 {
     constexpr int NUP = NB - 5;
     constexpr bool kSingle = 3 * NB + K <= 32;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint2* s_cls = reinterpret_cast<uint2*>(smem);
     uint32_t* s_rnk = reinterpret_cast<uint32_t*>(s_cls + size_t(kPlaneRows) * nwords);
     uint32_t* s_ro = s_rnk + size_t(kPlaneRows) * nwords * K;
-    __shared__ Cand s_res[4], s_ub[4];
+    __shared__ Cand s_res[4];
+    __shared__ int64_t s_top[4];
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
     const int tile_id = blockIdx.x;
@@ -161,15 +163,18 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     const int len2 = int(P.qoff[q + 1] - qbeg);
     const int64_t first = G.last >= 0 ? G.first : 0;
     const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
-    const int64_t tb = tile_base(first) + int64_t(t) * G.tile;      // multiple of 32
+    const int64_t tb = tile_base(first) + int64_t(t) * G.tile;      // multiple of 128
     const int64_t ln0 = tb + warp * 1024 + lane * 32;               // this lane's first offset
+
+    if (tid == 0) mbar_init(&s_bar, 1);
+    for (int k = tid; k < kSymbols * kRowPad; k += nthreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
 
     // valid offsets of this lane as a bit mask
     uint32_t vmask = 0;
     {
         const int64_t lo = first > ln0 ? first - ln0 : 0;
         const int64_t hi = (last - ln0) < 32 ? (last - ln0) : 32;
-        if (hi > lo) {
+        if (hi > lo && lo < 32) {
             const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << int(hi)) - 1u);
             const uint32_t below_lo = (1u << int(lo)) - 1u;
             vmask = upto_hi & ~below_lo;
@@ -184,37 +189,36 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
     racc[0] = ~vmask;                       // offsets outside the range count as saturated
     bool rank_on = K > 0;
+    uint32_t parity = 0;
 
     const int steps_total = (len2 + 31) & ~31;
     for (int c0 = 0; c0 < steps_total; c0 += chunk) {
         const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
-        const int need = warps * 32 + (cl >> 5);                    // window words actually read
-        __syncthreads();
-        {
-            const int64_t g0 = (tb + c0) >> 5;
-            const uint2* gc = P.cls_planes + g0;
-            for (int idx = tid; idx < kPlaneRows * need; idx += nthreads) {
-                const int row = idx / need, w = idx - row * need;
-                s_cls[row * nwords + w] = gc[int64_t(row) * P.plane_words + w];
-            }
-            if (K > 0) {
-                const uint32_t* gr = P.rank_planes + g0 * K;
-                for (int idx = tid; idx < kPlaneRows * need * K; idx += nthreads) {
-                    const int row = idx / (need * K), w = idx - row * (need * K);
-                    s_rnk[row * nwords * K + w] = gr[int64_t(row) * P.plane_words * K + w];
-                }
-            }
-            for (int s = tid; s < cl; s += nthreads) {
-                const int i = c0 + s;
-                uint32_t row = kZeroRow;
-                if (i < len2) {
-                    row = symbol_of(P.seq2s[qbeg + i]);
-                    if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
-                }
-                s_ro[s] = row * uint32_t(nwords) * 8u;
+        const int need = round_up4(warps * 32 + (cl >> 5));         // window words staged (multiple of 4)
+        __syncthreads();                                            // previous window fully consumed / barrier initialised
+        if (warp == 0) {
+            const int64_t g0 = (tb + c0) >> 5;                      // multiple of 4: every row starts on 16 bytes
+            if (lane == 0) mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(need) * uint32_t(8 + 4 * K));
+            __syncwarp();
+            if (lane < kPlaneRows) {
+                tma_load_1d(s_cls + lane * nwords, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(need) * 8u, &s_bar);
+                if (K > 0)
+                    tma_load_1d(s_rnk + size_t(lane) * nwords * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
+                                uint32_t(need) * 4u * K, &s_bar);
             }
         }
+        for (int s = tid; s < cl; s += nthreads) {
+            const int i = c0 + s;
+            uint32_t row = kZeroRow;
+            if (i < len2) {
+                row = symbol_of(P.seq2s[qbeg + i]);
+                if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
+            }
+            s_ro[s] = row * uint32_t(nwords) * 8u;
+        }
         __syncthreads();
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
         if (warp_active) {
             const int groups = cl >> 5;
             for (int g = 0; g < groups; g++) {
@@ -231,19 +235,23 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             }
         }
     }
+    __syncthreads();                         // the window is dead: its front becomes epilogue scratch
+    int64_t* s_ub = reinterpret_cast<int64_t*>(smem) + warp * 1024;
 
     // ---- epilogue: per-offset keys ---------------------------------------------------------------
-    LaneBest mine{ { kKeyNone, 0x7FFFFFFF }, { kKeyNone, 0x7FFFFFFF } };
+    Cand mine{ kKeyNone, 0x7FFFFFFF };       // best resolved (key, offset) of this lane
+    int64_t ub_best = kKeyNone;              // best upper bound among this lane's unresolved offsets
+    uint32_t umask = 0;                      // unresolved offsets of this lane
+    // ranks nranks, nranks-1, .. nranks-K+1 are tracked; anything else is <= floor_rank
+    const int floor_rank = T.nranks - K;
+    const bool floor_none = floor_rank <= 0;                          // nothing below the planes but "no substitute"
+    const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+    const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
     if (warp_active && vmask) {
         // key = len2*k0 + N(b0)*(k1-k0) + N(b1)*(k2-k0) + N(b0&b1)*(k3-k1-k2+k0) + kdiff[rank]
         const int64_t ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
         const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
         const int64_t kbase = int64_t(len2) * T.kcls[0];
-        // ranks nranks, nranks-1, .. nranks-K+1 are tracked; anything else is <= floor
-        const int floor_rank = T.nranks - K;
-        const bool floor_none = floor_rank <= 0;                        // nothing below the planes but "no substitute"
-        const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
-        const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
         int64_t ktop[K > 0 ? K : 1];
 #pragma unroll
         for (int k = 0; k < K; k++) ktop[k] = T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0];
@@ -276,7 +284,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             uint32_t nc, rb;
             if (kSingle) { nc = (v >> (kSingle ? 2 * NB : 0)) & kMask; rb = K > 0 ? (v >> (kSingle ? 3 * NB : 0)) & ((1u << K) - 1u) : 0u; }
             else { nc = m2[tt] & kMask; rb = K > 0 ? (m2[tt] >> NB) & ((1u << K) - 1u) : 0u; }
-            int64_t key = kbase + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
+            const int64_t key = kbase + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
             const int32_t off = int32_t(ln0 + tt);
             if (K > 0 && rb) {
                 // lowest set plane = best rank present
@@ -284,27 +292,82 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 #pragma unroll
                 for (int k = K - 2; k >= 0; k--)
                     if (rb & (1u << k)) d = ktop[k];
-                take(mine.res, key + d, off);
+                take(mine, key + d, off);
             } else if (floor_exact) {
-                if (!floor_none) take(mine.res, key + kfloor, off);
+                if (!floor_none) take(mine, key + kfloor, off);
             } else {
-                take(mine.ub, key + kfloor, off);
+                // best rank unknown (<= floor_rank): remember the bound, settle it below if it matters
+                const int64_t ub = key + kfloor;
+                s_ub[lane * 32 + tt] = ub;
+                umask |= 1u << tt;
+                ub_best = ub > ub_best ? ub : ub_best;
             }
         }
     }
-    mine.res = warp_best(mine.res);
-    mine.ub = warp_best(mine.ub);
-    if (lane == 0) { s_res[warp] = mine.res; s_ub[warp] = mine.ub; }
+
+    if (T.exact) {
+        // Exact order required from this kernel: settle every unresolved offset whose bound could beat the
+        // warp's best resolved key by looking up its true best rank (one pass over the alignment, lanes
+        // striding i).  The counts, hence the key without the difference term, are already exact.
+        Cand wbest = warp_best(mine);
+        if (__any_sync(0xFFFFFFFFu, umask != 0)) {
+            __syncwarp();
+            uint32_t need_bits = 0;
+            for (uint32_t mm = umask; mm; mm &= mm - 1u) {
+                const int tt = __ffs(int(mm)) - 1;
+                if (!better(wbest.key, wbest.off, s_ub[lane * 32 + tt], int32_t(ln0 + tt))) need_bits |= 1u << tt;
+            }
+            uint32_t lanes = __ballot_sync(0xFFFFFFFFu, need_bits != 0);
+            while (lanes) {
+                const int L = __ffs(int(lanes)) - 1;
+                lanes &= lanes - 1u;
+                uint32_t nm = __shfl_sync(0xFFFFFFFFu, need_bits, L);
+                const int64_t l0 = __shfl_sync(0xFFFFFFFFu, ln0, L);
+                while (nm) {
+                    const int tt = __ffs(int(nm)) - 1;
+                    nm &= nm - 1u;
+                    const int64_t ub = s_ub[L * 32 + tt];
+                    const int32_t off = int32_t(l0 + tt);
+                    if (better(wbest.key, wbest.off, ub, off)) continue;      // the bar has moved meanwhile
+                    uint32_t rmax = 0;
+                    for (int i = lane; i < len2; i += 32) {
+                        uint32_t c1 = symbol_of(P.seq1[off + i]), c2 = symbol_of(P.seq2s[qbeg + i]);
+                        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+                        rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
+                    }
+                    rmax = __reduce_max_sync(0xFFFFFFFFu, rmax);
+                    if (rmax) {
+                        const int64_t key = ub - kfloor + T.kdiff[rmax];
+                        if (better(key, off, wbest.key, wbest.off)) { wbest.key = key; wbest.off = off; }
+                    }
+                }
+            }
+        }
+        if (lane == 0) { s_res[warp] = wbest; s_top[warp] = kKeyNone; }
+    } else {
+        // Re-score mode: keys only pre-select; record an upper estimate per 32-offset word for k_finish.
+        const int64_t top = mine.key > ub_best ? mine.key : ub_best;
+        P.lane_keys[int64_t(tile_id) * (G.tile >> 5) + warp * 32 + lane] = top;
+        const Cand wbest = warp_best(mine);
+        int64_t wtop = top;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int64_t o = __shfl_xor_sync(0xFFFFFFFFu, wtop, d);
+            wtop = o > wtop ? o : wtop;
+        }
+        if (lane == 0) { s_res[warp] = wbest; s_top[warp] = wtop; }
+    }
     __syncthreads();
     if (tid == 0) {
-        Cand r = s_res[0], u = s_ub[0];
+        Cand r = s_res[0];
+        int64_t top = s_top[0];
         for (int w = 1; w < warps; w++) {
             take(r, s_res[w].key, s_res[w].off);
-            take(u, s_ub[w].key, s_ub[w].off);
+            top = s_top[w] > top ? s_top[w] : top;
         }
         TileRec rec;
         rec.key = r.key; rec.offset = r.off;
-        rec.ub_key = u.key; rec.ub_offset = u.off;
+        rec.ub_key = top; rec.ub_offset = 0x7FFFFFFF;
         rec.score = 0.0; rec.flags = 0; rec.pad = 0;
         P.tiles[tile_id] = rec;
     }
@@ -314,7 +377,7 @@ template <int NB, int K>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, cudaStream_t stream)
 {
     const int warps = G.tile / 1024;
-    const int nwords = warps * 32 + chunk / 32;
+    const int nwords = round_up4(warps * 32 + chunk / 32);
     const size_t smem = scan_smem_bytes(K, chunk, warps);
     cudaFuncSetAttribute(k_scan<NB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_scan<NB, K><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
@@ -335,14 +398,23 @@ void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
 
 int scan_chunk_steps(int, int64_t max_len2)
 {
-    const int64_t padded = (max_len2 + 31) & ~int64_t(31);
+    const int64_t padded = (max_len2 + 127) & ~int64_t(127);      // multiple of 128: window rows start on 16 bytes
     return int(padded < kScanChunkMax ? padded : kScanChunkMax);
 }
 
 size_t scan_smem_bytes(int rank_planes, int chunk, int warps)
 {
-    const size_t nwords = size_t(warps) * 32 + chunk / 32;
-    return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(chunk) * 4;
+    const size_t nwords = size_t(round_up4(warps * 32 + chunk / 32));
+    const size_t window = size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(chunk) * 4;
+    const size_t scratch = size_t(warps) * 1024 * sizeof(int64_t);
+    return window > scratch ? window : scratch;
+}
+
+int64_t scan_plane_words(int64_t len1)
+{
+    // every window read stays inside the row: last tile start < len1 + 128, + tile + chunk + rounding
+    const int64_t bits = len1 + 128 + kScanTile + kScanChunkMax + 256;
+    return ((bits + 31) / 32 + 3) & ~int64_t(3);
 }
 
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
