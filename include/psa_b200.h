@@ -100,6 +100,28 @@ long long psa_get_stat(const psa_context* ctx, const char* name);
 /* max_len2 sizes the exactness analysis (longest query in the batch). */
 int psa_build_pair_table(const double weights[4], int is_max, long long max_len2, psa_pair_table* out);
 
+/* ---- host-side partitioning (no GPU needed) ------------------------------------------------- */
+
+/* One shard of a batch: queries [q_begin,q_end) over all their offsets (first = last = -1), or -- when
+   the batch is a single query -- that query over absolute offsets [first,last). */
+typedef struct psa_shard {
+    int32_t q_begin, q_end;
+    int64_t first, last;
+} psa_shard;
+
+/* The partition psa_search_batch applies over a context's GPUs, exposed for multi-process callers
+   (one rank per GPU): contiguous query blocks balanced by pair evaluations, or for nq == 1 contiguous
+   offset ranges in whole multiples of `granule` offsets (remainder to the last shard, like the
+   reference's rank split cpu_funcs.c:128-133).  [first,last) restricts a single query (pass -1,-1 for
+   all offsets).  Writes nshards entries; empty shards have q_begin == q_end. */
+int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards, int64_t granule,
+                    int64_t first, int64_t last, psa_shard* out);
+
+/* Merge per-shard answers of ONE query given in ascending offset-range order, under the reference
+   order: strictly better score wins, ties keep the earlier shard = lower offsets
+   (MPI_MAXLOC/MINLOC on (score, rank), cpu_funcs.c:73-76; is_swapable cuda_funcs.cu:290-307). */
+int psa_merge_results(int is_max, const psa_result* parts, int nparts, psa_result* out);
+
 /* ---- the search ---------------------------------------------------------------------------- */
 
 /* Batched search: nq queries against one Seq1 under one (weights, goal).

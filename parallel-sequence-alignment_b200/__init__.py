@@ -64,6 +64,18 @@ class _CPairTable(C.Structure):
                 ("nranks", C.c_int32), ("exact", C.c_int32), ("frac_bits", C.c_int32), ("key_slack", C.c_int64)]
 
 
+class _CShard(C.Structure):
+    _fields_ = [("q_begin", C.c_int32), ("q_end", C.c_int32), ("first", C.c_int64), ("last", C.c_int64)]
+
+
+@dataclass
+class Shard:
+    q_begin: int
+    q_end: int
+    first: int = -1
+    last: int = -1
+
+
 @dataclass
 class Result:
     offset: int
@@ -109,6 +121,9 @@ def _sig():
     _lib.psa_get_stat.restype = C.c_longlong
     _lib.psa_get_stat.argtypes = [C.c_void_p, C.c_char_p]
     _lib.psa_build_pair_table.argtypes = [dp, C.c_int, C.c_longlong, C.POINTER(_CPairTable)]
+    _lib.psa_plan_shards.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                     C.POINTER(_CShard)]
+    _lib.psa_merge_results.argtypes = [C.c_int, C.POINTER(_CResult), C.c_int, C.POINTER(_CResult)]
     batch = [C.c_void_p, dp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     _lib.psa_search_batch.argtypes = batch + [C.POINTER(_CResult)]
     _lib.psa_batch_prepare.argtypes = batch
@@ -171,6 +186,35 @@ def build_pair_table(weights, is_max: bool, max_len2: int = 1) -> PairTable:
         diff=[[t.diff[a][b] for b in range(27)] for a in range(27)],
         rank=[[t.rank[a][b] for b in range(27)] for a in range(27)],
         nranks=t.nranks, exact=bool(t.exact), frac_bits=t.frac_bits, key_slack=t.key_slack)
+
+
+def plan_shards(len1: int, query_lens: Sequence[int], nshards: int, granule: int = 1024,
+                first: int = -1, last: int = -1) -> List[Shard]:
+    """The partition psa_search_batch applies over a context's GPUs (host only, no GPU needed)."""
+    offs = [0]
+    for n in query_lens:
+        offs.append(offs[-1] + int(n))
+    out = (_CShard * nshards)()
+    rc = _lib.psa_plan_shards(len1, (C.c_int64 * len(offs))(*offs), len(query_lens), nshards, granule, first, last, out)
+    if rc:
+        raise PsaError(rc, "psa_plan_shards")
+    return [Shard(o.q_begin, o.q_end, o.first, o.last) for o in out]
+
+
+def merge_results(is_max: bool, parts: Sequence[Result]) -> Result:
+    """Reference-order merge of per-shard answers of one query (shards in ascending offset order)."""
+    arr = (_CResult * len(parts))()
+    for a, p in zip(arr, parts):
+        a.mutant.offset, a.mutant.char_offset = p.offset, p.char_offset
+        a.mutant.ch = p.ch.encode("latin1") if p.ch else b"\x00"
+        a.score, a.rank = p.score, getattr(p, "rank", 0)
+        for k in range(4):
+            a.counts[k] = p.counts[k] if k < len(p.counts) else 0
+    out = _CResult()
+    rc = _lib.psa_merge_results(int(bool(is_max)), arr, len(parts), C.byref(out))
+    if rc:
+        raise PsaError(rc, "psa_merge_results")
+    return _py(out)
 
 
 class PinnedBuffer:

@@ -65,6 +65,7 @@ struct BatchGeom {
     int32_t nq;
     int32_t tile;           // offsets per tile
     int32_t total_tiles;
+    int32_t tiles_per_query;   // > 0 when every query has the same number of tiles (no search needed), else 0
 };
 
 } // namespace psa

@@ -64,8 +64,9 @@ __device__ __forceinline__ double double_from_sortable(int64_t k)
 }
 
 // query that owns global tile id `tile` (tile_start is a non-decreasing prefix sum, nq+1 entries)
-__device__ __forceinline__ int query_of_tile(const int32_t* __restrict__ tile_start, int nq, int tile)
+__device__ __forceinline__ int query_of_tile(const int32_t* __restrict__ tile_start, int nq, int tile, int tiles_per_query)
 {
+    if (tiles_per_query > 0) return tile / tiles_per_query;
     int lo = 0, hi = nq;            // invariant: tile_start[lo] <= tile < tile_start[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;

@@ -66,6 +66,8 @@ struct psa_context {
     bool prepared = false, ran = false;
     bool range_split = false;  // single query split by offset range over the GPUs
     DeviceTable table{};
+    bool table_valid = false;
+    int64_t table_len2 = -1;
     double weights[4] = { 0, 0, 0, 0 };
     int is_max = 0;
     int nq = 0;
@@ -169,13 +171,15 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     int64_t* hq = (int64_t*)d.h_qoff.p;
     int32_t* ht = (int32_t*)d.h_tile_start.p;
     const int64_t byte0 = q_off[q_begin];
-    int64_t tiles = 0;
+    int64_t tiles = 0, uniform = -1;
     for (int k = 0; k < nq; k++) {
         hq[k] = q_off[q_begin + k] - byte0;
         const int64_t len2 = q_off[q_begin + k + 1] - q_off[q_begin + k];
         const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, len2);
         ht[k] = (int32_t)tiles;
-        tiles += (l - tile_base(f) + tile - 1) / tile;
+        const int64_t mine = (l - tile_base(f) + tile - 1) / tile;
+        uniform = k == 0 ? mine : (uniform == mine ? uniform : 0);
+        tiles += mine;
         if (tiles > 0x7FFFFF00) return fail(ctx, PSA_ERR_ARG, "batch too large: more than 2^31 tiles on one GPU");
     }
     hq[nq] = q_off[q_end] - byte0;
@@ -210,6 +214,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.G.nq = nq;
     d.G.tile = tile;
     d.G.total_tiles = (int32_t)tiles;
+    d.G.tiles_per_query = uniform > 0 ? (int32_t)uniform : 0;
     d.P.seq1 = (const uint8_t*)d.seq1.p;
     d.P.seq2s = (const uint8_t*)d.seq2s.p;
     d.P.qoff = (const int64_t*)d.qoff.p;
@@ -385,6 +390,73 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     return -1;
 }
 
+int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards, int64_t granule,
+                    int64_t first, int64_t last, psa_shard* out)
+{
+    if (!q_off || !out || nq < 0 || nshards < 1 || granule < 1 || len1 < 1) return PSA_ERR_ARG;
+    for (int g = 0; g < nshards; g++) out[g] = psa_shard{ 0, 0, -1, -1 };
+    if (nq == 0) return PSA_OK;
+    if (nq == 1) {
+        const int64_t len2 = q_off[1] - q_off[0];
+        if (len2 < 1 || len2 > len1) return PSA_ERR_ARG;
+        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, len2);
+        if (f < 0 || f >= l || l > offsets_of(len1, len2)) return PSA_ERR_ARG;
+        // whole granules from the aligned base, so no shard gets a sliver and plane words stay aligned
+        const int64_t base = tile_base(f);
+        const int64_t ngran = (l - base + granule - 1) / granule;
+        const int use = (int)std::min<int64_t>(nshards, ngran);
+        int64_t t0 = 0;
+        for (int g = 0; g < use; g++) {
+            const int64_t t1 = ngran * (g + 1) / use;
+            out[g].q_begin = 0; out[g].q_end = 1;
+            out[g].first = std::max(f, base + t0 * granule);
+            out[g].last = std::min(l, base + t1 * granule);
+            t0 = t1;
+        }
+        return PSA_OK;
+    }
+    if (last >= 0) return PSA_ERR_ARG;               // an offset range is only defined for one query
+    std::vector<double> work(nq + 1, 0.0);
+    for (int q = 0; q < nq; q++) {
+        const int64_t len2 = q_off[q + 1] - q_off[q];
+        if (len2 < 1 || len2 > len1) return PSA_ERR_ARG;
+        work[q + 1] = work[q] + double(offsets_of(len1, len2)) * double(len2);
+    }
+    int qb = 0;
+    for (int g = 0; g < nshards; g++) {
+        int qe;
+        if (g == nshards - 1) qe = nq;
+        else {
+            const double target = work[nq] * double(g + 1) / double(nshards);
+            qe = int(std::lower_bound(work.begin(), work.end(), target) - work.begin());
+            if (qe > 0 && target - work[qe - 1] < work[std::min(qe, nq)] - target) qe--;     // nearest boundary
+            qe = std::max(qb, std::min(qe, nq));
+        }
+        out[g].q_begin = qb; out[g].q_end = qe;
+        qb = qe;
+    }
+    return PSA_OK;
+}
+
+int psa_merge_results(int is_max, const psa_result* parts, int nparts, psa_result* out)
+{
+    if (!parts || !out || nparts < 1) return PSA_ERR_ARG;
+    bool have = false;
+    psa_result best;
+    std::memset(&best, 0, sizeof(best));
+    for (int k = 0; k < nparts; k++) {
+        const psa_result& cur = parts[k];
+        if (cur.mutant.offset < 0 || cur.mutant.ch == '\0') continue;
+        if (!have || swapable(is_max, best.score, best.mutant.offset, cur.score, cur.mutant.offset)) { best = cur; have = true; }
+    }
+    if (!have) {
+        best.mutant.offset = -1; best.mutant.char_offset = -1; best.mutant.ch = '\0';
+        best.score = is_max ? -INFINITY : INFINITY;
+    }
+    *out = best;
+    return PSA_OK;
+}
+
 static int prepare_common(psa_context* ctx, const double* weights, int is_max, const char* seq1, int64_t len1,
                           const char* seq2s, const int64_t* q_off, int32_t nq, int64_t first, int64_t last)
 {
@@ -405,10 +477,18 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
         if (nq != 1 || first < 0 || first >= last || last > offsets_of(len1, max_len2))
             return fail(ctx, PSA_ERR_ARG, "offset range [%lld,%lld) invalid", (long long)first, (long long)last);
     }
-    int rc = build_tables(weights, is_max, std::max<int64_t>(max_len2, 1), nullptr, &ctx->table);
-    if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
-    std::memcpy(ctx->weights, weights, sizeof(ctx->weights));
-    ctx->is_max = is_max ? 1 : 0;
+    int rc;
+    // the table depends on (weights, goal) and, through the exactness analysis, on the longest query
+    if (!ctx->table_valid || std::memcmp(ctx->weights, weights, sizeof(ctx->weights)) != 0 ||
+        ctx->is_max != (is_max ? 1 : 0) || ctx->table_len2 != max_len2) {
+        ctx->table_valid = false;
+        rc = build_tables(weights, is_max, std::max<int64_t>(max_len2, 1), nullptr, &ctx->table);
+        if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
+        std::memcpy(ctx->weights, weights, sizeof(ctx->weights));
+        ctx->is_max = is_max ? 1 : 0;
+        ctx->table_len2 = max_len2;
+        ctx->table_valid = true;
+    }
     ctx->nq = nq;
     ctx->max_len2 = max_len2;
     ctx->engine = ctx->opt_engine ? ctx->opt_engine : kDefaultEngine;
@@ -434,38 +514,20 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
     for (DeviceState& d : ctx->devs) d.active = false;
     if (nq == 0) { ctx->prepared = true; return PSA_OK; }
 
-    if (nq == 1) {
-        // one query: contiguous offset ranges per GPU (cpu_funcs.c:128-133 with GPUs as ranks),
-        // rounded to whole tiles so no GPU gets a sliver
-        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, max_len2);
-        const int64_t tile = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
-        const int64_t ntiles = (l - tile_base(f) + tile - 1) / tile;
-        const int use = (int)std::min<int64_t>(ndev, ntiles);
-        ctx->range_split = use > 1;
-        int64_t t0 = 0;
-        for (int g = 0; g < use; g++) {
-            const int64_t t1 = ntiles * (g + 1) / use;
-            const int64_t gf = std::max(f, tile_base(f) + t0 * tile), gl = std::min(l, tile_base(f) + t1 * tile);
-            t0 = t1;
-            if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, 0, 1, gf, gl))) return rc;
-        }
-    } else {
-        // many queries: contiguous blocks balanced by pair evaluations
-        std::vector<double> work(nq + 1, 0.0);
-        for (int q = 0; q < nq; q++) work[q + 1] = work[q] + double(offsets_of(len1, ctx->len2s[q])) * double(ctx->len2s[q]);
-        int qb = 0;
-        for (int g = 0; g < ndev; g++) {
-            int qe;
-            if (g == ndev - 1) qe = nq;
-            else {
-                const double target = work[nq] * double(g + 1) / double(ndev);
-                qe = int(std::lower_bound(work.begin(), work.end(), target) - work.begin());
-                qe = std::max(qb, std::min(qe, nq));
-            }
-            if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, qb, qe, -1, -1))) return rc;
-            qb = qe;
-        }
+    const int64_t granule = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
+    std::vector<psa_shard> plan(ndev);
+    if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, plan.data())))
+        return fail(ctx, rc, "cannot partition the batch");
+    int used = 0;
+    for (int g = 0; g < ndev; g++) {
+        const psa_shard& sh = plan[g];
+        if (sh.q_begin == sh.q_end) continue;
+        used++;
+        if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, sh.q_begin, sh.q_end,
+                                 nq == 1 ? sh.first : -1, nq == 1 ? sh.last : -1)))
+            return rc;
     }
+    ctx->range_split = nq == 1 && used > 1;
     ctx->prepared = true;
     return PSA_OK;
 }
@@ -535,22 +597,16 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
     }
     if (bad_symbol) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
 
-    if (ctx->range_split || (ctx->nq == 1)) {
+    if (ctx->nq == 1) {
         // merge the per-GPU candidates of the single query in ascending offset order
-        psa_result best;
-        bool have = false;
+        std::vector<psa_result> parts;
         for (DeviceState& d : ctx->devs) {
             if (!d.active) continue;
             psa_result cur;
             to_result(ctx, ((const QueryRec*)d.h_out.p)[0], &cur);
-            if (cur.mutant.offset < 0) continue;
-            if (!have || swapable(ctx->is_max, best.score, best.mutant.offset, cur.score, cur.mutant.offset)) {
-                best = cur; have = true;
-            }
+            parts.push_back(cur);
         }
-        if (!have) { QueryRec none{}; none.offset = -1; to_result(ctx, none, &best); }
-        out[0] = best;
-        return PSA_OK;
+        return psa_merge_results(ctx->is_max, parts.data(), (int)parts.size(), out);
     }
     for (DeviceState& d : ctx->devs) {
         if (!d.active) continue;

@@ -51,7 +51,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
     __syncthreads();
 
     for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {
-        const int q = query_of_tile(P.tile_start, G.nq, tile_id);
+        const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
         const int t = tile_id - P.tile_start[q];
         const int64_t qbeg = P.qoff[q];
         const int len2 = int(P.qoff[q + 1] - qbeg);

@@ -22,6 +22,9 @@
 #include "psa_device.cuh"
 #include "psa_bitslice.h"
 
+#include <cmath>
+#include <type_traits>
+
 namespace psa {
 
 namespace {
@@ -72,13 +75,12 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 
 // -------------------------------------------------------------------------------------------------
 // One group = 32 alignment steps with compile-time shift amounts 0..31.
-//   pc / pr : this lane's low word in the class / rank window for step 0 of the group
-//   ro      : 32 byte offsets (row * nwords * 8), one per step, warp-uniform
+//   pw : this lane's low word in the staged window for step 0 of the group
+//   ro : 32 byte offsets (row * nwords * 8), one per step, warp-uniform
 // -------------------------------------------------------------------------------------------------
-template <int NUP, int K, bool RANK>
-__device__ __forceinline__ void scan_group(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C,
-                                           uint32_t (&racc)[K > 0 ? K : 1], const char* pc, const char* pr,
-                                           const uint32_t* ro)
+template <int NUP>
+__device__ __forceinline__ void class_group(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, const char* pw,
+                                            const uint32_t* ro)
 {
     uint32_t pa[5], pb[5], pn[5];
 #pragma unroll
@@ -89,37 +91,50 @@ __device__ __forceinline__ void scan_group(VCounter<NUP>& A, VCounter<NUP>& B, V
         for (int u = 0; u < 4; u++) {
             const int s = s4 + u;
             const uint32_t off = offs[u];
-            const uint2 lo = *reinterpret_cast<const uint2*>(pc + off);
+            const uint2 lo = *reinterpret_cast<const uint2*>(pw + off);
             uint32_t x0 = lo.x, x1 = lo.y;
             if (s != 0) {
-                const uint2 hi = *reinterpret_cast<const uint2*>(pc + off + 8);
+                const uint2 hi = *reinterpret_cast<const uint2*>(pw + off + 8);
                 x0 = __funnelshift_r(lo.x, hi.x, s);
                 x1 = __funnelshift_r(lo.y, hi.y, s);
             }
             vc_feed(A, pa, x0, s);
             vc_feed(B, pb, x1, s);
             vc_feed(C, pn, x0 & x1, s);
-            if (RANK) {
-                if (K == 1) {
-                    const uint32_t l = *reinterpret_cast<const uint32_t*>(pr + (off >> 1));
-                    uint32_t x = l;
-                    if (s != 0) x = __funnelshift_r(l, *reinterpret_cast<const uint32_t*>(pr + (off >> 1) + 4), s);
-                    racc[0] |= x;
-                } else if (K == 2) {
-                    const uint2 l = *reinterpret_cast<const uint2*>(pr + off);
-                    uint2 h = l;
-                    if (s != 0) h = *reinterpret_cast<const uint2*>(pr + off + 8);
-                    racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
-                    racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
-                } else if (K == 4) {
-                    const uint4 l = *reinterpret_cast<const uint4*>(pr + (off << 1));
-                    uint4 h = l;
-                    if (s != 0) h = *reinterpret_cast<const uint4*>(pr + (off << 1) + 16);
-                    racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
-                    racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
-                    racc[K > 2 ? 2 : 0] |= s ? __funnelshift_r(l.z, h.z, s) : l.z;
-                    racc[K > 3 ? 3 : 0] |= s ? __funnelshift_r(l.w, h.w, s) : l.w;
-                }
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void rank_group(uint32_t (&racc)[K > 0 ? K : 1], const char* pw, const uint32_t* ro)
+{
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s4 + u;
+            const uint32_t off = offs[u];                 // row * nwords * 8; rank entries are 4*K bytes wide
+            if (K == 1) {
+                const uint32_t l = *reinterpret_cast<const uint32_t*>(pw + (off >> 1));
+                uint32_t x = l;
+                if (s != 0) x = __funnelshift_r(l, *reinterpret_cast<const uint32_t*>(pw + (off >> 1) + 4), s);
+                racc[0] |= x;
+            } else if (K == 2) {
+                const uint2 l = *reinterpret_cast<const uint2*>(pw + off);
+                uint2 h = l;
+                if (s != 0) h = *reinterpret_cast<const uint2*>(pw + off + 8);
+                racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
+                racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
+            } else if (K == 4) {
+                const uint4 l = *reinterpret_cast<const uint4*>(pw + (off << 1));
+                uint4 h = l;
+                if (s != 0) h = *reinterpret_cast<const uint4*>(pw + (off << 1) + 16);
+                racc[0] |= s ? __funnelshift_r(l.x, h.x, s) : l.x;
+                racc[K > 1 ? 1 : 0] |= s ? __funnelshift_r(l.y, h.y, s) : l.y;
+                racc[K > 2 ? 2 : 0] |= s ? __funnelshift_r(l.z, h.z, s) : l.z;
+                racc[K > 3 ? 3 : 0] |= s ? __funnelshift_r(l.w, h.w, s) : l.w;
             }
         }
     }
@@ -133,23 +148,27 @@ __device__ __forceinline__ void take(Cand& c, int64_t key, int32_t off)
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 
 // -------------------------------------------------------------------------------------------------
-// NB : counter planes (len2 < 2^NB), K : rank planes tracked
-// block = warps x 32 threads, tile = warps x 1024 offsets, one block per tile
-// dynamic shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | [chunk] uint32 row offsets;
-// after the main loop the front of it is reused as per-warp scratch (1024 x int64) by the epilogue.
-// The window is filled by TMA bulk copies (one per plane row) that complete on an mbarrier while the
-// block converts its slice of Seq2 into row offsets.
+// NB : counter planes (len2 < 2^NB), K : rank planes tracked, KEY32 : keys fit 26 bits (packed compare)
+// block = warps x 32 threads, tile = warps x 1024 offsets, one block per tile.
+//
+// Two passes over the alignment share one shared-memory window [28 rows][nwords] (+ [chunk] row offsets):
+//   pass R  rank planes ([K] uint32 per word): OR-accumulate until every offset of the block has met the
+//           top rank (a few dozen steps on long queries) -- then the pass stops;
+//   pass C  class planes (uint2 per word): the three vertical counters over all len2 steps.
+// Keeping the passes apart halves the window, which is what bounds the blocks resident per SM.
+// Windows are filled by TMA bulk copies (one per plane row) completing on an mbarrier while the block
+// turns its slice of Seq2 into row offsets.  After the main loops the front of the window is reused as
+// per-warp scratch (1024 x int64) by the epilogue.
 // -------------------------------------------------------------------------------------------------
-template <int NB, int K>
+template <int NB, int K, bool KEY32>
 __global__ void __launch_bounds__(128)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk)
 {
     constexpr int NUP = NB - 5;
     constexpr bool kSingle = 3 * NB + K <= 32;
+    constexpr int kEntry = (4 * K > 8) ? 4 * K : 8;                 // bytes per window word (max of the two passes)
     extern __shared__ __align__(128) unsigned char smem[];
-    uint2* s_cls = reinterpret_cast<uint2*>(smem);
-    uint32_t* s_rnk = reinterpret_cast<uint32_t*>(s_cls + size_t(kPlaneRows) * nwords);
-    uint32_t* s_ro = s_rnk + size_t(kPlaneRows) * nwords * K;
+    uint32_t* s_ro = reinterpret_cast<uint32_t*>(smem + size_t(kPlaneRows) * nwords * kEntry);
     __shared__ Cand s_res[4];
     __shared__ int64_t s_top[4];
     __shared__ uint8_t s_code[kSymbols * kRowPad];
@@ -157,7 +176,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
     const int tile_id = blockIdx.x;
-    const int q = query_of_tile(P.tile_start, G.nq, tile_id);
+    const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
     const int t = tile_id - P.tile_start[q];
     const int64_t qbeg = P.qoff[q];
     const int len2 = int(P.qoff[q + 1] - qbeg);
@@ -182,31 +201,15 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
     const bool warp_active = __any_sync(0xFFFFFFFFu, vmask != 0);
 
-    VCounter<NUP> A, B, C;
-    A.clear(); B.clear(); C.clear();
     uint32_t racc[K > 0 ? K : 1];
 #pragma unroll
     for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
     racc[0] = ~vmask;                       // offsets outside the range count as saturated
-    bool rank_on = K > 0;
     uint32_t parity = 0;
-
     const int steps_total = (len2 + 31) & ~31;
-    for (int c0 = 0; c0 < steps_total; c0 += chunk) {
-        const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
-        const int need = round_up4(warps * 32 + (cl >> 5));         // window words staged (multiple of 4)
-        __syncthreads();                                            // previous window fully consumed / barrier initialised
-        if (warp == 0) {
-            const int64_t g0 = (tb + c0) >> 5;                      // multiple of 4: every row starts on 16 bytes
-            if (lane == 0) mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(need) * uint32_t(8 + 4 * K));
-            __syncwarp();
-            if (lane < kPlaneRows) {
-                tma_load_1d(s_cls + lane * nwords, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(need) * 8u, &s_bar);
-                if (K > 0)
-                    tma_load_1d(s_rnk + size_t(lane) * nwords * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
-                                uint32_t(need) * 4u * K, &s_bar);
-            }
-        }
+
+    // Seq2 slice -> per-step row offsets (row * nwords * 8 bytes); padding steps use the all-zero row
+    auto fill_row_offsets = [&](int c0, int cl) {
         for (int s = tid; s < cl; s += nthreads) {
             const int i = c0 + s;
             uint32_t row = kZeroRow;
@@ -216,23 +219,62 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             }
             s_ro[s] = row * uint32_t(nwords) * 8u;
         }
+    };
+
+    // ---- pass R: best rank per offset -----------------------------------------------------------------
+    if (K > 0) {
+        bool rank_on = warp_active;
+        for (int c0 = 0; c0 < steps_total; c0 += chunk) {
+            const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
+            const int need = round_up4(warps * 32 + (cl >> 5));
+            __syncthreads();                                        // previous window consumed / barrier initialised
+            if (warp == 0) {
+                const int64_t g0 = (tb + c0) >> 5;                  // multiple of 4: every row starts on 16 bytes
+                if (lane == 0) mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(need) * uint32_t(4 * K));
+                __syncwarp();
+                if (lane < kPlaneRows)
+                    tma_load_1d(smem + size_t(lane) * nwords * 4 * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
+                                uint32_t(need) * 4u * K, &s_bar);
+            }
+            fill_row_offsets(c0, cl);
+            __syncthreads();
+            mbar_wait(&s_bar, parity);
+            parity ^= 1u;
+            if (rank_on) {
+                const int groups = cl >> 5;
+                for (int g = 0; g < groups; g++) {
+                    rank_group<K>(racc, reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 4 * K, s_ro + g * 32);
+                    // every offset of the warp carries the top rank: the lower planes and later steps are moot
+                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) { rank_on = false; break; }
+                }
+            }
+            if (__syncthreads_and(!rank_on)) break;                 // the whole block is saturated
+        }
+    }
+
+    // ---- pass C: sign-class counts --------------------------------------------------------------------
+    VCounter<NUP> A, B, C;
+    A.clear(); B.clear(); C.clear();
+    for (int c0 = 0; c0 < steps_total; c0 += chunk) {
+        const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
+        const int need = round_up4(warps * 32 + (cl >> 5));
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t g0 = (tb + c0) >> 5;
+            if (lane == 0) mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(need) * 8u);
+            __syncwarp();
+            if (lane < kPlaneRows)
+                tma_load_1d(smem + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0,
+                            uint32_t(need) * 8u, &s_bar);
+        }
+        fill_row_offsets(c0, cl);
         __syncthreads();
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
         if (warp_active) {
             const int groups = cl >> 5;
-            for (int g = 0; g < groups; g++) {
-                const char* pc = reinterpret_cast<const char*>(s_cls + warp * 32 + lane + g);
-                const char* pr = reinterpret_cast<const char*>(s_rnk + size_t(warp * 32 + lane + g) * K);
-                const uint32_t* ro = s_ro + g * 32;
-                if (rank_on) {
-                    scan_group<NUP, K, true>(A, B, C, racc, pc, pr, ro);
-                    // every offset of the warp already carries the top rank: the lower planes are moot
-                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) rank_on = false;
-                } else {
-                    scan_group<NUP, K, false>(A, B, C, racc, pc, pr, ro);
-                }
-            }
+            for (int g = 0; g < groups; g++)
+                class_group<NUP>(A, B, C, reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 8, s_ro + g * 32);
         }
     }
     __syncthreads();                         // the window is dead: its front becomes epilogue scratch
@@ -249,12 +291,14 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
     if (warp_active && vmask) {
         // key = len2*k0 + N(b0)*(k1-k0) + N(b1)*(k2-k0) + N(b0&b1)*(k3-k1-k2+k0) + kdiff[rank]
-        const int64_t ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
-        const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
-        const int64_t kbase = int64_t(len2) * T.kcls[0];
-        int64_t ktop[K > 0 ? K : 1];
+        using key_t = typename std::conditional<KEY32, int32_t, int64_t>::type;
+        const key_t ka = key_t(T.kcls[1] - T.kcls[0]), kb = key_t(T.kcls[2] - T.kcls[0]);
+        const key_t kc = key_t(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
+        const key_t kbase = key_t(int64_t(len2) * T.kcls[0]);
+        const key_t kfl = key_t(kfloor);
+        key_t ktop[K > 0 ? K : 1];
 #pragma unroll
-        for (int k = 0; k < K; k++) ktop[k] = T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0];
+        for (int k = 0; k < K; k++) ktop[k] = key_t(T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0]);
 
         uint32_t m[32], m2[32];
 #pragma unroll
@@ -276,6 +320,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             transpose32(m2);
         }
         constexpr uint32_t kMask = (1u << NB) - 1u;
+        int32_t packed_best = INT32_MIN;     // KEY32: key * 32 + (31 - tt): one integer max orders (key desc, offset asc)
 #pragma unroll
         for (int tt = 0; tt < 32; tt++) {
             if (!((vmask >> tt) & 1u)) continue;
@@ -284,24 +329,32 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             uint32_t nc, rb;
             if (kSingle) { nc = (v >> (kSingle ? 2 * NB : 0)) & kMask; rb = K > 0 ? (v >> (kSingle ? 3 * NB : 0)) & ((1u << K) - 1u) : 0u; }
             else { nc = m2[tt] & kMask; rb = K > 0 ? (m2[tt] >> NB) & ((1u << K) - 1u) : 0u; }
-            const int64_t key = kbase + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
-            const int32_t off = int32_t(ln0 + tt);
+            const key_t key = kbase + key_t(na) * ka + key_t(nb) * kb + key_t(nc) * kc;
+            bool resolved = true;
+            key_t d = kfl;
             if (K > 0 && rb) {
-                // lowest set plane = best rank present
-                int64_t d = ktop[K > 0 ? K - 1 : 0];
+                d = ktop[K > 0 ? K - 1 : 0];         // lowest set plane = best rank present
 #pragma unroll
                 for (int k = K - 2; k >= 0; k--)
                     if (rb & (1u << k)) d = ktop[k];
-                take(mine, key + d, off);
-            } else if (floor_exact) {
-                if (!floor_none) take(mine, key + kfloor, off);
+            } else {
+                resolved = floor_exact;
+                if (floor_none) continue;            // no mutation possible here
+            }
+            if (resolved) {
+                if (KEY32) packed_best = max(packed_best, int32_t(key + d) * 32 + (31 - tt));
+                else take(mine, int64_t(key + d), int32_t(ln0 + tt));
             } else {
                 // best rank unknown (<= floor_rank): remember the bound, settle it below if it matters
-                const int64_t ub = key + kfloor;
+                const int64_t ub = int64_t(key + d);
                 s_ub[lane * 32 + tt] = ub;
                 umask |= 1u << tt;
                 ub_best = ub > ub_best ? ub : ub_best;
             }
+        }
+        if (KEY32 && packed_best != INT32_MIN) {
+            mine.key = int64_t(packed_best >> 5);
+            mine.off = int32_t(ln0 + 31 - (packed_best & 31));
         }
     }
 
@@ -373,24 +426,45 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
 }
 
-template <int NB, int K>
+// keys fit the packed 32-bit compare of the epilogue when |key| < 2^26
+bool keys_fit_32(const DeviceTable& T, int64_t max_len2)
+{
+    if (!T.exact) return false;
+    double m = 0;
+    for (int c = 0; c < 4; c++) m = fmax(m, fabs(double(T.kcls[c])));
+    double d = 0;
+    for (int r = 0; r <= T.nranks; r++) d = fmax(d, fabs(double(T.kdiff[r])));
+    return m * double(max_len2) * 3.0 + d < 67108864.0 / 2;        // generous: every partial sum stays below 2^25
+}
+
+template <int NB, int K, bool KEY32>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, cudaStream_t stream)
 {
     const int warps = G.tile / 1024;
     const int nwords = round_up4(warps * 32 + chunk / 32);
     const size_t smem = scan_smem_bytes(K, chunk, warps);
-    cudaFuncSetAttribute(k_scan<NB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_scan<NB, K><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
+    cudaFuncSetAttribute(k_scan<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_scan<NB, K, KEY32><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
 }
 
 template <int NB>
-void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, cudaStream_t stream)
+void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool key32,
+                    cudaStream_t stream)
 {
-    switch (K) {
-    case 0: launch_scan_inst<NB, 0>(T, G, P, chunk, stream); break;
-    case 1: launch_scan_inst<NB, 1>(T, G, P, chunk, stream); break;
-    case 2: launch_scan_inst<NB, 2>(T, G, P, chunk, stream); break;
-    default: launch_scan_inst<NB, 4>(T, G, P, chunk, stream); break;
+    if (key32) {
+        switch (K) {
+        case 0: launch_scan_inst<NB, 0, true>(T, G, P, chunk, stream); break;
+        case 1: launch_scan_inst<NB, 1, true>(T, G, P, chunk, stream); break;
+        case 2: launch_scan_inst<NB, 2, true>(T, G, P, chunk, stream); break;
+        default: launch_scan_inst<NB, 4, true>(T, G, P, chunk, stream); break;
+        }
+    } else {
+        switch (K) {
+        case 0: launch_scan_inst<NB, 0, false>(T, G, P, chunk, stream); break;
+        case 1: launch_scan_inst<NB, 1, false>(T, G, P, chunk, stream); break;
+        case 2: launch_scan_inst<NB, 2, false>(T, G, P, chunk, stream); break;
+        default: launch_scan_inst<NB, 4, false>(T, G, P, chunk, stream); break;
+        }
     }
 }
 
@@ -405,7 +479,8 @@ int scan_chunk_steps(int, int64_t max_len2)
 size_t scan_smem_bytes(int rank_planes, int chunk, int warps)
 {
     const size_t nwords = size_t(round_up4(warps * 32 + chunk / 32));
-    const size_t window = size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(chunk) * 4;
+    const size_t entry = 4 * size_t(rank_planes) > 8 ? 4 * size_t(rank_planes) : 8;      // the two passes share the window
+    const size_t window = size_t(kPlaneRows) * nwords * entry + size_t(chunk) * 4;
     const size_t scratch = size_t(warps) * 1024 * sizeof(int64_t);
     return window > scratch ? window : scratch;
 }
@@ -437,9 +512,10 @@ void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, i
 {
     if (G.total_tiles < 1) return;
     const int chunk = scan_chunk_steps(rank_planes, max_len2);
-    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, stream);
-    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, stream);
-    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, stream);
+    const bool key32 = keys_fit_32(T, max_len2);
+    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, key32, stream);
+    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, key32, stream);
+    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, key32, stream);
 }
 
 } // namespace psa
