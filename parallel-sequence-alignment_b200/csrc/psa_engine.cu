@@ -62,6 +62,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
     // current batch
     bool prepared = false, ran = false;
     bool range_split = false;  // single query split by offset range over the GPUs
@@ -74,6 +75,7 @@ struct psa_context {
     int engine = 1;
     int rank_planes = 0;
     int scan_tile = kScanTile;   // offsets per scan tile = 1024 x warps per block
+    bool batch_mode = false;     // scan engine: queries share staged windows (k_scan_batch)
     int64_t max_len2 = 0;
     std::vector<int64_t> len2s;
     // stats of the last run
@@ -146,7 +148,7 @@ int pick_rank_planes(const psa_context* ctx)
     if (avail < 0) avail = 0;
     // offsets the planes leave unresolved are settled inside the scan kernel, so the plane count is a pure
     // speed knob: long queries saturate the top rank within a few dozen steps, short ones benefit from two
-    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : (ctx->max_len2 >= 128 ? 1 : 2);
+    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : (ctx->max_len2 >= 256 ? 1 : ctx->max_len2 >= 128 ? 2 : 4);
     if (want > 2) want = 4;                                          // supported widths: 0,1,2,4
     return std::min(want, std::max(avail, 0));
 }
@@ -239,7 +241,7 @@ int run_device(psa_context* ctx, DeviceState& d)
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
-        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, d.stream);
+        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, d.sm_count, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 2;
     } else {
@@ -372,6 +374,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
     return PSA_ERR_ARG;
 }
@@ -386,6 +389,7 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "engine")) return ctx->engine;
     if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
+    if (!std::strcmp(name, "batch_mode")) return ctx->batch_mode ? 1 : 0;
     if (!std::strcmp(name, "exact")) return ctx->table.exact;
     return -1;
 }
@@ -507,6 +511,14 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
             if (w == kScanWarps || cost < best_cost) { best_cost = cost; best_w = w; }
         }
         ctx->scan_tile = ctx->opt_scan_warps > 0 ? 1024 * ctx->opt_scan_warps : 1024 * best_w;
+        // batch mode (every query fits one window): tiles are single warps that share a staged window
+        BatchGeom probe{};
+        probe.last = last;
+        probe.len1 = len1;
+        probe.nq = (nq + (int)ctx->devs.size() - 1) / (int)ctx->devs.size();
+        ctx->batch_mode = ctx->opt_batch_mode != 0 && (ctx->opt_batch_mode == 1 || ctx->opt_scan_warps == 0) &&
+                          scan_batch_mode(probe, max_len2, ctx->opt_batch_mode == 1 ? 0 : ctx->devs[0].sm_count);
+        if (ctx->batch_mode) ctx->scan_tile = 1024;
     }
 
     const int ndev = (int)ctx->devs.size();

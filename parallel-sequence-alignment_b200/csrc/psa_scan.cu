@@ -147,7 +147,155 @@ __device__ __forceinline__ void take(Cand& c, int64_t key, int32_t off)
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 
+__device__ __forceinline__ uint32_t valid_mask(int64_t ln0, int64_t first, int64_t last)
+{
+    const int64_t lo = first > ln0 ? first - ln0 : 0;
+    const int64_t hi = (last - ln0) < 32 ? (last - ln0) : 32;
+    if (hi <= lo || lo >= 32) return 0u;
+    const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << int(hi)) - 1u);
+    return upto_hi & ~((1u << int(lo)) - 1u);
+}
+
 // -------------------------------------------------------------------------------------------------
+// Epilogue shared by both scan kernels: from the vertical counters of one lane (32 offsets) to per-offset
+// keys.  A 32x32 bit transpose turns plane k / offset t into offset t / bit k; the key of an offset is
+//   key = len2*k0 + N(b0)*(k1-k0) + N(b1)*(k2-k0) + N(b0&b1)*(k3-k1-k2+k0) + kdiff[rank]
+// Offsets that met none of the K tracked rank planes only get an upper bound (kdiff[floor_rank]).
+// -------------------------------------------------------------------------------------------------
+template <int NB, int K, bool KEY32>
+struct OffsetKeys {
+    static constexpr bool kSingle = 3 * NB + K <= 32;
+    using key_t = typename std::conditional<KEY32, int32_t, int64_t>::type;
+    uint32_t m[32], m2[kSingle ? 1 : 32];
+    key_t ka, kb, kc, kbase, kfl, ktop[K > 0 ? K : 1];
+    bool floor_none, floor_exact;
+
+    template <int NUP>
+    __device__ __forceinline__ void build(const DeviceTable& T, int len2, const VCounter<NUP>& A, const VCounter<NUP>& B,
+                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1])
+    {
+        ka = key_t(T.kcls[1] - T.kcls[0]);
+        kb = key_t(T.kcls[2] - T.kcls[0]);
+        kc = key_t(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
+        kbase = key_t(int64_t(len2) * T.kcls[0]);
+        // ranks nranks, nranks-1, .. nranks-K+1 are tracked; anything else is <= floor_rank
+        const int floor_rank = T.nranks - K;
+        floor_none = floor_rank <= 0;                                  // nothing below the planes but "no substitute"
+        floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+        kfl = floor_none ? key_t(0) : key_t(T.kdiff[floor_rank]);
+#pragma unroll
+        for (int k = 0; k < K; k++) ktop[k] = key_t(T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0]);
+#pragma unroll
+        for (int k = 0; k < 32; k++) m[k] = 0;
+#pragma unroll
+        for (int k = 0; k < NB; k++) { m[k] = A.plane(k); m[NB + k] = B.plane(k); }
+        if (kSingle) {
+#pragma unroll
+            for (int k = 0; k < NB; k++) m[(kSingle ? 2 * NB : 0) + k] = C.plane(k);
+#pragma unroll
+            for (int k = 0; k < K; k++) m[(kSingle ? 3 * NB : 0) + k] = racc[k];
+            transpose32(m);
+        } else {
+            uint32_t (&mm)[32] = reinterpret_cast<uint32_t (&)[32]>(m2);
+#pragma unroll
+            for (int k = 0; k < 32; k++) mm[k] = 0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) mm[k] = C.plane(k);
+#pragma unroll
+            for (int k = 0; k < K; k++) mm[NB + k] = racc[k];
+            transpose32(m);
+            transpose32(mm);
+        }
+    }
+
+    // Visit the offsets in `mask`: resolved ones compete for `res`, unresolved ones for `ub` and are
+    // reported in the returned mask.  (key desc, offset asc) order in both.
+    __device__ __forceinline__ uint32_t scan(uint32_t mask, int64_t ln0, Cand& res, Cand& ub) const
+    {
+        constexpr uint32_t kMask = (1u << NB) - 1u;
+        uint32_t unresolved = 0;
+        int32_t pres = INT32_MIN, pub = INT32_MIN;      // KEY32: key * 32 + (31 - t): one integer max orders (key desc, offset asc)
+#pragma unroll
+        for (int tt = 0; tt < 32; tt++) {
+            if (!((mask >> tt) & 1u)) continue;
+            const uint32_t v = m[tt];
+            const uint32_t na = v & kMask, nb = (v >> NB) & kMask;
+            uint32_t nc, rb;
+            if (kSingle) { nc = (v >> (kSingle ? 2 * NB : 0)) & kMask; rb = K > 0 ? (v >> (kSingle ? 3 * NB : 0)) & ((1u << K) - 1u) : 0u; }
+            else { nc = m2[kSingle ? 0 : tt] & kMask; rb = K > 0 ? (m2[kSingle ? 0 : tt] >> NB) & ((1u << K) - 1u) : 0u; }
+            const key_t key = kbase + key_t(na) * ka + key_t(nb) * kb + key_t(nc) * kc;
+            bool resolved = true;
+            key_t d = kfl;
+            if (K > 0 && rb) {
+                d = ktop[K > 0 ? K - 1 : 0];            // lowest set plane = best rank present
+#pragma unroll
+                for (int k = K - 2; k >= 0; k--)
+                    if (rb & (1u << k)) d = ktop[k];
+            } else {
+                if (floor_none) continue;               // no mutation possible at this offset
+                resolved = floor_exact;
+            }
+            if (resolved) {
+                if (KEY32) pres = max(pres, int32_t(key + d) * 32 + (31 - tt));
+                else take(res, int64_t(key + d), int32_t(ln0 + tt));
+            } else {
+                unresolved |= 1u << tt;
+                if (KEY32) pub = max(pub, int32_t(key + d) * 32 + (31 - tt));
+                else take(ub, int64_t(key + d), int32_t(ln0 + tt));
+            }
+        }
+        if (KEY32) {
+            if (pres != INT32_MIN) take(res, int64_t(pres >> 5), int32_t(ln0 + 31 - (pres & 31)));
+            if (pub != INT32_MIN) take(ub, int64_t(pub >> 5), int32_t(ln0 + 31 - (pub & 31)));
+        }
+        return unresolved;
+    }
+};
+
+// Exact order is required from the scan in exact mode: settle every unresolved offset whose bound could
+// beat the warp's best resolved key by looking up its true best rank (one pass over the alignment, lanes
+// striding i; the counts, hence the key without the difference term, are already exact).  Returns the
+// warp's exact best.  All 32 lanes must call.
+template <int NB, int K, bool KEY32>
+__device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_code,
+                                                  const OffsetKeys<NB, K, KEY32>& keys, Cand mine, Cand ub, uint32_t umask,
+                                                  int64_t ln0, int64_t qbeg, int len2)
+{
+    Cand wbest = warp_best(mine);
+    if (!__any_sync(0xFFFFFFFFu, umask != 0)) return wbest;
+    uint32_t settled = 0;
+    const int64_t kfloor = int64_t(keys.kfl);
+    for (;;) {
+        const bool could_win = ub.key != kKeyNone && !better(wbest.key, wbest.off, ub.key, ub.off);
+        const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, could_win);
+        if (!lanes) break;
+        const int L = __ffs(int(lanes)) - 1;
+        const int64_t ukey = __shfl_sync(0xFFFFFFFFu, ub.key, L);
+        const int32_t off = __shfl_sync(0xFFFFFFFFu, ub.off, L);
+        uint32_t rmax = 0;
+        for (int i = int(threadIdx.x & 31); i < len2; i += 32) {
+            uint32_t c1 = symbol_of(P.seq1[off + i]), c2 = symbol_of(P.seq2s[qbeg + i]);
+            if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+            rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
+        }
+        rmax = __reduce_max_sync(0xFFFFFFFFu, rmax);
+        if (rmax) {
+            const int64_t key = ukey - kfloor + T.kdiff[rmax];
+            if (better(key, off, wbest.key, wbest.off)) { wbest.key = key; wbest.off = off; }
+        }
+        if (int(threadIdx.x & 31) == L) {
+            // this lane's next-best unresolved offset
+            settled |= 1u << int(int64_t(off) - ln0);
+            Cand unused{ kKeyNone, 0x7FFFFFFF };
+            ub = Cand{ kKeyNone, 0x7FFFFFFF };
+            keys.scan(umask & ~settled, ln0, unused, ub);
+        }
+    }
+    return wbest;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_scan (long mode: one query tile per block, len2 of any size up to 32767)
 // NB : counter planes (len2 < 2^NB), K : rank planes tracked, KEY32 : keys fit 26 bits (packed compare)
 // block = warps x 32 threads, tile = warps x 1024 offsets, one block per tile.
 //
@@ -155,17 +303,14 @@ __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 //   pass R  rank planes ([K] uint32 per word): OR-accumulate until every offset of the block has met the
 //           top rank (a few dozen steps on long queries) -- then the pass stops;
 //   pass C  class planes (uint2 per word): the three vertical counters over all len2 steps.
-// Keeping the passes apart halves the window, which is what bounds the blocks resident per SM.
 // Windows are filled by TMA bulk copies (one per plane row) completing on an mbarrier while the block
-// turns its slice of Seq2 into row offsets.  After the main loops the front of the window is reused as
-// per-warp scratch (1024 x int64) by the epilogue.
+// turns its slice of Seq2 into row offsets.
 // -------------------------------------------------------------------------------------------------
 template <int NB, int K, bool KEY32>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk)
 {
     constexpr int NUP = NB - 5;
-    constexpr bool kSingle = 3 * NB + K <= 32;
     constexpr int kEntry = (4 * K > 8) ? 4 * K : 8;                 // bytes per window word (max of the two passes)
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* s_ro = reinterpret_cast<uint32_t*>(smem + size_t(kPlaneRows) * nwords * kEntry);
@@ -176,6 +321,8 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
     const int tile_id = blockIdx.x;
+    if (T.exact)            // only the settle path reads it
+        for (int k = tid; k < kSymbols * kRowPad; k += nthreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
     const int t = tile_id - P.tile_start[q];
     const int64_t qbeg = P.qoff[q];
@@ -186,19 +333,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     const int64_t ln0 = tb + warp * 1024 + lane * 32;               // this lane's first offset
 
     if (tid == 0) mbar_init(&s_bar, 1);
-    for (int k = tid; k < kSymbols * kRowPad; k += nthreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
-
-    // valid offsets of this lane as a bit mask
-    uint32_t vmask = 0;
-    {
-        const int64_t lo = first > ln0 ? first - ln0 : 0;
-        const int64_t hi = (last - ln0) < 32 ? (last - ln0) : 32;
-        if (hi > lo && lo < 32) {
-            const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << int(hi)) - 1u);
-            const uint32_t below_lo = (1u << int(lo)) - 1u;
-            vmask = upto_hi & ~below_lo;
-        }
-    }
+    const uint32_t vmask = valid_mask(ln0, first, last);
     const bool warp_active = __any_sync(0xFFFFFFFFu, vmask != 0);
 
     uint32_t racc[K > 0 ? K : 1];
@@ -277,129 +412,22 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
                 class_group<NUP>(A, B, C, reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 8, s_ro + g * 32);
         }
     }
-    __syncthreads();                         // the window is dead: its front becomes epilogue scratch
-    int64_t* s_ub = reinterpret_cast<int64_t*>(smem) + warp * 1024;
 
-    // ---- epilogue: per-offset keys ---------------------------------------------------------------
-    Cand mine{ kKeyNone, 0x7FFFFFFF };       // best resolved (key, offset) of this lane
-    int64_t ub_best = kKeyNone;              // best upper bound among this lane's unresolved offsets
-    uint32_t umask = 0;                      // unresolved offsets of this lane
-    // ranks nranks, nranks-1, .. nranks-K+1 are tracked; anything else is <= floor_rank
-    const int floor_rank = T.nranks - K;
-    const bool floor_none = floor_rank <= 0;                          // nothing below the planes but "no substitute"
-    const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
-    const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
-    if (warp_active && vmask) {
-        // key = len2*k0 + N(b0)*(k1-k0) + N(b1)*(k2-k0) + N(b0&b1)*(k3-k1-k2+k0) + kdiff[rank]
-        using key_t = typename std::conditional<KEY32, int32_t, int64_t>::type;
-        const key_t ka = key_t(T.kcls[1] - T.kcls[0]), kb = key_t(T.kcls[2] - T.kcls[0]);
-        const key_t kc = key_t(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
-        const key_t kbase = key_t(int64_t(len2) * T.kcls[0]);
-        const key_t kfl = key_t(kfloor);
-        key_t ktop[K > 0 ? K : 1];
-#pragma unroll
-        for (int k = 0; k < K; k++) ktop[k] = key_t(T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0]);
-
-        uint32_t m[32], m2[32];
-#pragma unroll
-        for (int k = 0; k < 32; k++) { m[k] = 0; m2[k] = 0; }
-#pragma unroll
-        for (int k = 0; k < NB; k++) { m[k] = A.plane(k); m[NB + k] = B.plane(k); }
-        if (kSingle) {
-#pragma unroll
-            for (int k = 0; k < NB; k++) m[2 * NB + k] = C.plane(k);
-#pragma unroll
-            for (int k = 0; k < K; k++) m[3 * NB + k] = racc[k];
-            transpose32(m);
-        } else {
-#pragma unroll
-            for (int k = 0; k < NB; k++) m2[k] = C.plane(k);
-#pragma unroll
-            for (int k = 0; k < K; k++) m2[NB + k] = racc[k];
-            transpose32(m);
-            transpose32(m2);
-        }
-        constexpr uint32_t kMask = (1u << NB) - 1u;
-        int32_t packed_best = INT32_MIN;     // KEY32: key * 32 + (31 - tt): one integer max orders (key desc, offset asc)
-#pragma unroll
-        for (int tt = 0; tt < 32; tt++) {
-            if (!((vmask >> tt) & 1u)) continue;
-            const uint32_t v = m[tt];
-            const uint32_t na = v & kMask, nb = (v >> NB) & kMask;
-            uint32_t nc, rb;
-            if (kSingle) { nc = (v >> (kSingle ? 2 * NB : 0)) & kMask; rb = K > 0 ? (v >> (kSingle ? 3 * NB : 0)) & ((1u << K) - 1u) : 0u; }
-            else { nc = m2[tt] & kMask; rb = K > 0 ? (m2[tt] >> NB) & ((1u << K) - 1u) : 0u; }
-            const key_t key = kbase + key_t(na) * ka + key_t(nb) * kb + key_t(nc) * kc;
-            bool resolved = true;
-            key_t d = kfl;
-            if (K > 0 && rb) {
-                d = ktop[K > 0 ? K - 1 : 0];         // lowest set plane = best rank present
-#pragma unroll
-                for (int k = K - 2; k >= 0; k--)
-                    if (rb & (1u << k)) d = ktop[k];
-            } else {
-                resolved = floor_exact;
-                if (floor_none) continue;            // no mutation possible here
-            }
-            if (resolved) {
-                if (KEY32) packed_best = max(packed_best, int32_t(key + d) * 32 + (31 - tt));
-                else take(mine, int64_t(key + d), int32_t(ln0 + tt));
-            } else {
-                // best rank unknown (<= floor_rank): remember the bound, settle it below if it matters
-                const int64_t ub = int64_t(key + d);
-                s_ub[lane * 32 + tt] = ub;
-                umask |= 1u << tt;
-                ub_best = ub > ub_best ? ub : ub_best;
-            }
-        }
-        if (KEY32 && packed_best != INT32_MIN) {
-            mine.key = int64_t(packed_best >> 5);
-            mine.off = int32_t(ln0 + 31 - (packed_best & 31));
-        }
+    // ---- epilogue -------------------------------------------------------------------------------------
+    Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
+    uint32_t umask = 0;
+    OffsetKeys<NB, K, KEY32> keys;
+    if (warp_active) {
+        keys.build(T, len2, A, B, C, racc);
+        umask = keys.scan(vmask, ln0, mine, ub);
     }
-
     if (T.exact) {
-        // Exact order required from this kernel: settle every unresolved offset whose bound could beat the
-        // warp's best resolved key by looking up its true best rank (one pass over the alignment, lanes
-        // striding i).  The counts, hence the key without the difference term, are already exact.
-        Cand wbest = warp_best(mine);
-        if (__any_sync(0xFFFFFFFFu, umask != 0)) {
-            __syncwarp();
-            uint32_t need_bits = 0;
-            for (uint32_t mm = umask; mm; mm &= mm - 1u) {
-                const int tt = __ffs(int(mm)) - 1;
-                if (!better(wbest.key, wbest.off, s_ub[lane * 32 + tt], int32_t(ln0 + tt))) need_bits |= 1u << tt;
-            }
-            uint32_t lanes = __ballot_sync(0xFFFFFFFFu, need_bits != 0);
-            while (lanes) {
-                const int L = __ffs(int(lanes)) - 1;
-                lanes &= lanes - 1u;
-                uint32_t nm = __shfl_sync(0xFFFFFFFFu, need_bits, L);
-                const int64_t l0 = __shfl_sync(0xFFFFFFFFu, ln0, L);
-                while (nm) {
-                    const int tt = __ffs(int(nm)) - 1;
-                    nm &= nm - 1u;
-                    const int64_t ub = s_ub[L * 32 + tt];
-                    const int32_t off = int32_t(l0 + tt);
-                    if (better(wbest.key, wbest.off, ub, off)) continue;      // the bar has moved meanwhile
-                    uint32_t rmax = 0;
-                    for (int i = lane; i < len2; i += 32) {
-                        uint32_t c1 = symbol_of(P.seq1[off + i]), c2 = symbol_of(P.seq2s[qbeg + i]);
-                        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-                        rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
-                    }
-                    rmax = __reduce_max_sync(0xFFFFFFFFu, rmax);
-                    if (rmax) {
-                        const int64_t key = ub - kfloor + T.kdiff[rmax];
-                        if (better(key, off, wbest.key, wbest.off)) { wbest.key = key; wbest.off = off; }
-                    }
-                }
-            }
-        }
+        Cand wbest{ kKeyNone, 0x7FFFFFFF };
+        if (warp_active) wbest = settle_unresolved(T, P, s_code, keys, mine, ub, umask, ln0, qbeg, len2);
         if (lane == 0) { s_res[warp] = wbest; s_top[warp] = kKeyNone; }
     } else {
         // Re-score mode: keys only pre-select; record an upper estimate per 32-offset word for k_finish.
-        const int64_t top = mine.key > ub_best ? mine.key : ub_best;
+        const int64_t top = mine.key > ub.key ? mine.key : ub.key;
         P.lane_keys[int64_t(tile_id) * (G.tile >> 5) + warp * 32 + lane] = top;
         const Cand wbest = warp_best(mine);
         int64_t wtop = top;
@@ -426,6 +454,115 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_scan_batch (batch mode: every query fits one window, len2 <= 1023)
+// The bit-plane window of a tile depends only on the offsets, not on the query, so a block stages the
+// windows of ONE 1024-offset tile once (class + rank planes, TMA) and then each of its warps walks its own
+// queries against them: no block-wide barrier after the staging, warps drift apart freely, and the L2 -> SM
+// traffic per pair evaluation drops by the number of queries per block.
+//   grid = (query groups, offset tiles); warp w of block (g, t) handles queries g*qpb + w, + warps, ...
+//   shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | per warp [chunk] uint32 row offsets
+// One TileRec per (query, tile) is written by the warp that computed it.
+// -------------------------------------------------------------------------------------------------
+template <int NB, int K, bool KEY32>
+__global__ void __launch_bounds__(128, 4)
+k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
+             const int queries_per_block)
+{
+    constexpr int NUP = NB - 5;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_cls = smem;
+    unsigned char* s_rnk = smem + size_t(kPlaneRows) * nwords * 8;
+    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + size_t(kPlaneRows) * nwords * 4 * K);
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+    uint32_t* s_ro = s_ro_all + size_t(warp) * chunk;
+    const int tile = blockIdx.y;
+    const int64_t tb = int64_t(tile) * 1024;                        // batch mode always scans from offset 0
+    const int64_t ln0 = tb + lane * 32;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(nwords) * uint32_t(8 + 4 * K));
+    }
+    if (T.exact)
+        for (int k = tid; k < kSymbols * kRowPad; k += blockDim.x) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    __syncthreads();
+    if (warp == 0 && lane < kPlaneRows) {
+        const int64_t g0 = tb >> 5;
+        tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(nwords) * 8u, &s_bar);
+        if (K > 0)
+            tma_load_1d(s_rnk + size_t(lane) * nwords * 4 * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
+                        uint32_t(nwords) * 4u * K, &s_bar);
+    }
+    bool staged = false;
+
+    const int q_begin = blockIdx.x * queries_per_block;
+    const int q_end = (q_begin + queries_per_block) < G.nq ? (q_begin + queries_per_block) : G.nq;
+    for (int q = q_begin + warp; q < q_end; q += warps) {
+        const int64_t qbeg = P.qoff[q];
+        const int len2 = int(P.qoff[q + 1] - qbeg);
+        const int64_t last = G.len1 - len2 + 1;
+        if (tb >= last) continue;                                   // this query does not reach the tile
+        const uint32_t vmask = valid_mask(ln0, 0, last);
+        const int steps_total = (len2 + 31) & ~31;
+        __syncwarp();                                               // previous query's row offsets are no longer read
+        for (int s = lane; s < steps_total; s += 32) {
+            uint32_t row = kZeroRow;
+            if (s < len2) {
+                row = symbol_of(P.seq2s[qbeg + s]);
+                if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
+            }
+            s_ro[s] = row * uint32_t(nwords) * 8u;
+        }
+        __syncwarp();
+        if (!staged) { mbar_wait(&s_bar, 0); staged = true; }
+
+        uint32_t racc[K > 0 ? K : 1];
+#pragma unroll
+        for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
+        racc[0] = ~vmask;
+        const int groups = steps_total >> 5;
+        if (K > 0) {
+            for (int g = 0; g < groups; g++) {
+                rank_group<K>(racc, reinterpret_cast<const char*>(s_rnk) + size_t(lane + g) * 4 * K, s_ro + g * 32);
+                if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+            }
+        }
+        VCounter<NUP> A, B, C;
+        A.clear(); B.clear(); C.clear();
+        for (int g = 0; g < groups; g++)
+            class_group<NUP>(A, B, C, reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8, s_ro + g * 32);
+
+        Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
+        OffsetKeys<NB, K, KEY32> keys;
+        keys.build(T, len2, A, B, C, racc);
+        const uint32_t umask = keys.scan(vmask, ln0, mine, ub);
+        const int rec_id = P.tile_start[q] + tile;
+        TileRec rec;
+        rec.score = 0.0; rec.flags = 0; rec.pad = 0; rec.ub_offset = 0x7FFFFFFF;
+        if (T.exact) {
+            const Cand wbest = settle_unresolved(T, P, s_code, keys, mine, ub, umask, ln0, qbeg, len2);
+            rec.key = wbest.key; rec.offset = wbest.off; rec.ub_key = kKeyNone;
+        } else {
+            const int64_t top = mine.key > ub.key ? mine.key : ub.key;
+            P.lane_keys[int64_t(rec_id) * 32 + lane] = top;
+            const Cand wbest = warp_best(mine);
+            int64_t wtop = top;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const int64_t o = __shfl_xor_sync(0xFFFFFFFFu, wtop, d);
+                wtop = o > wtop ? o : wtop;
+            }
+            rec.key = wbest.key; rec.offset = wbest.off; rec.ub_key = wtop;
+        }
+        if (lane == 0) P.tiles[rec_id] = rec;
+    }
+    if (!staged) mbar_wait(&s_bar, 0);      // never leave with a bulk copy in flight
+}
+
 // keys fit the packed 32-bit compare of the epilogue when |key| < 2^26
 bool keys_fit_32(const DeviceTable& T, int64_t max_len2)
 {
@@ -437,33 +574,55 @@ bool keys_fit_32(const DeviceTable& T, int64_t max_len2)
     return m * double(max_len2) * 3.0 + d < 67108864.0 / 2;        // generous: every partial sum stays below 2^25
 }
 
-template <int NB, int K, bool KEY32>
-void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, cudaStream_t stream)
+size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
 {
-    const int warps = G.tile / 1024;
-    const int nwords = round_up4(warps * 32 + chunk / 32);
-    const size_t smem = scan_smem_bytes(K, chunk, warps);
-    cudaFuncSetAttribute(k_scan<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_scan<NB, K, KEY32><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
+    const size_t nwords = size_t(round_up4(32 + chunk / 32));
+    return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(warps) * chunk * 4;
+}
+
+template <int NB, int K, bool KEY32>
+void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, bool batch, int sm_count,
+                      cudaStream_t stream)
+{
+    if (batch) {
+        const int warps = 4;
+        const int nwords = round_up4(32 + chunk / 32);
+        const size_t smem = batch_smem_bytes(K, chunk, warps);
+        const int tiles = int((G.len1 + 1023) / 1024);              // upper bound: tiles past a query's last offset are skipped
+        // about 8 blocks per SM in flight over the whole launch; more queries per block = better use of a staged window
+        int64_t qpb = (int64_t(G.nq) * tiles + int64_t(sm_count) * 8 - 1) / (int64_t(sm_count) * 8);
+        qpb = ((qpb + warps - 1) / warps) * warps;
+        if (qpb < warps) qpb = warps;
+        if (qpb > 4096) qpb = 4096;
+        dim3 grid((G.nq + qpb - 1) / qpb, tiles);
+        cudaFuncSetAttribute(k_scan_batch<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_scan_batch<NB, K, KEY32><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb));
+    } else {
+        const int warps = G.tile / 1024;
+        const int nwords = round_up4(warps * 32 + chunk / 32);
+        const size_t smem = scan_smem_bytes(K, chunk, warps);
+        cudaFuncSetAttribute(k_scan<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_scan<NB, K, KEY32><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
+    }
 }
 
 template <int NB>
-void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool key32,
-                    cudaStream_t stream)
+void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool key32, bool batch,
+                    int sm_count, cudaStream_t stream)
 {
     if (key32) {
         switch (K) {
-        case 0: launch_scan_inst<NB, 0, true>(T, G, P, chunk, stream); break;
-        case 1: launch_scan_inst<NB, 1, true>(T, G, P, chunk, stream); break;
-        case 2: launch_scan_inst<NB, 2, true>(T, G, P, chunk, stream); break;
-        default: launch_scan_inst<NB, 4, true>(T, G, P, chunk, stream); break;
+        case 0: launch_scan_inst<NB, 0, true>(T, G, P, chunk, batch, sm_count, stream); break;
+        case 1: launch_scan_inst<NB, 1, true>(T, G, P, chunk, batch, sm_count, stream); break;
+        case 2: launch_scan_inst<NB, 2, true>(T, G, P, chunk, batch, sm_count, stream); break;
+        default: launch_scan_inst<NB, 4, true>(T, G, P, chunk, batch, sm_count, stream); break;
         }
     } else {
         switch (K) {
-        case 0: launch_scan_inst<NB, 0, false>(T, G, P, chunk, stream); break;
-        case 1: launch_scan_inst<NB, 1, false>(T, G, P, chunk, stream); break;
-        case 2: launch_scan_inst<NB, 2, false>(T, G, P, chunk, stream); break;
-        default: launch_scan_inst<NB, 4, false>(T, G, P, chunk, stream); break;
+        case 0: launch_scan_inst<NB, 0, false>(T, G, P, chunk, batch, sm_count, stream); break;
+        case 1: launch_scan_inst<NB, 1, false>(T, G, P, chunk, batch, sm_count, stream); break;
+        case 2: launch_scan_inst<NB, 2, false>(T, G, P, chunk, batch, sm_count, stream); break;
+        default: launch_scan_inst<NB, 4, false>(T, G, P, chunk, batch, sm_count, stream); break;
         }
     }
 }
@@ -476,13 +635,19 @@ int scan_chunk_steps(int, int64_t max_len2)
     return int(padded < kScanChunkMax ? padded : kScanChunkMax);
 }
 
+// batch mode: every query of the batch fits one staged window and no offset range is imposed
+// and there are enough (query, tile) tasks that sharing a staged window among the queries of a block pays off
+bool scan_batch_mode(const BatchGeom& G, int64_t max_len2, int sm_count)
+{
+    const int64_t tasks = int64_t(G.nq) * ((G.len1 + 1023) / 1024);
+    return max_len2 <= 1023 && G.last < 0 && tasks >= int64_t(sm_count) * 64;
+}
+
 size_t scan_smem_bytes(int rank_planes, int chunk, int warps)
 {
     const size_t nwords = size_t(round_up4(warps * 32 + chunk / 32));
     const size_t entry = 4 * size_t(rank_planes) > 8 ? 4 * size_t(rank_planes) : 8;      // the two passes share the window
-    const size_t window = size_t(kPlaneRows) * nwords * entry + size_t(chunk) * 4;
-    const size_t scratch = size_t(warps) * 1024 * sizeof(int64_t);
-    return window > scratch ? window : scratch;
+    return size_t(kPlaneRows) * nwords * entry + size_t(chunk) * 4;
 }
 
 int64_t scan_plane_words(int64_t len1)
@@ -507,15 +672,16 @@ void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
     }
 }
 
-void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
-                 cudaStream_t stream)
+void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2, bool batch,
+                 int sm_count, cudaStream_t stream)
 {
     if (G.total_tiles < 1) return;
     const int chunk = scan_chunk_steps(rank_planes, max_len2);
     const bool key32 = keys_fit_32(T, max_len2);
-    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, key32, stream);
-    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, key32, stream);
-    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, key32, stream);
+    batch = batch && max_len2 <= 1023 && G.last < 0 && G.tile == 1024;
+    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
+    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
+    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
 }
 
 } // namespace psa

@@ -12,16 +12,21 @@ pytestmark = pytest.mark.gpu
 ALPHA = [chr(65 + i) for i in range(26)] + ["-"]
 # (engine, rank planes, warps per block): the scalar engine, and the bit-sliced scan with every plane count
 # (0 planes = every offset unresolved -> the select + exact-candidate path carries the result)
-ENGINES = [(1, -1, 0), (2, -1, 0), (2, 0, 1), (2, 1, 2), (2, 4, 3), (2, 2, 4)]
+# (engine, rank planes, warps per block, batch mode): the scalar engine, and the bit-sliced scan with every plane
+# count (0 planes = every offset unresolved -> the in-kernel settle path carries the result), both tile shapes
+ENGINES = [(1, -1, 0, -1), (2, -1, 0, -1), (2, 0, 1, 0), (2, 1, 2, 0), (2, 4, 3, 0), (2, 2, 4, 0), (2, 0, 0, 1), (2, 2, 0, 1),
+           (2, 4, 0, 1)]
 
 
-def _set_engine(ctx, engine, planes=-1, warps=0):
+def _set_engine(ctx, engine, planes=-1, warps=0, batch=-1):
     ctx.set_option("engine", engine)
     ctx.set_option("rank_planes", planes)
     ctx.set_option("scan_warps", warps)
+    ctx.set_option("batch_mode", batch)
 
 
-@pytest.fixture(params=ENGINES, ids=["scalar", "scan", "scan-k0-w1", "scan-k1-w2", "scan-k4-w3", "scan-k2-w4"])
+@pytest.fixture(params=ENGINES, ids=["scalar", "scan", "scan-k0-w1", "scan-k1-w2", "scan-k4-w3", "scan-k2-w4", "batch-k0",
+                                     "batch-k2", "batch-k4"])
 def engine(request, ctx):
     _set_engine(ctx, *request.param)
     yield request.param[0]
