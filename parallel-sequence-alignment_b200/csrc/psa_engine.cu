@@ -62,6 +62,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
     int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
     // current batch
     bool prepared = false, ran = false;
@@ -241,7 +242,7 @@ int run_device(psa_context* ctx, DeviceState& d)
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
-        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, d.sm_count, d.stream);
+        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, ctx->opt_sliced_keys != 0, d.sm_count, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 2;
     } else {
@@ -374,6 +375,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
     return PSA_ERR_ARG;

@@ -39,7 +39,7 @@ void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
                     cudaStream_t stream);
 // bit-sliced scan of every tile
 void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
-                 bool batch, int sm_count, cudaStream_t stream);
+                 bool batch, bool sliced_keys_ok, int sm_count, cudaStream_t stream);
 // batch mode (window shared by many queries, tile = 1024) applies when every query fits one window
 bool scan_batch_mode(const BatchGeom& G, int64_t max_len2, int sm_count);
 

@@ -22,6 +22,7 @@
 #include "psa_device.cuh"
 #include "psa_bitslice.h"
 
+#include <algorithm>
 #include <cmath>
 #include <type_traits>
 
@@ -172,7 +173,8 @@ struct OffsetKeys {
 
     template <int NUP>
     __device__ __forceinline__ void build(const DeviceTable& T, int len2, const VCounter<NUP>& A, const VCounter<NUP>& B,
-                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1])
+                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1], int /*planes*/,
+                                          int64_t /*bias*/)
     {
         ka = key_t(T.kcls[1] - T.kcls[0]);
         kb = key_t(T.kcls[2] - T.kcls[0]);
@@ -252,13 +254,96 @@ struct OffsetKeys {
     }
 };
 
+// -------------------------------------------------------------------------------------------------
+// The same keys without leaving the bit-sliced domain (small integer weights, exact mode): the key planes
+// are built with bit-sliced shift-and-add from the three vertical counters, the rank term is selected by
+// the rank planes, and the best offset of the lane falls out of an MSB-first elimination over the planes.
+// ~300 ALU ops per lane instead of ~900 for transpose + 32 scalar keys.
+//   key' = key + bias  (bias makes every key' non-negative and < 2^planes; both come from the host)
+// -------------------------------------------------------------------------------------------------
+template <int NB, int K>
+struct SlicedKeys {
+    uint32_t acc[kSlicedMaxPlanes];
+    uint32_t rmask;      // offsets whose best rank the tracked planes determine
+    uint32_t nokey;      // offsets with no possible mutation (only when some pair has no substitute)
+    int planes;
+    int64_t bias, kfl;
+
+    template <int NUP>
+    __device__ __forceinline__ void build(const DeviceTable& T, int len2, const VCounter<NUP>& A, const VCounter<NUP>& B,
+                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1], int planes_, int64_t bias_)
+    {
+        planes = planes_;
+        bias = bias_;
+        const int ka = int(T.kcls[1] - T.kcls[0]), kb = int(T.kcls[2] - T.kcls[0]);
+        const int kc = int(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
+        const int floor_rank = T.nranks - K;
+        const bool floor_none = floor_rank <= 0;
+        const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+        kfl = floor_none ? 0 : T.kdiff[floor_rank];
+        int64_t ktop[K > 0 ? K : 1];
+        int64_t dmin = floor_none ? INT64_MAX : kfl;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            ktop[k] = T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0];
+            dmin = ktop[k] < dmin ? ktop[k] : dmin;
+        }
+        const uint32_t c0 = uint32_t(bias + int64_t(len2) * T.kcls[0] + dmin);
+#pragma unroll
+        for (int j = 0; j < kSlicedMaxPlanes; j++) acc[j] = ((c0 >> j) & 1u) ? 0xFFFFFFFFu : 0u;
+        uint32_t x[NB];
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = A.plane(k);
+        sliced_add_scaled<NB>(acc, planes, x, ka);
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = B.plane(k);
+        sliced_add_scaled<NB>(acc, planes, x, kb);
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = C.plane(k);
+        sliced_add_scaled<NB>(acc, planes, x, kc);
+        // rank term: one-hot selection masks, best tracked plane first
+        uint32_t seen = 0, dpl[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) dpl[j] = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t sel = racc[k] & ~seen;
+            seen |= racc[k];
+            const uint32_t dv = uint32_t(ktop[k] - dmin);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((dv >> j) & 1u) dpl[j] |= sel;
+        }
+        if (!floor_none) {
+            const uint32_t dv = uint32_t(kfl - dmin);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((dv >> j) & 1u) dpl[j] |= ~seen;
+        }
+        sliced_add_scaled<8>(acc, planes, dpl, 1);
+        rmask = floor_exact ? 0xFFFFFFFFu : seen;
+        nokey = floor_none ? ~seen : 0u;
+    }
+
+    __device__ __forceinline__ uint32_t scan(uint32_t mask, int64_t ln0, Cand& res, Cand& ub) const
+    {
+        uint32_t v;
+        int b;
+        mask &= ~nokey;
+        if (sliced_argmax(acc, planes, mask & rmask, v, b)) take(res, int64_t(v) - bias, int32_t(ln0 + b));
+        const uint32_t unresolved = mask & ~rmask;
+        if (sliced_argmax(acc, planes, unresolved, v, b)) take(ub, int64_t(v) - bias, int32_t(ln0 + b));
+        return unresolved;
+    }
+};
+
 // Exact order is required from the scan in exact mode: settle every unresolved offset whose bound could
 // beat the warp's best resolved key by looking up its true best rank (one pass over the alignment, lanes
 // striding i; the counts, hence the key without the difference term, are already exact).  Returns the
 // warp's exact best.  All 32 lanes must call.
-template <int NB, int K, bool KEY32>
+template <class Keys>
 __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_code,
-                                                  const OffsetKeys<NB, K, KEY32>& keys, Cand mine, Cand ub, uint32_t umask,
+                                                  const Keys& keys, Cand mine, Cand ub, uint32_t umask,
                                                   int64_t ln0, int64_t qbeg, int len2)
 {
     Cand wbest = warp_best(mine);
@@ -306,9 +391,10 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 // Windows are filled by TMA bulk copies (one per plane row) completing on an mbarrier while the block
 // turns its slice of Seq2 into row offsets.
 // -------------------------------------------------------------------------------------------------
-template <int NB, int K, bool KEY32>
+template <int NB, int K, bool BS>
 __global__ void __launch_bounds__(128, 4)
-k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk)
+k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
+       const int key_planes, const int64_t key_bias)
 {
     constexpr int NUP = NB - 5;
     constexpr int kEntry = (4 * K > 8) ? 4 * K : 8;                 // bytes per window word (max of the two passes)
@@ -416,9 +502,9 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     // ---- epilogue -------------------------------------------------------------------------------------
     Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
     uint32_t umask = 0;
-    OffsetKeys<NB, K, KEY32> keys;
+    typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
     if (warp_active) {
-        keys.build(T, len2, A, B, C, racc);
+        keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
         umask = keys.scan(vmask, ln0, mine, ub);
     }
     if (T.exact) {
@@ -464,10 +550,10 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 //   shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | per warp [chunk] uint32 row offsets
 // One TileRec per (query, tile) is written by the warp that computed it.
 // -------------------------------------------------------------------------------------------------
-template <int NB, int K, bool KEY32>
+template <int NB, int K, bool BS>
 __global__ void __launch_bounds__(128, 4)
 k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
-             const int queries_per_block)
+             const int queries_per_block, const int key_planes, const int64_t key_bias)
 {
     constexpr int NUP = NB - 5;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -537,8 +623,8 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
             class_group<NUP>(A, B, C, reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8, s_ro + g * 32);
 
         Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
-        OffsetKeys<NB, K, KEY32> keys;
-        keys.build(T, len2, A, B, C, racc);
+        typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
+        keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
         const uint32_t umask = keys.scan(vmask, ln0, mine, ub);
         const int rec_id = P.tile_start[q] + tile;
         TileRec rec;
@@ -563,15 +649,24 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     if (!staged) mbar_wait(&s_bar, 0);      // never leave with a bulk copy in flight
 }
 
-// keys fit the packed 32-bit compare of the epilogue when |key| < 2^26
-bool keys_fit_32(const DeviceTable& T, int64_t max_len2)
+// The bit-sliced epilogue applies when keys are small integers: exact mode, |multipliers| <= 255, rank terms
+// spread <= 255 and every biased key below 2^kSlicedMaxPlanes.  Returns the plane count (0 = not applicable).
+int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int64_t* bias_out)
 {
-    if (!T.exact) return false;
-    double m = 0;
-    for (int c = 0; c < 4; c++) m = fmax(m, fabs(double(T.kcls[c])));
-    double d = 0;
-    for (int r = 0; r <= T.nranks; r++) d = fmax(d, fabs(double(T.kdiff[r])));
-    return m * double(max_len2) * 3.0 + d < 67108864.0 / 2;        // generous: every partial sum stays below 2^25
+    if (!T.exact) return 0;
+    const int64_t k0 = T.kcls[0], ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
+    const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
+    auto mag = [](int64_t v) { return v < 0 ? -v : v; };
+    if (mag(ka) > 255 || mag(kb) > 255 || mag(kc) > 255 || mag(k0) > (int64_t(1) << 20)) return 0;
+    int64_t dmin = INT64_MAX, dmax = INT64_MIN;
+    for (int r = 1; r <= T.nranks; r++) { dmin = std::min(dmin, T.kdiff[r]); dmax = std::max(dmax, T.kdiff[r]); }
+    if (T.nranks < 1 || dmax - dmin > 255) return 0;
+    const int64_t bias = max_len2 * (mag(ka) + mag(kb) + mag(kc) + mag(k0)) + std::max(mag(dmin), mag(dmax)) + 1;
+    int planes = 1;
+    while ((int64_t(1) << planes) <= 2 * bias + 512) planes++;
+    if (planes > kSlicedMaxPlanes) return 0;
+    *bias_out = bias;
+    return planes;
 }
 
 size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
@@ -580,9 +675,9 @@ size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
     return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(warps) * chunk * 4;
 }
 
-template <int NB, int K, bool KEY32>
+template <int NB, int K, bool BS>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, bool batch, int sm_count,
-                      cudaStream_t stream)
+                      int key_planes, int64_t key_bias, cudaStream_t stream)
 {
     if (batch) {
         const int warps = 4;
@@ -595,36 +690,32 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         if (qpb < warps) qpb = warps;
         if (qpb > 4096) qpb = 4096;
         dim3 grid((G.nq + qpb - 1) / qpb, tiles);
-        cudaFuncSetAttribute(k_scan_batch<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_scan_batch<NB, K, KEY32><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb));
+        cudaFuncSetAttribute(k_scan_batch<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_scan_batch<NB, K, BS><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
     } else {
         const int warps = G.tile / 1024;
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
-        cudaFuncSetAttribute(k_scan<NB, K, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_scan<NB, K, KEY32><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk);
+        cudaFuncSetAttribute(k_scan<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_scan<NB, K, BS><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias);
     }
 }
 
 template <int NB>
-void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool key32, bool batch,
-                    int sm_count, cudaStream_t stream)
+void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool batch, int sm_count,
+                    int key_planes, int64_t key_bias, cudaStream_t stream)
 {
-    if (key32) {
-        switch (K) {
-        case 0: launch_scan_inst<NB, 0, true>(T, G, P, chunk, batch, sm_count, stream); break;
-        case 1: launch_scan_inst<NB, 1, true>(T, G, P, chunk, batch, sm_count, stream); break;
-        case 2: launch_scan_inst<NB, 2, true>(T, G, P, chunk, batch, sm_count, stream); break;
-        default: launch_scan_inst<NB, 4, true>(T, G, P, chunk, batch, sm_count, stream); break;
-        }
-    } else {
-        switch (K) {
-        case 0: launch_scan_inst<NB, 0, false>(T, G, P, chunk, batch, sm_count, stream); break;
-        case 1: launch_scan_inst<NB, 1, false>(T, G, P, chunk, batch, sm_count, stream); break;
-        case 2: launch_scan_inst<NB, 2, false>(T, G, P, chunk, batch, sm_count, stream); break;
-        default: launch_scan_inst<NB, 4, false>(T, G, P, chunk, batch, sm_count, stream); break;
-        }
+#define PSA_SCAN_CASE(KK)                                                                                              \
+    if (key_planes > 0) launch_scan_inst<NB, KK, true>(T, G, P, chunk, batch, sm_count, key_planes, key_bias, stream); \
+    else launch_scan_inst<NB, KK, false>(T, G, P, chunk, batch, sm_count, 0, 0, stream);                              \
+    break;
+    switch (K) {
+    case 0: PSA_SCAN_CASE(0)
+    case 1: PSA_SCAN_CASE(1)
+    case 2: PSA_SCAN_CASE(2)
+    default: PSA_SCAN_CASE(4)
     }
+#undef PSA_SCAN_CASE
 }
 
 } // namespace
@@ -673,15 +764,16 @@ void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
 }
 
 void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2, bool batch,
-                 int sm_count, cudaStream_t stream)
+                 bool sliced_ok, int sm_count, cudaStream_t stream)
 {
     if (G.total_tiles < 1) return;
     const int chunk = scan_chunk_steps(rank_planes, max_len2);
-    const bool key32 = keys_fit_32(T, max_len2);
+    int64_t key_bias = 0;
+    const int key_planes = sliced_ok ? sliced_key_planes(T, max_len2, &key_bias) : 0;
     batch = batch && max_len2 <= 1023 && G.last < 0 && G.tile == 1024;
-    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
-    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
-    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, key32, batch, sm_count, stream);
+    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
+    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
+    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
 }
 
 } // namespace psa

@@ -10,10 +10,11 @@ for name in ("c3","c5","c4","c1"):
         b=json.load(open('/root/repo/tests/golden/input_blocks.json'))[0]
         wl=synth.Workload("c1", b["weights"], b["goal"]=="maximum", b["seq1"].encode(), [b["seq2"].encode()])
     b = psa.Batch(wl.seq1, wl.queries)
-    for planes, bm in ((-1, -1), (1, 1), (2, 1), (4, 1), (1, 0), (2, 0), (4, 0)):
+    for planes, bm, sl in ((-1, -1, 1), (-1, -1, 0), (1, 1, 1), (2, 1, 1), (4, 1, 1), (2, 1, 0), (4, 1, 0), (1, 0, 1), (2, 0, 1), (4, 0, 1)):
         ctx.set_option("rank_planes", planes)
         ctx.set_option("batch_mode", bm)
+        ctx.set_option("sliced_keys", sl)
         ctx.prepare(wl.weights, wl.is_max, b)
         ms = min(ctx.run() for _ in range(5)); ctx.fetch()
         t = psa.build_pair_table(wl.weights, wl.is_max, max(b.lens))
-        print(name, "planes", ctx.stat("rank_planes"), "nranks", t.nranks, "exact", t.exact, "tiles", ctx.stat("tiles"), "rescored_words", ctx.stat("candidate_tiles"), "warps", ctx.stat("scan_warps"), "batch", ctx.stat("batch_mode"), "run_ms %.3f"%ms, "scan_ms %.3f"%(ctx.stat("main_kernel_ns")/1e6))
+        print(name, "planes", ctx.stat("rank_planes"), "nranks", t.nranks, "exact", t.exact, "tiles", ctx.stat("tiles"), "rescored_words", ctx.stat("candidate_tiles"), "warps", ctx.stat("scan_warps"), "batch", ctx.stat("batch_mode"), "sliced", sl, "run_ms %.3f"%ms, "scan_ms %.3f"%(ctx.stat("main_kernel_ns")/1e6))
