@@ -92,63 +92,58 @@ PSA_HD void transpose32(uint32_t (&a)[32])
 
 
 // ---- bit-sliced integer arithmetic on "vertical" numbers (plane j = bit j of 32 independent values) ----
-constexpr int kSlicedMaxPlanes = 22;
+constexpr int kSlicedMaxBits = 5;        // multipliers |k| < 2^5
 
-// acc += sign * (x << shift) for every set bit `shift` of |k|, i.e. acc += k * x, modulo 2^planes.
-// x has nx planes (unsigned).  Straight-line code once unrolled; the branches are on warp-uniform data.
-template <int NX>
-PSA_HD void sliced_add_scaled(uint32_t (&acc)[kSlicedMaxPlanes], const int planes, const uint32_t (&x)[NX], const int k)
+// acc += k * x modulo 2^P, x unsigned with NX planes, |k| < 2^kSlicedMaxBits.
+// Shift-and-add, one ripple-carry pass per set bit of |k| (two LOP3 per plane).  Negative k: two's complement,
+// i.e. the operand is inverted (ones below the shift) and each term gets a carry-in of 1.  All plane indices
+// are compile-time constants; the branches are on warp-uniform data.
+template <int NX, int P>
+PSA_HD void sliced_add_scaled(uint32_t (&acc)[P], const uint32_t (&x)[NX], const int k)
 {
     if (k == 0) return;
-    const uint32_t sm = k < 0 ? 0xFFFFFFFFu : 0u;          // two's complement: invert, carry-in 1
+    const uint32_t sm = k < 0 ? 0xFFFFFFFFu : 0u;
     const uint32_t mag = uint32_t(k < 0 ? -k : k);
     uint32_t xi[NX];
 PSA_UNROLL
     for (int i = 0; i < NX; i++) xi[i] = x[i] ^ sm;
 PSA_UNROLL
-    for (int s = 0; s < 8; s++) {
-        if (!((mag >> s) & 1u)) continue;
-        uint32_t carry = sm;
+    for (int s = 0; s < kSlicedMaxBits; s++) {
+        if ((mag >> s) & 1u) {
+            uint32_t carry = sm;
 PSA_UNROLL
-        for (int j = 0; j < kSlicedMaxPlanes; j++) {
-            if (j < s) continue;
-            if (j >= planes) break;
-            const uint32_t xo = (j - s) < NX ? xi[(j - s) < NX ? (j - s) : 0] : sm;
-            uint32_t sum, cy;
-            csa(sum, cy, acc[j], xo, carry);
-            acc[j] = sum;
-            carry = cy;
+            for (int j = s; j < P; j++) {
+                const uint32_t xo = (j - s) < NX ? xi[(j - s) < NX ? (j - s) : 0] : sm;
+                uint32_t sum, cy;
+                csa(sum, cy, acc[j], xo, carry);
+                acc[j] = sum;
+                carry = cy;
+            }
         }
     }
 }
 
 // largest value among the offsets in `alive` and the lowest offset holding it; returns false if alive == 0
-PSA_HD bool sliced_argmax(const uint32_t (&acc)[kSlicedMaxPlanes], const int planes, uint32_t alive, uint32_t& value, int& bit)
+template <int P>
+PSA_HD bool sliced_argmax(const uint32_t (&acc)[P], uint32_t alive, uint32_t& value, int& bit)
 {
     if (!alive) return false;
     uint32_t v = 0;
 PSA_UNROLL
-    for (int j = kSlicedMaxPlanes - 1; j >= 0; j--) {
-        if (j >= planes) continue;
+    for (int j = P - 1; j >= 0; j--) {
         const uint32_t t = alive & acc[j];
         const bool nz = t != 0;
         alive = nz ? t : alive;
         v = (v << 1) | (nz ? 1u : 0u);
     }
     value = v;
-    // lowest set bit
 #if defined(__CUDA_ARCH__)
     bit = __ffs(int(alive)) - 1;
-    return true;
-#endif
+#else
     int b = 0;
-    uint32_t a = alive;
-    if (!(a & 0xFFFFu)) { b += 16; a >>= 16; }
-    if (!(a & 0xFFu)) { b += 8; a >>= 8; }
-    if (!(a & 0xFu)) { b += 4; a >>= 4; }
-    if (!(a & 0x3u)) { b += 2; a >>= 2; }
-    if (!(a & 0x1u)) { b += 1; }
+    while (!((alive >> b) & 1u)) b++;
     bit = b;
+#endif
     return true;
 }
 

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -149,7 +150,8 @@ int pick_rank_planes(const psa_context* ctx)
     if (avail < 0) avail = 0;
     // offsets the planes leave unresolved are settled inside the scan kernel, so the plane count is a pure
     // speed knob: long queries saturate the top rank within a few dozen steps, short ones benefit from two
-    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : (ctx->max_len2 >= 256 ? 1 : ctx->max_len2 >= 128 ? 2 : 4);
+    // measured (tools/stats.py): one plane is best at every length once unresolved offsets are settled in-kernel
+    int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : 1;
     if (want > 2) want = 4;                                          // supported widths: 0,1,2,4
     return std::min(want, std::max(avail, 0));
 }
@@ -633,10 +635,20 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
 int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
                      const char* seq2s, const int64_t* q_off, int32_t nq, psa_result* out)
 {
+    static const bool trace = std::getenv("PSA_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     if ((rc = run_async(ctx))) return rc;
-    return psa_batch_fetch(ctx, out);
+    const auto t2 = std::chrono::steady_clock::now();
+    rc = psa_batch_fetch(ctx, out);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        std::fprintf(stderr, "[psa] prepare+H2D enqueue %.1f us, launch %.1f us, wait+D2H+host %.1f us\n", us(t0, t1), us(t1, t2), us(t2, t3));
+    }
+    return rc;
 }
 
 int psa_search_range(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,

@@ -261,19 +261,20 @@ struct OffsetKeys {
 // ~300 ALU ops per lane instead of ~900 for transpose + 32 scalar keys.
 //   key' = key + bias  (bias makes every key' non-negative and < 2^planes; both come from the host)
 // -------------------------------------------------------------------------------------------------
+constexpr int sliced_planes(int nb) { return nb + 8; }     // key planes by counter width: 15 / 18 / 23
+
 template <int NB, int K>
 struct SlicedKeys {
-    uint32_t acc[kSlicedMaxPlanes];
+    static constexpr int P = sliced_planes(NB);
+    uint32_t acc[P];
     uint32_t rmask;      // offsets whose best rank the tracked planes determine
     uint32_t nokey;      // offsets with no possible mutation (only when some pair has no substitute)
-    int planes;
     int64_t bias, kfl;
 
     template <int NUP>
     __device__ __forceinline__ void build(const DeviceTable& T, int len2, const VCounter<NUP>& A, const VCounter<NUP>& B,
-                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1], int planes_, int64_t bias_)
+                                          const VCounter<NUP>& C, const uint32_t (&racc)[K > 0 ? K : 1], int /*planes*/, int64_t bias_)
     {
-        planes = planes_;
         bias = bias_;
         const int ka = int(T.kcls[1] - T.kcls[0]), kb = int(T.kcls[2] - T.kcls[0]);
         const int kc = int(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
@@ -290,17 +291,17 @@ struct SlicedKeys {
         }
         const uint32_t c0 = uint32_t(bias + int64_t(len2) * T.kcls[0] + dmin);
 #pragma unroll
-        for (int j = 0; j < kSlicedMaxPlanes; j++) acc[j] = ((c0 >> j) & 1u) ? 0xFFFFFFFFu : 0u;
+        for (int j = 0; j < P; j++) acc[j] = ((c0 >> j) & 1u) ? 0xFFFFFFFFu : 0u;
         uint32_t x[NB];
 #pragma unroll
         for (int k = 0; k < NB; k++) x[k] = A.plane(k);
-        sliced_add_scaled<NB>(acc, planes, x, ka);
+        sliced_add_scaled<NB, P>(acc, x, ka);
 #pragma unroll
         for (int k = 0; k < NB; k++) x[k] = B.plane(k);
-        sliced_add_scaled<NB>(acc, planes, x, kb);
+        sliced_add_scaled<NB, P>(acc, x, kb);
 #pragma unroll
         for (int k = 0; k < NB; k++) x[k] = C.plane(k);
-        sliced_add_scaled<NB>(acc, planes, x, kc);
+        sliced_add_scaled<NB, P>(acc, x, kc);
         // rank term: one-hot selection masks, best tracked plane first
         uint32_t seen = 0, dpl[8];
 #pragma unroll
@@ -320,7 +321,7 @@ struct SlicedKeys {
             for (int j = 0; j < 8; j++)
                 if ((dv >> j) & 1u) dpl[j] |= ~seen;
         }
-        sliced_add_scaled<8>(acc, planes, dpl, 1);
+        sliced_add_scaled<8, P>(acc, dpl, 1);
         rmask = floor_exact ? 0xFFFFFFFFu : seen;
         nokey = floor_none ? ~seen : 0u;
     }
@@ -330,9 +331,9 @@ struct SlicedKeys {
         uint32_t v;
         int b;
         mask &= ~nokey;
-        if (sliced_argmax(acc, planes, mask & rmask, v, b)) take(res, int64_t(v) - bias, int32_t(ln0 + b));
+        if (sliced_argmax<P>(acc, mask & rmask, v, b)) take(res, int64_t(v) - bias, int32_t(ln0 + b));
         const uint32_t unresolved = mask & ~rmask;
-        if (sliced_argmax(acc, planes, unresolved, v, b)) take(ub, int64_t(v) - bias, int32_t(ln0 + b));
+        if (sliced_argmax<P>(acc, unresolved, v, b)) take(ub, int64_t(v) - bias, int32_t(ln0 + b));
         return unresolved;
     }
 };
@@ -649,24 +650,23 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     if (!staged) mbar_wait(&s_bar, 0);      // never leave with a bulk copy in flight
 }
 
-// The bit-sliced epilogue applies when keys are small integers: exact mode, |multipliers| <= 255, rank terms
-// spread <= 255 and every biased key below 2^kSlicedMaxPlanes.  Returns the plane count (0 = not applicable).
-int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int64_t* bias_out)
+// The bit-sliced epilogue applies when keys are small integers: exact mode, |multipliers| < 2^kSlicedMaxBits, rank
+// terms spread <= 255 and every biased key below 2^sliced_planes(NB).  Returns the plane count (0 = not applicable).
+int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int nb, int64_t* bias_out)
 {
     if (!T.exact) return 0;
     const int64_t k0 = T.kcls[0], ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
     const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
     auto mag = [](int64_t v) { return v < 0 ? -v : v; };
-    if (mag(ka) > 255 || mag(kb) > 255 || mag(kc) > 255 || mag(k0) > (int64_t(1) << 20)) return 0;
+    const int64_t lim = (int64_t(1) << kSlicedMaxBits) - 1;
+    if (mag(ka) > lim || mag(kb) > lim || mag(kc) > lim || mag(k0) > (int64_t(1) << 20)) return 0;
     int64_t dmin = INT64_MAX, dmax = INT64_MIN;
     for (int r = 1; r <= T.nranks; r++) { dmin = std::min(dmin, T.kdiff[r]); dmax = std::max(dmax, T.kdiff[r]); }
     if (T.nranks < 1 || dmax - dmin > 255) return 0;
     const int64_t bias = max_len2 * (mag(ka) + mag(kb) + mag(kc) + mag(k0)) + std::max(mag(dmin), mag(dmax)) + 1;
-    int planes = 1;
-    while ((int64_t(1) << planes) <= 2 * bias + 512) planes++;
-    if (planes > kSlicedMaxPlanes) return 0;
+    if (2 * bias + 512 >= (int64_t(1) << sliced_planes(nb))) return 0;
     *bias_out = bias;
-    return planes;
+    return sliced_planes(nb);
 }
 
 size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
@@ -691,12 +691,14 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         if (qpb > 4096) qpb = 4096;
         dim3 grid((G.nq + qpb - 1) / qpb, tiles);
         cudaFuncSetAttribute(k_scan_batch<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_scan_batch<NB, K, BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         k_scan_batch<NB, K, BS><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
     } else {
         const int warps = G.tile / 1024;
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         cudaFuncSetAttribute(k_scan<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_scan<NB, K, BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         k_scan<NB, K, BS><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias);
     }
 }
@@ -769,7 +771,8 @@ void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, i
     if (G.total_tiles < 1) return;
     const int chunk = scan_chunk_steps(rank_planes, max_len2);
     int64_t key_bias = 0;
-    const int key_planes = sliced_ok ? sliced_key_planes(T, max_len2, &key_bias) : 0;
+    const int nb = max_len2 <= 127 ? 7 : max_len2 <= 1023 ? 10 : 15;
+    const int key_planes = sliced_ok ? sliced_key_planes(T, max_len2, nb, &key_bias) : 0;
     batch = batch && max_len2 <= 1023 && G.last < 0 && G.tile == 1024;
     if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
     else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
