@@ -66,6 +66,7 @@ struct BatchGeom {
     int32_t tile;           // offsets per tile
     int32_t total_tiles;
     int32_t tiles_per_query;   // > 0 when every query has the same number of tiles (no search needed), else 0
+    int32_t uniform_len2;      // > 0 when every query has this length: qoff / tile_start are implicit (not uploaded)
 };
 
 } // namespace psa

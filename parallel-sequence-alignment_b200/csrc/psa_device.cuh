@@ -75,6 +75,34 @@ __device__ __forceinline__ int query_of_tile(const int32_t* __restrict__ tile_st
     return lo;
 }
 
+// Query geometry: batches of equal-length queries (the common case) carry no per-query arrays at all.
+struct QueryGeom {
+    int64_t qbeg;     // byte offset of the query in seq2s
+    int32_t len2;
+    int32_t tile0;    // first tile record of the query
+};
+
+__device__ __forceinline__ int32_t first_tile_of(const BatchGeom& G, const int32_t* __restrict__ tile_start, int q)
+{
+    return G.uniform_len2 > 0 ? q * G.tiles_per_query : tile_start[q];
+}
+
+__device__ __forceinline__ QueryGeom query_geom(const BatchGeom& G, const int64_t* __restrict__ qoff,
+                                                const int32_t* __restrict__ tile_start, int q)
+{
+    QueryGeom g;
+    if (G.uniform_len2 > 0) {
+        g.len2 = G.uniform_len2;
+        g.qbeg = int64_t(q) * G.uniform_len2;
+        g.tile0 = q * G.tiles_per_query;
+    } else {
+        g.qbeg = qoff[q];
+        g.len2 = int32_t(qoff[q + 1] - g.qbeg);
+        g.tile0 = tile_start[q];
+    }
+    return g;
+}
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, global -> shared), sm_90+/sm_100a -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 

@@ -79,7 +79,7 @@ struct psa_context {
     int scan_tile = kScanTile;   // offsets per scan tile = 1024 x warps per block
     bool batch_mode = false;     // scan engine: queries share staged windows (k_scan_batch)
     int64_t max_len2 = 0;
-    std::vector<int64_t> len2s;
+    int64_t uniform_len2 = 0;    // > 0: all queries of the batch have this length
     // stats of the last run
     long long st_launches = 0, st_cand = 0, st_tiles = 0, st_main_ns = 0;
 };
@@ -169,33 +169,44 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     const bool scan = ctx->engine == 2;
     const int tile = scan ? ctx->scan_tile : kExactTile;
     int rc;
-    if ((rc = ensure_pin(ctx, d.h_qoff, sizeof(int64_t) * (nq + 1)))) return rc;
-    if ((rc = ensure_pin(ctx, d.h_tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
     if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq))) return rc;
     if ((rc = ensure_pin(ctx, d.h_flags, sizeof(int32_t) * 4))) return rc;
-    int64_t* hq = (int64_t*)d.h_qoff.p;
-    int32_t* ht = (int32_t*)d.h_tile_start.p;
     const int64_t byte0 = q_off[q_begin];
+    const int64_t seq2_bytes = q_off[q_end] - byte0;
+    const bool uniform_len = ctx->uniform_len2 > 0;       // every query of the batch has the same length
     int64_t tiles = 0, uniform = -1;
-    for (int k = 0; k < nq; k++) {
-        hq[k] = q_off[q_begin + k] - byte0;
-        const int64_t len2 = q_off[q_begin + k + 1] - q_off[q_begin + k];
-        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, len2);
-        ht[k] = (int32_t)tiles;
-        const int64_t mine = (l - tile_base(f) + tile - 1) / tile;
-        uniform = k == 0 ? mine : (uniform == mine ? uniform : 0);
-        tiles += mine;
+    if (uniform_len) {
+        // nothing per query to build or upload: offsets and tile ranges are implicit on the device
+        const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, ctx->uniform_len2);
+        uniform = (l - tile_base(f) + tile - 1) / tile;
+        tiles = uniform * nq;
         if (tiles > 0x7FFFFF00) return fail(ctx, PSA_ERR_ARG, "batch too large: more than 2^31 tiles on one GPU");
+    } else {
+        if ((rc = ensure_pin(ctx, d.h_qoff, sizeof(int64_t) * (nq + 1)))) return rc;
+        if ((rc = ensure_pin(ctx, d.h_tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
+        int64_t* hq = (int64_t*)d.h_qoff.p;
+        int32_t* ht = (int32_t*)d.h_tile_start.p;
+        for (int k = 0; k < nq; k++) {
+            hq[k] = q_off[q_begin + k] - byte0;
+            const int64_t len2 = q_off[q_begin + k + 1] - q_off[q_begin + k];
+            const int64_t f = last >= 0 ? first : 0, l = last >= 0 ? last : offsets_of(len1, len2);
+            ht[k] = (int32_t)tiles;
+            const int64_t mine = (l - tile_base(f) + tile - 1) / tile;
+            uniform = k == 0 ? mine : (uniform == mine ? uniform : 0);
+            tiles += mine;
+            if (tiles > 0x7FFFFF00) return fail(ctx, PSA_ERR_ARG, "batch too large: more than 2^31 tiles on one GPU");
+        }
+        hq[nq] = seq2_bytes;
+        ht[nq] = (int32_t)tiles;
     }
-    hq[nq] = q_off[q_end] - byte0;
-    ht[nq] = (int32_t)tiles;
-    const int64_t seq2_bytes = hq[nq];
 
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
-    if ((rc = ensure_dev(ctx, d.qoff, sizeof(int64_t) * (nq + 1)))) return rc;
-    if ((rc = ensure_dev(ctx, d.tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
+    if (!uniform_len) {
+        if ((rc = ensure_dev(ctx, d.qoff, sizeof(int64_t) * (nq + 1)))) return rc;
+        if ((rc = ensure_dev(ctx, d.tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
+    }
     if ((rc = ensure_dev(ctx, d.tiles, sizeof(TileRec) * (size_t)tiles))) return rc;
     if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq))) return rc;
     if (scan && !ctx->table.exact)
@@ -210,8 +221,10 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
     PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2s + byte0, (size_t)seq2_bytes, cudaMemcpyHostToDevice, d.stream));
-    PSA_CUDA(ctx, cudaMemcpyAsync(d.qoff.p, hq, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
-    PSA_CUDA(ctx, cudaMemcpyAsync(d.tile_start.p, ht, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
+    if (!uniform_len) {
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.qoff.p, d.h_qoff.p, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.tile_start.p, d.h_tile_start.p, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
+    }
 
     d.G.len1 = len1;
     d.G.first = last >= 0 ? first : 0;
@@ -220,6 +233,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.G.tile = tile;
     d.G.total_tiles = (int32_t)tiles;
     d.G.tiles_per_query = uniform > 0 ? (int32_t)uniform : 0;
+    d.G.uniform_len2 = uniform_len ? (int32_t)ctx->uniform_len2 : 0;
     d.P.seq1 = (const uint8_t*)d.seq1.p;
     d.P.seq2s = (const uint8_t*)d.seq2s.p;
     d.P.qoff = (const int64_t*)d.qoff.p;
@@ -424,6 +438,10 @@ int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards,
         return PSA_OK;
     }
     if (last >= 0) return PSA_ERR_ARG;               // an offset range is only defined for one query
+    if (nshards == 1) {                              // nothing to balance (lengths are validated by the caller's pass)
+        out[0].q_begin = 0; out[0].q_end = nq;
+        return PSA_OK;
+    }
     std::vector<double> work(nq + 1, 0.0);
     for (int q = 0; q < nq; q++) {
         const int64_t len2 = q_off[q + 1] - q_off[q];
@@ -472,14 +490,14 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
     ctx->prepared = ctx->ran = false;
     if (!weights || !seq1 || !seq2s || !q_off || nq < 0) return fail(ctx, PSA_ERR_ARG, "null argument or nq < 0");
     if (len1 < 1 || len1 > 0x7FFF0000ll) return fail(ctx, PSA_ERR_ARG, "len1 out of range");
-    int64_t max_len2 = 0;
-    ctx->len2s.resize(nq);
+    int64_t max_len2 = 0, min_len2 = INT64_MAX;
     for (int q = 0; q < nq; q++) {
         const int64_t len2 = q_off[q + 1] - q_off[q];
         if (len2 < 1 || len2 > len1) return fail(ctx, PSA_ERR_ARG, "query %d: len2=%lld must be in [1, len1]", q, (long long)len2);
-        ctx->len2s[q] = len2;
         max_len2 = std::max(max_len2, len2);
+        min_len2 = std::min(min_len2, len2);
     }
+    ctx->uniform_len2 = nq > 0 && min_len2 == max_len2 ? max_len2 : 0;
     if (max_len2 > kExactMaxLen2) return fail(ctx, PSA_ERR_ARG, "len2 > %lld is not supported", (long long)kExactMaxLen2);
     if (last >= 0) {
         if (nq != 1 || first < 0 || first >= last || last > offsets_of(len1, max_len2))
@@ -508,10 +526,13 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
         int best_w = kScanWarps;
         for (int w = kScanWarps; w >= 1; w--) {
             double cost = 0;
-            for (int q = 0; q < nq; q++) {
-                const int64_t n = last >= 0 ? last - tile_base(first) : offsets_of(len1, ctx->len2s[q]);
-                cost += double((n + 1024 * w - 1) / (1024 * w)) * w;
-            }
+            auto tiles_of = [&](int64_t len2) {
+                const int64_t n = last >= 0 ? last - tile_base(first) : offsets_of(len1, len2);
+                return double((n + 1024 * w - 1) / (1024 * w)) * w;
+            };
+            if (ctx->uniform_len2 > 0) cost = tiles_of(ctx->uniform_len2) * nq;
+            else
+                for (int q = 0; q < nq; q++) cost += tiles_of(q_off[q + 1] - q_off[q]);
             if (w == kScanWarps || cost < best_cost) { best_cost = cost; best_w = w; }
         }
         ctx->scan_tile = ctx->opt_scan_warps > 0 ? 1024 * ctx->opt_scan_warps : 1024 * best_w;

@@ -52,9 +52,10 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 
     for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {
         const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
-        const int t = tile_id - P.tile_start[q];
-        const int64_t qbeg = P.qoff[q];
-        const int len2 = int(P.qoff[q + 1] - qbeg);
+        const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
+        const int t = tile_id - qg.tile0;
+        const int64_t qbeg = qg.qbeg;
+        const int len2 = qg.len2;
         const int64_t first = G.last >= 0 ? G.first : 0;
         const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
         const int64_t tb = tile_base(first) + int64_t(t) * G.tile;
@@ -159,12 +160,13 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     __shared__ unsigned long long s_pos;
     __shared__ int s_cnt[4];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t0 = P.tile_start[q], t1 = P.tile_start[q + 1];
+    const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
+    const int t0 = qg.tile0, t1 = q + 1 < G.nq ? first_tile_of(G, P.tile_start, q + 1) : G.total_tiles;
     for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     if (tid < 4) s_w[tid] = T.wcls[tid];
 
-    const int64_t qbeg = P.qoff[q];
-    const int len2 = int(P.qoff[q + 1] - qbeg);
+    const int64_t qbeg = qg.qbeg;
+    const int len2 = qg.len2;
     const int64_t first = G.last >= 0 ? G.first : 0;
     const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
     const uint8_t* b = P.seq2s + qbeg;

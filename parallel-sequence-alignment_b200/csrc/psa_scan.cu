@@ -411,9 +411,10 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     if (T.exact)            // only the settle path reads it
         for (int k = tid; k < kSymbols * kRowPad; k += nthreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
-    const int t = tile_id - P.tile_start[q];
-    const int64_t qbeg = P.qoff[q];
-    const int len2 = int(P.qoff[q + 1] - qbeg);
+    const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
+    const int t = tile_id - qg.tile0;
+    const int64_t qbeg = qg.qbeg;
+    const int len2 = qg.len2;
     const int64_t first = G.last >= 0 ? G.first : 0;
     const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
     const int64_t tb = tile_base(first) + int64_t(t) * G.tile;      // multiple of 128
@@ -589,8 +590,9 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     const int q_begin = blockIdx.x * queries_per_block;
     const int q_end = (q_begin + queries_per_block) < G.nq ? (q_begin + queries_per_block) : G.nq;
     for (int q = q_begin + warp; q < q_end; q += warps) {
-        const int64_t qbeg = P.qoff[q];
-        const int len2 = int(P.qoff[q + 1] - qbeg);
+        const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
+        const int64_t qbeg = qg.qbeg;
+        const int len2 = qg.len2;
         const int64_t last = G.len1 - len2 + 1;
         if (tb >= last) continue;                                   // this query does not reach the tile
         const uint32_t vmask = valid_mask(ln0, 0, last);
@@ -627,7 +629,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
         keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
         const uint32_t umask = keys.scan(vmask, ln0, mine, ub);
-        const int rec_id = P.tile_start[q] + tile;
+        const int rec_id = qg.tile0 + tile;
         TileRec rec;
         rec.score = 0.0; rec.flags = 0; rec.pad = 0; rec.ub_offset = 0x7FFFFFFF;
         if (T.exact) {
@@ -675,6 +677,18 @@ size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
     return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(warps) * chunk * 4;
 }
 
+// function attributes are per device and sticky: set them once per (kernel, device) instead of per launch
+template <class Kernel>
+void allow_big_smem(Kernel kernel, bool (&done)[64])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (dev >= 0 && dev < 64) done[dev] = true;
+}
+
 template <int NB, int K, bool BS>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, bool batch, int sm_count,
                       int key_planes, int64_t key_bias, cudaStream_t stream)
@@ -690,15 +704,15 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         if (qpb < warps) qpb = warps;
         if (qpb > 4096) qpb = 4096;
         dim3 grid((G.nq + qpb - 1) / qpb, tiles);
-        cudaFuncSetAttribute(k_scan_batch<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_scan_batch<NB, K, BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        static bool done[64];
+        allow_big_smem(k_scan_batch<NB, K, BS>, done);
         k_scan_batch<NB, K, BS><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
     } else {
         const int warps = G.tile / 1024;
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
-        cudaFuncSetAttribute(k_scan<NB, K, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_scan<NB, K, BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        static bool done[64];
+        allow_big_smem(k_scan<NB, K, BS>, done);
         k_scan<NB, K, BS><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias);
     }
 }
