@@ -139,32 +139,47 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 }
 
 // -------------------------------------------------------------------------------------------------
-// Finish: one block per query.
+// Finish: one warp per query, 8 queries per block (WPQ = 1), or -- for small batches, where a single warp
+// would crawl through dependent global loads -- the whole block on one query (WPQ = 8).
 //  (1) winner over the query's tile records under (key desc, offset asc);
 //  (2) only when the weights are not exactly summable and the records come from the bit-sliced scan:
 //      the integer keys order offsets like the reference only up to key_slack, so every 32-offset word
-//      whose key estimate is within key_slack of the best key is re-scored here with a double
-//      accumulated over i = 0..len2-1 in the reference's order (cpu_funcs.c:271-299), and the winner is
-//      chosen among those doubles under is_swapable's order (cuda_funcs.cu:290-307);
+//      whose key estimate is within key_slack of the best key is re-scored here -- one lane per offset,
+//      a double accumulated over i = 0..len2-1 in the reference's order (cpu_funcs.c:271-299), symbols
+//      staged through shared memory 256 steps at a time -- and the winner is chosen among those doubles
+//      under is_swapable's order (cuda_funcs.cu:290-307);
 //  (3) one pass over the winning alignment for the sign counts, the first position carrying the best
 //      rank (cpu_funcs.c:287-294: strict compare, so the lowest i wins ties) and its replacement letter.
 // -------------------------------------------------------------------------------------------------
-constexpr int kFinishThreads = 128;
+constexpr int kFinishWarps = 8;
+constexpr int kFinishThreads = kFinishWarps * 32;
+constexpr int kFinishChunk = 256;
 
+template <int WPQ>
 __global__ void __launch_bounds__(kFinishThreads)
 k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int scan_records)
 {
-    __shared__ Cand s_part[kFinishThreads / 32];
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
-    __shared__ double s_w[4];
+    constexpr int kGroup = WPQ * 32;                                    // threads working on one query
+    __shared__ Cand s_part[kFinishWarps];
     __shared__ unsigned long long s_pos;
     __shared__ int s_cnt[4];
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
-    const int t0 = qg.tile0, t1 = q + 1 < G.nq ? first_tile_of(G, P.tile_start, q + 1) : G.total_tiles;
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ double s_w[4];
+    __shared__ uint16_t s_q[kFinishWarps][kFinishChunk];               // Seq2 symbol * kRowPad
+    __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     if (tid < 4) s_w[tid] = T.wcls[tid];
+    if (tid == 0) s_pos = 0ull;
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    const int q = WPQ == 1 ? blockIdx.x * kFinishWarps + warp : blockIdx.x;
+    if (q >= G.nq) return;
+    const int gtid = WPQ == 1 ? lane : tid;                             // index within the query's thread group
+    const int gwarp = WPQ == 1 ? 0 : warp;
 
+    const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
+    const int t0 = qg.tile0, t1 = q + 1 < G.nq ? first_tile_of(G, P.tile_start, q + 1) : G.total_tiles;
     const int64_t qbeg = qg.qbeg;
     const int len2 = qg.len2;
     const int64_t first = G.last >= 0 ? G.first : 0;
@@ -172,11 +187,12 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     const uint8_t* b = P.seq2s + qbeg;
 
     Cand mine{ kKeyNone, 0x7FFFFFFF };
-    for (int t = t0 + tid; t < t1; t += kFinishThreads) {
+#pragma unroll 4
+    for (int t = t0 + gtid; t < t1; t += kGroup) {
         const TileRec r = P.tiles[t];
         if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
     }
-    Cand win = block_best<kFinishThreads>(mine, s_part);     // also orders the s_code / s_w writes
+    Cand win = WPQ == 1 ? warp_best(mine) : block_best<kFinishThreads>(mine, s_part);
 
     if (!T.exact && scan_records) {
         const int64_t threshold = win.key == kKeyNone ? kKeyNone : win.key - T.key_slack;   // |key| < 2^61: no wrap
@@ -189,32 +205,54 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
             if (top == kKeyNone || top < threshold) continue;
             const int64_t* lk = P.lane_keys + int64_t(t) * tile_words;
             const int64_t tb = tile_base(first) + int64_t(t - t0) * G.tile;
-            for (int w = warp; w < tile_words; w += kFinishThreads / 32) {
-                const int64_t k = lk[w];
-                if (k == kKeyNone || k < threshold) continue;
-                words++;
-                const int64_t n = tb + 32 * w + lane;
-                if (n < first || n >= last) continue;
-                const uint8_t* a = P.seq1 + n;
-                double total = 0.0;
-                uint32_t best_rank = 0;
-#pragma unroll 4
-                for (int i = 0; i < len2; i++) {
-                    uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
-                    if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }      // flagged by the kernels before us
-                    const uint32_t code = s_code[c2 * kRowPad + c1];
-                    total += s_w[code & 3u];
-                    best_rank = max(best_rank, code >> 2);
-                }
-                if (best_rank) {
-                    const double score = total + T.wdiff[best_rank];                       // cpu_funcs.c:299
-                    const int64_t key = sortable_from_double(T.is_max ? score : -score);
-                    if (better(key, int32_t(n), mine2.key, mine2.off)) { mine2.key = key; mine2.off = int32_t(n); }
+            for (int w0 = 0; w0 < tile_words; w0 += 32) {
+                // which of the next 32 words are candidates (one ballot instead of 32 broadcast loads)
+                const int64_t k = (w0 + lane) < tile_words ? lk[w0 + lane] : kKeyNone;
+                uint32_t cand = __ballot_sync(0xFFFFFFFFu, k != kKeyNone && k >= threshold);
+                while (cand) {
+                    const int w = w0 + __ffs(int(cand)) - 1;
+                    cand &= cand - 1u;
+                    if (WPQ > 1 && (w % WPQ) != gwarp) continue;       // candidate words go round the warps of the block
+                    words++;
+                    const int64_t n0 = tb + 32 * w;                    // the word's first offset; this lane owns n0 + lane
+                    const int64_t n = n0 + lane;
+                    double total = 0.0;
+                    uint32_t best_rank = 0;
+                    for (int c0 = 0; c0 < len2; c0 += kFinishChunk) {
+                        const int cl = (len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk;
+                        __syncwarp();
+#pragma unroll 8
+                        for (int i = lane; i < cl; i += 32) {
+                            uint32_t c2 = symbol_of(b[c0 + i]);
+                            if (c2 == 0xFFu) c2 = 0;                   // flagged by the kernels before us
+                            s_q[warp][i] = uint16_t(c2 * kRowPad);
+                        }
+#pragma unroll 9
+                        for (int i = lane; i < cl + 31; i += 32) {
+                            const int64_t p = n0 + c0 + i;
+                            uint32_t c1 = p < G.len1 ? symbol_of(P.seq1[p]) : 0u;
+                            if (c1 == 0xFFu) c1 = 0;
+                            s_win[warp][i] = uint8_t(c1);
+                        }
+                        __syncwarp();
+                        const uint8_t* wv = &s_win[warp][lane];
+#pragma unroll 8
+                        for (int i = 0; i < cl; i++) {
+                            const uint32_t code = s_code[uint32_t(s_q[warp][i]) + wv[i]];
+                            total += s_w[code & 3u];
+                            best_rank = max(best_rank, code >> 2);
+                        }
+                    }
+                    if (best_rank && n >= first && n < last) {
+                        const double score = total + T.wdiff[best_rank];                   // cpu_funcs.c:299
+                        const int64_t key = sortable_from_double(T.is_max ? score : -score);
+                        if (better(key, int32_t(n), mine2.key, mine2.off)) { mine2.key = key; mine2.off = int32_t(n); }
+                    }
                 }
             }
         }
         if (lane == 0 && words) atomicAdd(P.cand_count, words);
-        win = block_best<kFinishThreads>(mine2, s_part);
+        win = WPQ == 1 ? warp_best(mine2) : block_best<kFinishThreads>(mine2, s_part);
     }
 
     QueryRec out;
@@ -222,17 +260,15 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
     out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
     if (win.key == kKeyNone) {            // no mutation possible at any offset (never seen in practice)
-        if (tid == 0) P.out[q] = out;
+        if (gtid == 0) P.out[q] = out;
         return;
     }
-    if (tid == 0) s_pos = 0ull;
-    if (tid < 4) s_cnt[tid] = 0;
-    __syncthreads();
 
     const uint8_t* a = P.seq1 + win.off;
     int cnt[4] = { 0, 0, 0, 0 };
     unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
-    for (int i = tid; i < len2; i += kFinishThreads) {
+#pragma unroll 4
+    for (int i = gtid; i < len2; i += kGroup) {
         uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
         if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
         const uint32_t code = s_code[c2 * kRowPad + c1];
@@ -247,22 +283,27 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
 #pragma unroll
         for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
     }
-    if (lane == 0) {
-        atomicMax(&s_pos, pos);
+    if (WPQ > 1) {
+        if (lane == 0) {
+            atomicMax(&s_pos, pos);
 #pragma unroll
-        for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
+            for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
+        }
+        __syncthreads();
+        pos = s_pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] = s_cnt[c];
     }
-    __syncthreads();
-    if (tid == 0) {
-        const int rank = int(s_pos >> 32);
-        const int i = int(~uint32_t(s_pos));
+    if (gtid == 0) {
+        const int rank = int(pos >> 32);
+        const int i = int(~uint32_t(pos));
         uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
         if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
         out.offset = win.off;
         out.char_offset = i;
         out.ch = T.sub[c2][c1];
         out.rank = rank;
-        for (int c = 0; c < 4; c++) out.counts[c] = s_cnt[c];
+        for (int c = 0; c < 4; c++) out.counts[c] = cnt[c];
         const bool key_is_double = !T.exact;     // engine 1 tile keys and re-scored keys are sortable doubles
         if (key_is_double) out.score = (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key);
         P.out[q] = out;
@@ -281,7 +322,8 @@ void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtr
 void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream)
 {
     if (G.nq < 1) return;
-    k_finish<<<G.nq, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
+    if (G.nq >= 256) k_finish<1><<<(G.nq + kFinishWarps - 1) / kFinishWarps, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
+    else k_finish<kFinishWarps><<<G.nq, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
 }
 
 } // namespace psa
