@@ -393,7 +393,7 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 // turns its slice of Seq2 into row offsets.
 // -------------------------------------------------------------------------------------------------
 template <int NB, int K, bool BS>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
        const int key_planes, const int64_t key_bias)
 {
@@ -553,7 +553,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 // One TileRec per (query, tile) is written by the warp that computed it.
 // -------------------------------------------------------------------------------------------------
 template <int NB, int K, bool BS>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
              const int queries_per_block, const int key_planes, const int64_t key_bias)
 {
