@@ -211,3 +211,26 @@ def test_config4_long_seq1(ctx, port, synth):
     assert same_answer(r, port.search(wl.weights, wl.is_max, wl.seq1, wl.queries[0], nthreads=8))
     r2 = ctx.search([1, 3, 4, 2], False, wl.seq1, wl.queries[0])
     assert same_answer(r2, port.search([1, 3, 4, 2], False, wl.seq1, wl.queries[0], nthreads=8))
+
+
+def test_multi_gpu_single_process(psa, port, synth):
+    """One process driving every visible GPU (the replacement of the reference's MPI ranks): offset ranges of
+    one query and query blocks of a batch must give the single-GPU / oracle answer.  Needs >= 2 GPUs."""
+    n = psa.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    s1 = synth.letters(61, 200_000)
+    s2 = synth.letters(62, 1500)
+    qs = [synth.letters(70 + k, 64 + 8 * k) for k in range(97)]
+    with psa.Context(ngpus=n) as c:
+        for w, is_max in (([1, 3, 4, 2], False), ([2, 1.5, 1.1, 1.3], True), ([1, 1, 1, 1], True)):
+            r = c.search(w, is_max, s1, s2)
+            assert same_answer(r, port.search(w, is_max, s1, s2, nthreads=8)), (w, is_max)
+            got = c.search_batch(w, is_max, s1[:20000], qs)
+            exp = port.search_batch(w, is_max, s1[:20000], qs)
+            assert all(same_answer(g, e) for g, e in zip(got, exp)), (w, is_max)
+        # planted ties across the GPU boundary: the lowest offset must win wherever the split falls
+        core = synth.letters(63, 700)
+        tied = synth.letters(64, 50_000) + core + synth.letters(65, 80_000) + core + synth.letters(66, 30_000)
+        r = c.search([1, 3, 4, 2], True, tied, core)
+        assert r.offset == 50_000 and same_answer(r, port.search([1, 3, 4, 2], True, tied, core, nthreads=8))
