@@ -176,6 +176,12 @@ int psa_write_output_file(const char* path, const char* mutant, int offset, doub
 /* The whole reference program for one input file: read, search on the context's GPUs, write. */
 int psa_run_files(psa_context* ctx, const char* input_path, const char* output_path, psa_result* out);
 
+/* Extension: the reference's own input.txt stacks 15 problem blocks but reads only the first
+   (cpu_funcs.c:353-368 parses one group of 4 weights + Seq1 + Seq2 + goal and ignores the rest).  This entry
+   point consumes EVERY complete block of the file and writes one output stanza per block, stanzas separated
+   by a newline, each exactly what the reference writes for that block alone.  *nblocks receives the count. */
+int psa_run_files_all(psa_context* ctx, const char* input_path, const char* output_path, int* nblocks);
+
 #ifdef __cplusplus
 }
 #endif

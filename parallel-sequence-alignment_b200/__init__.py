@@ -139,6 +139,7 @@ def _sig():
     _lib.psa_read_input_file.argtypes = [C.c_char_p, dp, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     _lib.psa_write_output_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double]
     _lib.psa_run_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(_CResult)]
+    _lib.psa_run_files_all.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
 
 
 _sig()
@@ -365,6 +366,16 @@ class Context:
         out = _CResult()
         self._check(_lib.psa_run_files(self._h, input_path.encode(), output_path.encode(), C.byref(out)))
         return _py(out)
+
+
+def _run_files_all(self, input_path: str, output_path: str) -> int:
+    """Every problem block stacked in the input file -> one output stanza per block; returns the count."""
+    n = C.c_int()
+    self._check(_lib.psa_run_files_all(self._h, input_path.encode(), output_path.encode(), C.byref(n)))
+    return n.value
+
+
+Context.run_files_all = _run_files_all
 
 
 def make_program_data(weights, is_max: bool, seq1, seq2) -> ProgramData:

@@ -152,4 +152,56 @@ int psa_run_files(psa_context* ctx, const char* input_path, const char* output_p
     return rc;
 }
 
+int psa_run_files_all(psa_context* ctx, const char* input_path, const char* output_path, int* nblocks)
+{
+    if (!ctx || !input_path || !output_path) return PSA_ERR_ARG;
+    if (nblocks) *nblocks = 0;
+    FILE* f = std::fopen(input_path, "r");
+    if (!f) return PSA_ERR_IO;
+    std::vector<std::string> tok;
+    {
+        std::string cur;
+        int c;
+        while ((c = std::fgetc(f)) != EOF) {
+            if (std::isspace(c)) { if (!cur.empty()) { tok.push_back(cur); cur.clear(); } }
+            else cur.push_back((char)c);
+        }
+        if (!cur.empty()) tok.push_back(cur);
+    }
+    std::fclose(f);
+    if (tok.size() < 7) return PSA_ERR_IO;                      // not even one complete block
+    std::string text;
+    int done = 0;
+    for (size_t k = 0; k + 7 <= tok.size(); k += 7) {
+        double w[4];
+        bool ok = true;
+        for (int i = 0; i < 4 && ok; i++) {
+            char* end = nullptr;
+            w[i] = std::strtod(tok[k + i].c_str(), &end);
+            ok = end && *end == '\0' && end != tok[k + i].c_str();
+        }
+        if (!ok) return PSA_ERR_IO;
+        const std::string &s1 = tok[k + 4], &s2 = tok[k + 5];
+        const int is_max = tok[k + 6] == "maximum" ? 1 : 0;
+        const int64_t q_off[2] = { 0, (int64_t)s2.size() };
+        psa_result r;
+        int rc = psa_search_batch(ctx, w, is_max, s1.c_str(), (int64_t)s1.size(), s2.c_str(), q_off, 1, &r);
+        if (rc) return rc;
+        std::string mut(s2);
+        if (r.mutant.char_offset >= 0) mut[(size_t)r.mutant.char_offset] = r.mutant.ch;
+        char tail[96];
+        std::snprintf(tail, sizeof(tail), "\n%d %g", r.mutant.offset, r.score);
+        if (done) text += "\n";
+        text += mut;
+        text += tail;
+        done++;
+    }
+    FILE* o = std::fopen(output_path, "w");
+    if (!o) return PSA_ERR_IO;
+    bool wrote = std::fwrite(text.data(), 1, text.size(), o) == text.size();
+    wrote = (std::fclose(o) == 0) && wrote;
+    if (nblocks) *nblocks = done;
+    return wrote ? PSA_OK : PSA_ERR_IO;
+}
+
 } // extern "C"

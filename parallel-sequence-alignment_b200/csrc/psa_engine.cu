@@ -45,7 +45,8 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, flags, cls_planes, rank_planes;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, flags, cls_planes, rank_planes, partial;
+    SliceGeom SG{};
     PinBuf h_qoff, h_tile_start, h_out, h_flags;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
@@ -63,6 +64,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
     int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
     // current batch
@@ -130,7 +132,7 @@ int ensure_pin(psa_context* ctx, PinBuf& b, size_t bytes)
 void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
-    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.flags,
+    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.flags, &d.partial,
                        &d.cls_planes, &d.rank_planes })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out, &d.h_flags })
@@ -200,6 +202,32 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         ht[nq] = (int32_t)tiles;
     }
 
+    // Slice mode: one query whose warp-tiles cannot fill the GPU is also cut along the alignment steps
+    d.SG = SliceGeom{};
+    int fin_tile = tile;
+    if (scan && !ctx->batch_mode && nq == 1 && last >= 0 && ctx->opt_slices != 1 && ctx->max_len2 >= 256) {
+        const int64_t span = last - tile_base(first);
+        const int64_t warp_tiles = (span + 1023) / 1024;
+        const int64_t steps_all = (ctx->max_len2 + 31) & ~int64_t(31);
+        int64_t want = ctx->opt_slices > 1 ? ctx->opt_slices : (int64_t(d.sm_count) * 16) / warp_tiles;
+        want = std::min<int64_t>(want, steps_all / 128);
+        if (want >= 2) {
+            const int64_t slice_len = ((steps_all + want - 1) / want + 127) & ~int64_t(127);
+            d.SG.slice_len = (int)slice_len;
+            d.SG.slices = (int)((steps_all + slice_len - 1) / slice_len);
+            d.SG.scan_tile = tile;
+            d.SG.scan_tiles = (int)tiles;
+            if (d.SG.slices >= 2) {
+                fin_tile = kCombineTile;
+                tiles = (span + fin_tile - 1) / fin_tile;       // tile records now come from k_combine
+                uniform = tiles;
+                if ((rc = ensure_dev(ctx, d.partial, sizeof(uint2) * (size_t)d.SG.slices * d.SG.scan_tiles * d.SG.scan_tile))) return rc;
+            } else {
+                d.SG = SliceGeom{};
+            }
+        }
+    }
+
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
@@ -210,7 +238,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     if ((rc = ensure_dev(ctx, d.tiles, sizeof(TileRec) * (size_t)tiles))) return rc;
     if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq))) return rc;
     if (scan && !ctx->table.exact)
-        if ((rc = ensure_dev(ctx, d.lane_keys, sizeof(int64_t) * (size_t)tiles * (tile / 32)))) return rc;
+        if ((rc = ensure_dev(ctx, d.lane_keys, sizeof(int64_t) * (size_t)tiles * (fin_tile / 32)))) return rc;
     if ((rc = ensure_dev(ctx, d.flags, sizeof(int32_t) * 4))) return rc;
     if (scan) {
         if ((rc = ensure_dev(ctx, d.cls_planes, sizeof(uint2) * (size_t)plane_words * kPlaneRows))) return rc;
@@ -230,7 +258,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.G.first = last >= 0 ? first : 0;
     d.G.last = last >= 0 ? last : -1;
     d.G.nq = nq;
-    d.G.tile = tile;
+    d.G.tile = fin_tile;
     d.G.total_tiles = (int32_t)tiles;
     d.G.tiles_per_query = uniform > 0 ? (int32_t)uniform : 0;
     d.G.uniform_len2 = uniform_len ? (int32_t)ctx->uniform_len2 : 0;
@@ -241,6 +269,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.tiles = (TileRec*)d.tiles.p;
     d.P.out = (QueryRec*)d.out.p;
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
+    d.P.partial = (uint2*)d.partial.p;
+    d.P.partial_stride = int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
     d.P.cand_count = (int32_t*)d.flags.p;
     d.P.err_flag = (int32_t*)d.flags.p + 1;
     d.P.cls_planes = (uint2*)d.cls_planes.p;
@@ -258,7 +288,8 @@ int run_device(psa_context* ctx, DeviceState& d)
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
-        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, ctx->opt_sliced_keys != 0, d.sm_count, d.stream);
+        launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, ctx->opt_sliced_keys != 0, d.sm_count, d.SG, d.stream);
+        if (d.SG.slices > 1) ctx->st_launches += 1;
         PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 2;
     } else {
@@ -391,6 +422,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
@@ -408,6 +440,7 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
     if (!std::strcmp(name, "batch_mode")) return ctx->batch_mode ? 1 : 0;
+    if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.slices; return 1; }
     if (!std::strcmp(name, "exact")) return ctx->table.exact;
     return -1;
 }

@@ -154,6 +154,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 constexpr int kFinishWarps = 8;
 constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kFinishChunk = 256;
+constexpr int kFinishList = 32;       // candidate tiles remembered per query before falling back to a full walk
 
 template <int WPQ>
 __global__ void __launch_bounds__(kFinishThreads)
@@ -165,6 +166,8 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     __shared__ int s_cnt[4];
     __shared__ uint8_t s_code[kSymbols * kRowPad];
     __shared__ double s_w[4];
+    __shared__ int s_list[kFinishWarps][kFinishList];
+    __shared__ int s_nlist[kFinishWarps];
     __shared__ uint16_t s_q[kFinishWarps][kFinishChunk];               // Seq2 symbol * kRowPad
     __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,10 +202,29 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
         const int tile_words = G.tile >> 5;
         Cand mine2{ kKeyNone, 0x7FFFFFFF };
         int words = 0;
-        for (int t = t0; t < t1; t++) {
+        // candidate tiles, found in parallel (a query can have thousands of tiles and one or two candidates)
+        int* my_list = s_list[WPQ == 1 ? warp : 0];
+        int* my_count = &s_nlist[WPQ == 1 ? warp : 0];
+        if (gtid == 0) *my_count = 0;
+        if (WPQ == 1) __syncwarp(); else __syncthreads();
+        for (int t = t0 + gtid; t < t1; t += kGroup) {
             const TileRec r = P.tiles[t];
             const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
             if (top == kKeyNone || top < threshold) continue;
+            const int slot = atomicAdd(my_count, 1);
+            if (slot < kFinishList) my_list[slot] = t;
+        }
+        if (WPQ == 1) __syncwarp(); else __syncthreads();
+        const int nlist = *my_count;
+        const bool listed = nlist <= kFinishList;               // else: walk every tile (correct, just slower)
+        const int ntry = listed ? nlist : (t1 - t0);
+        for (int k = 0; k < ntry; k++) {
+            const int t = listed ? my_list[k] : t0 + k;
+            if (!listed) {
+                const TileRec r = P.tiles[t];
+                const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
+                if (top == kKeyNone || top < threshold) continue;
+            }
             const int64_t* lk = P.lane_keys + int64_t(t) * tile_words;
             const int64_t tb = tile_base(first) + int64_t(t - t0) * G.tile;
             for (int w0 = 0; w0 < tile_words; w0 += 32) {

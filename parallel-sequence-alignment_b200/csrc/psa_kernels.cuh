@@ -14,6 +14,8 @@ struct BatchPtrs {
     TileRec*       tiles;       // total_tiles records
     QueryRec*      out;         // nq records
     int64_t*       lane_keys;   // scan engine, re-score mode: per (tile, 32-offset word) upper estimate of its keys
+    uint2*         partial;     // slice mode: [slice][offset] partial counts {N(b0) | N(b1) << 16, N(b0&b1) | rank bits << 16}
+    int64_t        partial_stride;   // offsets per slice row of `partial`
     int32_t*       cand_count;  // [0] = number of 32-offset words re-scored in reference order (statistic)
     int32_t*       err_flag;    // bit0: symbol outside [A-Z-]
     // bit-plane profile of Seq1 (scan engine): [row][word] of 64-bit (class planes) and
@@ -28,6 +30,16 @@ struct BatchPtrs {
 // with [first, last).
 __host__ __device__ inline int64_t tile_base(int64_t first) { return first & ~int64_t(127); }
 
+// Slice mode (one query that cannot fill the GPU): the alignment steps are cut into `slices` ranges of
+// `slice_len` steps, each scanned by its own blocks; k_combine adds the partial counts per offset.
+struct SliceGeom {
+    int slices = 1;        // 1 = off
+    int slice_len = 0;     // steps per slice (multiple of 128)
+    int scan_tile = 0;     // offsets per scan block (warps x 1024)
+    int scan_tiles = 0;    // scan blocks per slice
+};
+constexpr int kCombineTile = 256;   // offsets per tile record in slice mode
+
 // ---- launchers (all asynchronous on `stream`) -------------------------------------------------
 // exact scalar kernel over every tile (engine 1)
 void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);
@@ -39,7 +51,7 @@ void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
                     cudaStream_t stream);
 // bit-sliced scan of every tile
 void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2,
-                 bool batch, bool sliced_keys_ok, int sm_count, cudaStream_t stream);
+                 bool batch, bool sliced_keys_ok, int sm_count, const SliceGeom& slices, cudaStream_t stream);
 // batch mode (window shared by many queries, tile = 1024) applies when every query fits one window
 bool scan_batch_mode(const BatchGeom& G, int64_t max_len2, int sm_count);
 

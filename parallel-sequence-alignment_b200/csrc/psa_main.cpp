@@ -3,7 +3,8 @@
 // the same three stdout lines.  argv[1] keeps the reference's meaning (CUDA percentage, -100 =
 // sequential CPU) but is only echoed: there is no CPU path here, every offset runs on the GPU.
 //
-//   psa_b200_cli [cuda_percentage] [--gpus N] [--input PATH] [--output PATH]
+//   psa_b200_cli [cuda_percentage] [--gpus N] [--input PATH] [--output PATH] [--all-blocks]
+// --all-blocks: consume every problem block stacked in the input file (the reference reads only the first)
 #include "psa_b200.h"
 
 #include <chrono>
@@ -17,10 +18,12 @@ int main(int argc, char** argv)
     const char* out = "./output.txt";   // def.h:21
     int gpus = 1;
     int percentage = 100;
+    bool all_blocks = false;
     for (int i = 1; i < argc; i++) {
         if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--input") && i + 1 < argc) in = argv[++i];
         else if (!std::strcmp(argv[i], "--output") && i + 1 < argc) out = argv[++i];
+        else if (!std::strcmp(argv[i], "--all-blocks")) all_blocks = true;
         else percentage = std::atoi(argv[i]);
     }
     (void)percentage;
@@ -34,7 +37,8 @@ int main(int argc, char** argv)
     std::printf("CUDA percentage set to %d\n", 100);              // cpu_funcs.c:153
     auto t0 = std::chrono::steady_clock::now();
     psa_result r;
-    rc = psa_run_files(ctx, in, out, &r);
+    int blocks = 1;
+    rc = all_blocks ? psa_run_files_all(ctx, in, out, &blocks) : psa_run_files(ctx, in, out, &r);
     auto t1 = std::chrono::steady_clock::now();
     if (rc) {
         if (rc == PSA_ERR_IO) std::printf("Error reading input file `%s` or writing `%s`\n", in, out);   // cpu_funcs.c:37,43,103

@@ -392,10 +392,13 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 // Windows are filled by TMA bulk copies (one per plane row) completing on an mbarrier while the block
 // turns its slice of Seq2 into row offsets.
 // -------------------------------------------------------------------------------------------------
-template <int NB, int K, bool BS>
+// SLICE = true (single query, few warp-tiles): blockIdx.y selects a slice of the alignment steps
+// [slice * slice_len, ...); the block leaves its partial counts and rank bits per offset in P.partial and
+// k_combine adds the slices up -- this multiplies the warps in flight when one query cannot fill the GPU.
+template <int NB, int K, bool BS, bool SLICE>
 __global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
-       const int key_planes, const int64_t key_bias)
+       const int key_planes, const int64_t key_bias, const int slice_len)
 {
     constexpr int NUP = NB - 5;
     constexpr int kEntry = (4 * K > 8) ? 4 * K : 8;                 // bytes per window word (max of the two passes)
@@ -429,7 +432,9 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
     racc[0] = ~vmask;                       // offsets outside the range count as saturated
     uint32_t parity = 0;
-    const int steps_total = (len2 + 31) & ~31;
+    const int steps_all = (len2 + 31) & ~31;
+    const int step_begin = SLICE ? int(blockIdx.y) * slice_len : 0;                    // multiple of 128
+    const int steps_total = SLICE ? ((step_begin + slice_len) < steps_all ? (step_begin + slice_len) : steps_all) : steps_all;
 
     // Seq2 slice -> per-step row offsets (row * nwords * 8 bytes); padding steps use the all-zero row
     auto fill_row_offsets = [&](int c0, int cl) {
@@ -447,7 +452,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     // ---- pass R: best rank per offset -----------------------------------------------------------------
     if (K > 0) {
         bool rank_on = warp_active;
-        for (int c0 = 0; c0 < steps_total; c0 += chunk) {
+        for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
             const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
             const int need = round_up4(warps * 32 + (cl >> 5));
             __syncthreads();                                        // previous window consumed / barrier initialised
@@ -478,7 +483,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     // ---- pass C: sign-class counts --------------------------------------------------------------------
     VCounter<NUP> A, B, C;
     A.clear(); B.clear(); C.clear();
-    for (int c0 = 0; c0 < steps_total; c0 += chunk) {
+    for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
         const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
         const int need = round_up4(warps * 32 + (cl >> 5));
         __syncthreads();
@@ -502,6 +507,25 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
 
     // ---- epilogue -------------------------------------------------------------------------------------
+    if (SLICE) {
+        // partial counts of this slice, one uint2 per offset: {N(b0) | N(b1) << 16, N(b0&b1) | rank bits << 16}
+        if (warp_active) {
+            uint32_t m[32], m2[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) { m[k] = 0; m2[k] = 0; }
+#pragma unroll
+            for (int k = 0; k < NB; k++) { m[k] = A.plane(k); m[16 + k] = B.plane(k); m2[k] = C.plane(k); }
+#pragma unroll
+            for (int k = 0; k < K; k++) m2[16 + k] = racc[k];
+            transpose32(m);
+            transpose32(m2);
+            uint2* dst = P.partial + int64_t(blockIdx.y) * P.partial_stride + (ln0 - tile_base(first));
+#pragma unroll
+            for (int tt = 0; tt < 32; tt++)
+                if ((vmask >> tt) & 1u) dst[tt] = make_uint2(m[tt], m2[tt]);
+        }
+        return;
+    }
     Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
     uint32_t umask = 0;
     typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
@@ -539,6 +563,98 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
         rec.ub_key = top; rec.ub_offset = 0x7FFFFFFF;
         rec.score = 0.0; rec.flags = 0; rec.pad = 0;
         P.tiles[tile_id] = rec;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_combine (slice mode): one thread per offset adds the slices' partial counts, forms the key, and the
+// block (256 offsets = one tile record for k_finish) reduces to its best.  Offsets that met no tracked rank
+// plane are settled here when the order must be exact: those whose bound could beat the block's best walk
+// the alignment for their true best rank (rare, and only for the few that matter).
+// -------------------------------------------------------------------------------------------------
+constexpr int kCombineThreads = 256;
+
+template <int K>
+__global__ void __launch_bounds__(kCombineThreads)
+k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int slices)
+{
+    __shared__ Cand s_part[kCombineThreads / 32];
+    __shared__ int64_t s_top[kCombineThreads / 32];
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < kSymbols * kRowPad; k += kCombineThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    const int len2 = G.uniform_len2;
+    const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
+    const int64_t rel = int64_t(blockIdx.x) * kCombineThreads + tid;
+    const int64_t n = tile_base(first) + rel;
+    const bool valid = n >= first && n < last;
+
+    int64_t key = kKeyNone;
+    bool unresolved = false;
+    const int floor_rank = T.nranks - K;
+    const bool floor_none = floor_rank <= 0;
+    const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+    const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
+    if (valid) {
+        uint32_t na = 0, nb = 0, nc = 0, rb = 0;
+        for (int sl = 0; sl < slices; sl++) {
+            const uint2 v = P.partial[int64_t(sl) * P.partial_stride + rel];
+            na += v.x & 0xFFFFu; nb += v.x >> 16; nc += v.y & 0xFFFFu; rb |= v.y >> 16;
+        }
+        const int64_t ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
+        const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
+        key = int64_t(len2) * T.kcls[0] + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
+        if (K > 0 && rb) {
+            key += T.kdiff[T.nranks - (__ffs(int(rb)) - 1)];        // lowest set plane = best rank present
+        } else if (floor_none) {
+            key = kKeyNone;
+        } else {
+            key += kfloor;
+            unresolved = !floor_exact;
+        }
+    }
+    Cand mine{ unresolved ? kKeyNone : key, unresolved || key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
+    Cand best = block_best<kCombineThreads>(mine, s_part);          // also orders the s_code writes
+    if (T.exact) {
+        // settle: any unresolved offset whose bound could beat the block's best looks up its true rank
+        int again = __syncthreads_or(unresolved && !better(best.key, best.off, key, int32_t(n)));
+        while (again) {
+            if (unresolved && !better(best.key, best.off, key, int32_t(n))) {
+                uint32_t rmax = 0;
+                for (int i = 0; i < len2; i++) {
+                    uint32_t c1 = symbol_of(P.seq1[n + i]), c2 = symbol_of(P.seq2s[i]);
+                    if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+                    rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
+                }
+                key = rmax ? key - kfloor + T.kdiff[rmax] : kKeyNone;
+                unresolved = false;
+                mine = Cand{ key, key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
+            }
+            best = block_best<kCombineThreads>(mine, s_part);
+            again = __syncthreads_or(unresolved && !better(best.key, best.off, key, int32_t(n)));
+        }
+    } else {
+        // re-score mode: per 32-offset word an upper estimate of its keys for k_finish
+        int64_t top = valid ? key : kKeyNone;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int64_t o = __shfl_xor_sync(0xFFFFFFFFu, top, d);
+            top = o > top ? o : top;
+        }
+        if (lane == 0) {
+            P.lane_keys[int64_t(blockIdx.x) * (kCombineThreads / 32) + warp] = top;
+            s_top[warp] = top;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        TileRec rec;
+        rec.key = best.key; rec.offset = best.off;
+        rec.ub_key = kKeyNone;
+        if (!T.exact)
+            for (int w = 0; w < kCombineThreads / 32; w++) rec.ub_key = s_top[w] > rec.ub_key ? s_top[w] : rec.ub_key;
+        rec.ub_offset = 0x7FFFFFFF; rec.score = 0.0; rec.flags = 0; rec.pad = 0;
+        P.tiles[blockIdx.x] = rec;
     }
 }
 
@@ -691,8 +807,24 @@ void allow_big_smem(Kernel kernel, bool (&done)[64])
 
 template <int NB, int K, bool BS>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, bool batch, int sm_count,
-                      int key_planes, int64_t key_bias, cudaStream_t stream)
+                      int key_planes, int64_t key_bias, const SliceGeom& SG, cudaStream_t stream)
 {
+    if (SG.slices > 1) {
+        // G is the finish geometry (256-offset tiles); the scan runs on its own warp tiles
+        BatchGeom Gs = G;
+        Gs.tile = SG.scan_tile;
+        Gs.total_tiles = SG.scan_tiles;
+        Gs.tiles_per_query = SG.scan_tiles;
+        const int warps = Gs.tile / 1024;
+        const int nwords = round_up4(warps * 32 + chunk / 32);
+        const size_t smem = scan_smem_bytes(K, chunk, warps);
+        static bool done[64];
+        allow_big_smem(k_scan<NB, K, false, true>, done);
+        k_scan<NB, K, false, true><<<dim3(Gs.total_tiles, SG.slices), warps * 32, smem, stream>>>(T, Gs, P, nwords, chunk, 0, 0,
+                                                                                                 SG.slice_len);
+        k_combine<K><<<G.total_tiles, kCombineThreads, 0, stream>>>(T, G, P, SG.slices);
+        return;
+    }
     if (batch) {
         const int warps = 4;
         const int nwords = round_up4(32 + chunk / 32);
@@ -712,18 +844,18 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         static bool done[64];
-        allow_big_smem(k_scan<NB, K, BS>, done);
-        k_scan<NB, K, BS><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias);
+        allow_big_smem(k_scan<NB, K, BS, false>, done);
+        k_scan<NB, K, BS, false><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias, 0);
     }
 }
 
 template <int NB>
 void launch_scan_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int K, int chunk, bool batch, int sm_count,
-                    int key_planes, int64_t key_bias, cudaStream_t stream)
+                    int key_planes, int64_t key_bias, const SliceGeom& SG, cudaStream_t stream)
 {
-#define PSA_SCAN_CASE(KK)                                                                                              \
-    if (key_planes > 0) launch_scan_inst<NB, KK, true>(T, G, P, chunk, batch, sm_count, key_planes, key_bias, stream); \
-    else launch_scan_inst<NB, KK, false>(T, G, P, chunk, batch, sm_count, 0, 0, stream);                              \
+#define PSA_SCAN_CASE(KK)                                                                                                  \
+    if (key_planes > 0) launch_scan_inst<NB, KK, true>(T, G, P, chunk, batch, sm_count, key_planes, key_bias, SG, stream); \
+    else launch_scan_inst<NB, KK, false>(T, G, P, chunk, batch, sm_count, 0, 0, SG, stream);                              \
     break;
     switch (K) {
     case 0: PSA_SCAN_CASE(0)
@@ -780,7 +912,7 @@ void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P
 }
 
 void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int64_t max_len2, bool batch,
-                 bool sliced_ok, int sm_count, cudaStream_t stream)
+                 bool sliced_ok, int sm_count, const SliceGeom& SG, cudaStream_t stream)
 {
     if (G.total_tiles < 1) return;
     const int chunk = scan_chunk_steps(rank_planes, max_len2);
@@ -788,9 +920,9 @@ void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, i
     const int nb = max_len2 <= 127 ? 7 : max_len2 <= 1023 ? 10 : 15;
     const int key_planes = sliced_ok ? sliced_key_planes(T, max_len2, nb, &key_bias) : 0;
     batch = batch && max_len2 <= 1023 && G.last < 0 && G.tile == 1024;
-    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
-    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
-    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, stream);
+    if (max_len2 <= 127) launch_scan_nb<7>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, SG, stream);
+    else if (max_len2 <= 1023) launch_scan_nb<10>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, SG, stream);
+    else launch_scan_nb<15>(T, G, P, rank_planes, chunk, batch, sm_count, key_planes, key_bias, SG, stream);
 }
 
 } // namespace psa

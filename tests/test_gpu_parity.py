@@ -234,3 +234,46 @@ def test_multi_gpu_single_process(psa, port, synth):
         tied = synth.letters(64, 50_000) + core + synth.letters(65, 80_000) + core + synth.letters(66, 30_000)
         r = c.search([1, 3, 4, 2], True, tied, core)
         assert r.offset == 50_000 and same_answer(r, port.search([1, 3, 4, 2], True, tied, core, nthreads=8))
+
+
+def test_all_stacked_blocks(psa, ctx, tmp_path, input_blocks):
+    """every block of an input.txt-style file (the reference parses only the first)."""
+    _set_engine(ctx, 0)
+    text = "\n\n".join(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] for b in input_blocks)
+    (tmp_path / "input.txt").write_text(text + "\n\n")
+    n = ctx.run_files_all(str(tmp_path / "input.txt"), str(tmp_path / "output.txt"))
+    assert n == len(input_blocks)
+    lines = (tmp_path / "output.txt").read_text().split("\n")
+    assert len(lines) == 2 * n
+    for k, b in enumerate(input_blocks):
+        e = b["expect"]
+        mut = b["seq2"][: e["char_offset"]] + e["ch"] + b["seq2"][e["char_offset"] + 1:]
+        assert lines[2 * k] == mut and lines[2 * k + 1] == "%d %s" % (e["offset"], e["score_g"])
+    import subprocess
+    p = subprocess.run([psa.CLI_PATH, "--all-blocks"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and (tmp_path / "output.txt").read_text().split("\n") == lines
+
+
+@pytest.mark.parametrize("slices,planes", [(0, -1), (2, -1), (5, 0), (16, 1)])
+def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes):
+    """One query cut along its alignment steps (k_scan slices + k_combine): same answers as the oracle for exact
+    and re-scored weights, explicit ranges, unresolved ranks (0 planes) and ties."""
+    _set_engine(ctx, 2, planes)
+    ctx.set_option("slices", slices)
+    try:
+        for b in (input_blocks[0], input_blocks[4], input_blocks[6], input_blocks[9]):
+            r = ctx.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"])
+            assert same_answer(r, b["expect"]), (slices, planes, b["weights_text"], r)
+        s1, s2 = synth.letters(91, 30000), synth.letters(92, 777)
+        core = synth.letters(93, 900)
+        tied = synth.letters(94, 3000) + core + synth.letters(95, 4000) + core + synth.letters(96, 100)
+        for w in ([1, 3, 4, 2], [1.5, 2.6, 0.1, 0.2], [1, 1, 1, 1]):
+            for is_max in (True, False):
+                assert same_answer(ctx.search(w, is_max, s1, s2), port.search(w, is_max, s1, s2, nthreads=4))
+                assert same_answer(ctx.search_range(w, is_max, s1, s2, 1000, 20011), port.search(w, is_max, s1, s2, 1000, 20011))
+                assert same_answer(ctx.search(w, is_max, tied, core), port.search(w, is_max, tied, core))
+        if slices >= 2:
+            assert ctx.stat("slices") >= 2
+    finally:
+        ctx.set_option("slices", 0)
+        _set_engine(ctx, 0)
