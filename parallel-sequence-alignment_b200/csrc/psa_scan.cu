@@ -30,47 +30,74 @@ namespace psa {
 
 namespace {
 
-constexpr int kProfileThreads = 256;
+constexpr int kProfileThreads = 64;      // few, fat threads: a 3000-letter Seq1 is only ~300 words
 constexpr int kScanChunkMax = 1024;     // alignment steps staged per shared-memory window
 
+// -------------------------------------------------------------------------------------------------
+// k_profile: bit planes of Seq1 against every Seq2 symbol.  One thread per 32-position word: each position
+// contributes, per plane kind, a 28-bit column (one bit per row symbol) looked up by its Seq1 symbol; a
+// 32x32 bit transpose then turns 32 columns into the 28 row words.  (2+K) transposes per word instead of
+// 28 x 32 table lookups.
 // -------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kProfileThreads)
 k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
 {
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
-    for (int k = threadIdx.x; k < kSymbols * kRowPad; k += kProfileThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
+    if (threadIdx.x < 32) {
+        const int c = threadIdx.x;
+        uint32_t b0 = 0, b1 = 0, rk[K > 0 ? K : 1] = {};
+        if (c < kSymbols) {
+            for (int r = 0; r < kSymbols; r++) {
+                const uint32_t code = T.code[r][c];
+                b0 |= (code & 1u) << r;
+                b1 |= ((code >> 1) & 1u) << r;
+                const int rank = int(code >> 2);
+#pragma unroll
+                for (int k = 0; k < K; k++) rk[k] |= uint32_t(rank != 0 && rank == T.nranks - k) << r;
+            }
+        }
+        s_col[0][c] = b0;
+        s_col[1][c] = b1;
+#pragma unroll
+        for (int k = 0; k < K; k++) s_col[2 + k][c] = rk[k];
+    }
     __syncthreads();
-    const int64_t total = int64_t(kPlaneRows) * P.plane_words;
-    for (int64_t idx = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; idx < total;
-         idx += int64_t(gridDim.x) * kProfileThreads) {
-        const int row = int(idx / P.plane_words);
-        const int64_t w = idx - int64_t(row) * P.plane_words;
+    for (int64_t w = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; w < P.plane_words;
+         w += int64_t(gridDim.x) * kProfileThreads) {
         const int64_t base = w * 32;
-        uint32_t b0 = 0, b1 = 0, r[K > 0 ? K : 1] = {};
-        if (row < kSymbols && base < G.len1) {
+        uint8_t sym[32];
+        int n = 0;
+        if (base < G.len1) {
             // 32 bytes of Seq1; the buffer is padded so the vector loads stay inside the allocation
             const uint4 v0 = *reinterpret_cast<const uint4*>(P.seq1 + base);
             const uint4 v1 = *reinterpret_cast<const uint4*>(P.seq1 + base + 16);
             const uint32_t words[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-            const int n = (G.len1 - base) < 32 ? int(G.len1 - base) : 32;
+            n = (G.len1 - base) < 32 ? int(G.len1 - base) : 32;
 #pragma unroll
             for (int t = 0; t < 32; t++) {
-                if (t < n) {
-                    uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
-                    if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
-                    const uint32_t code = s_code[row * kRowPad + c];
-                    b0 |= (code & 1u) << t;
-                    b1 |= ((code >> 1) & 1u) << t;
-                    const int rank = int(code >> 2);
-#pragma unroll
-                    for (int k = 0; k < K; k++) r[k] |= uint32_t(rank != 0 && rank == T.nranks - k) << t;
-                }
+                uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
+                if (t < n && c == 0xFFu) atomicOr(P.err_flag, 1);
+                sym[t] = uint8_t(c == 0xFFu ? 0u : c);
             }
         }
-        P.cls_planes[idx] = make_uint2(b0, b1);
+        uint32_t m[32], b0rows[kPlaneRows];
 #pragma unroll
-        for (int k = 0; k < K; k++) P.rank_planes[idx * K + k] = r[k];
+        for (int kind = 0; kind < 2 + K; kind++) {
+#pragma unroll
+            for (int t = 0; t < 32; t++) m[t] = t < n ? s_col[kind][sym[t]] : 0u;
+            transpose32(m);
+            if (kind == 0) {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) b0rows[r] = m[r];
+            } else if (kind == 1) {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) P.cls_planes[int64_t(r) * P.plane_words + w] = make_uint2(b0rows[r], m[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) P.rank_planes[(int64_t(r) * P.plane_words + w) * K + (kind - 2)] = m[r];
+            }
+        }
     }
 }
 
@@ -899,8 +926,7 @@ int64_t scan_plane_words(int64_t len1)
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
                     cudaStream_t stream)
 {
-    const int64_t total = int64_t(kPlaneRows) * P.plane_words;
-    int64_t blocks = (total + kProfileThreads - 1) / kProfileThreads;
+    int64_t blocks = (P.plane_words + kProfileThreads - 1) / kProfileThreads;
     const int64_t cap = int64_t(sm_count) * 16;
     if (blocks > cap) blocks = cap;
     switch (rank_planes) {
