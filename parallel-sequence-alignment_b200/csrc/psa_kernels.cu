@@ -153,7 +153,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 // -------------------------------------------------------------------------------------------------
 constexpr int kFinishWarps = 8;
 constexpr int kFinishThreads = kFinishWarps * 32;
-constexpr int kFinishChunk = 256;
+constexpr int kFinishChunk = 1024;
 constexpr int kFinishList = 32;       // candidate tiles remembered per query before falling back to a full walk
 
 template <int WPQ>
@@ -249,7 +249,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
                             if (c2 == 0xFFu) c2 = 0;                   // flagged by the kernels before us
                             s_q[warp][i] = uint16_t(c2 * kRowPad);
                         }
-#pragma unroll 9
+#pragma unroll 8
                         for (int i = lane; i < cl + 31; i += 32) {
                             const int64_t p = n0 + c0 + i;
                             uint32_t c1 = p < G.len1 ? symbol_of(P.seq1[p]) : 0u;

@@ -609,7 +609,8 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     __shared__ int64_t s_top[kCombineThreads / 32];
     __shared__ uint8_t s_code[kSymbols * kRowPad];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < kSymbols * kRowPad; k += kCombineThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    if (T.exact)            // only the settle path reads it
+        for (int k = tid; k < kSymbols * kRowPad; k += kCombineThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     const int len2 = G.uniform_len2;
     const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
     const int64_t rel = int64_t(blockIdx.x) * kCombineThreads + tid;
