@@ -51,6 +51,19 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
 
 
+def profiled_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    capture of this workload (profiles/r01_summary.json, written by tools/ncu_summary.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "r01_summary.json")
+    if not os.path.exists(p):
+        return None, None
+    rec = json.load(open(p)).get(workload, {})
+    for name, v in rec.items():
+        if name.startswith(kernel):
+            return v.get("dram_bytes_per_launch"), v
+    return None, None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -272,6 +285,8 @@ def run_ours(args, synth, rank, local_rank, world):
         peak = SM_COUNT * 128 * clk / LANE_OPS_PER_PAIR_EVAL
         alg_bytes = batch.len1 + sum(batch.lens) + batch.nq * HBM_BYTES_PER_QUERY_FIXED
         engine = ctx.stat("engine")
+        kname = ("k_scan_batch" if ctx.stat("batch_mode") else "k_scan") if engine == 2 else "k_exact_tiles"
+        traffic, prof = profiled_traffic(args.workload, kname)
         # the scan kernel's own bound: its inner loop issues ALU_OPS_PER_WARP_STEP integer-ALU instructions (LOP3/SHF,
         # 64 lanes/clk/SM) per warp per alignment step, and a warp step covers 1024 pair-evals (profiles/)
         kernel_model_peak = SM_COUNT * 64 * clk * 32.0 / ALU_OPS_PER_WARP_STEP
@@ -287,8 +302,12 @@ def run_ours(args, synth, rank, local_rank, world):
                     "d2h_bytes_per_step": 48 * batch.nq + 16, "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "int-alu-issue", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
-                         "traffic": None,
-                         "kernel": "k_scan" if engine == 2 else "k_exact_tiles", "kernel_ms": k_s * 1e3,
+                         "traffic": traffic,
+                         "kernel": kname, "kernel_ms": k_s * 1e3,
+                         "ncu": None if prof is None else {"capture": "profiles/" + prof["capture"].replace(".ncu-rep", "_metrics.csv"),
+                                                           "alu_pipe_pct_of_peak_active": prof["alu_pipe_pct_of_peak_active"],
+                                                           "issue_active_pct": prof["issue_active_pct"],
+                                                           "dram_throughput_pct": prof["dram_throughput_pct"]},
                          "kernel_share_of_step": (main_ns * 1e-6) / dev_ms if dev_ms else None,
                          "model": "SURVEY 8(d): 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM x 148 SMs x "
                                   f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} clock); not HBM, not tensor. frac > 1 is "
