@@ -242,8 +242,18 @@ def run_ours(args, synth, rank, local_rank, world):
     for _ in range(args.steps):
         flush_l2()
         dev_ms += ctx.run()
+        launches += ctx.stat("kernel_launches")
+    barrier()
+    # the same K steps once more with the dominant kernel bracketed by its own events (roofline numerator);
+    # kept out of the loop above because an event between two kernels stops them from overlapping
+    ctx.set_option("kernel_events", 1)
+    dev_ms_bracketed = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        dev_ms_bracketed += ctx.run()
         main_ns += ctx.stat("main_kernel_ns")
         launches += ctx.stat("kernel_launches")
+    ctx.set_option("kernel_events", 0)
     barrier()
     dev_ms_max = max_over_ranks(dev_ms)
     total_pe = sum_over_ranks(float(pair_evals))
@@ -308,7 +318,7 @@ def run_ours(args, synth, rank, local_rank, world):
                                                            "alu_pipe_pct_of_peak_active": prof["alu_pipe_pct_of_peak_active"],
                                                            "issue_active_pct": prof["issue_active_pct"],
                                                            "dram_throughput_pct": prof["dram_throughput_pct"]},
-                         "kernel_share_of_step": (main_ns * 1e-6) / dev_ms if dev_ms else None,
+                         "kernel_share_of_step": (main_ns * 1e-6) / dev_ms_bracketed if dev_ms_bracketed else None,
                          "model": "SURVEY 8(d): 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM x 148 SMs x "
                                   f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} clock); not HBM, not tensor. frac > 1 is "
                                   "possible because the bit-sliced kernel spends 0.32 ALU lane-ops per pair-eval, not 2",

@@ -103,6 +103,13 @@ __device__ __forceinline__ QueryGeom query_geom(const BatchGeom& G, const int64_
     return g;
 }
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with the PDL attribute may start while its
+// predecessor in the stream is still running; it must call pdl_wait() before touching anything the predecessor
+// writes.  The predecessor calls pdl_launch_dependents() once its blocks no longer need the SM to themselves.
+// Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, global -> shared), sm_90+/sm_100a -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 

@@ -64,6 +64,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
     int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
@@ -279,29 +280,29 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     return PSA_OK;
 }
 
-int run_device(psa_context* ctx, DeviceState& d)
+int run_device(psa_context* ctx, DeviceState& d, bool timed)
 {
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
-    PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     PSA_CUDA(ctx, cudaMemsetAsync(d.flags.p, 0, sizeof(int32_t) * 4, d.stream));
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
-        PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, ctx->opt_sliced_keys != 0, d.sm_count, d.SG, d.stream);
         if (d.SG.slices > 1) ctx->st_launches += 1;
-        PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 2;
     } else {
-        PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_exact_tiles(ctx->table, d.G, d.P, d.stream);
-        PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         ctx->st_launches += 1;
     }
     launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
     ctx->st_launches += 1;
     PSA_CUDA(ctx, cudaGetLastError());
-    PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     ctx->st_tiles += d.G.total_tiles;
     return PSA_OK;
 }
@@ -422,6 +423,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
@@ -613,12 +615,12 @@ int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, con
     return PSA_OK;
 }
 
-static int run_async(psa_context* ctx)
+static int run_async(psa_context* ctx, bool timed)
 {
     if (!ctx || !ctx->prepared) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch prepared") : PSA_ERR_ARG;
     ctx->st_launches = ctx->st_cand = ctx->st_tiles = ctx->st_main_ns = 0;
     for (DeviceState& d : ctx->devs) {
-        int rc = run_device(ctx, d);
+        int rc = run_device(ctx, d, timed);
         if (rc) return rc;
     }
     ctx->ran = true;
@@ -627,7 +629,7 @@ static int run_async(psa_context* ctx)
 
 int psa_batch_run(psa_context* ctx, float* device_ms)
 {
-    int rc = run_async(ctx);
+    int rc = run_async(ctx, true);
     if (rc) return rc;
     float worst = 0.f;
     for (DeviceState& d : ctx->devs) {
@@ -637,9 +639,11 @@ int psa_batch_run(psa_context* ctx, float* device_ms)
         float ms = 0.f;
         PSA_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         worst = std::max(worst, ms);
-        float kms = 0.f;
-        PSA_CUDA(ctx, cudaEventElapsedTime(&kms, d.evk0, d.evk1));
-        ctx->st_main_ns = std::max(ctx->st_main_ns, (long long)(kms * 1e6));
+        if (ctx->opt_kernel_events) {
+            float kms = 0.f;
+            PSA_CUDA(ctx, cudaEventElapsedTime(&kms, d.evk0, d.evk1));
+            ctx->st_main_ns = std::max(ctx->st_main_ns, (long long)(kms * 1e6));
+        }
     }
     if (device_ms) *device_ms = worst;
     return PSA_OK;
@@ -694,7 +698,7 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, cons
     int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
     if (rc) return rc;
     const auto t1 = std::chrono::steady_clock::now();
-    if ((rc = run_async(ctx))) return rc;
+    if ((rc = run_async(ctx, false))) return rc;
     const auto t2 = std::chrono::steady_clock::now();
     rc = psa_batch_fetch(ctx, out);
     if (trace) {
@@ -712,7 +716,7 @@ int psa_search_range(psa_context* ctx, const double weights[4], int is_max, cons
     const int64_t q_off[2] = { 0, len2 };
     int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2, q_off, 1, first, last);
     if (rc) return rc;
-    if ((rc = run_async(ctx))) return rc;
+    if ((rc = run_async(ctx, false))) return rc;
     return psa_batch_fetch(ctx, out);
 }
 

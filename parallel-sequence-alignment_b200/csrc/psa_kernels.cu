@@ -136,6 +136,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
             P.tiles[tile_id] = r;
         }
     }
+    pdl_launch_dependents();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -176,6 +177,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     if (tid == 0) s_pos = 0ull;
     if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
+    pdl_wait();                                                         // tile records come from the kernel before us
     const int q = WPQ == 1 ? blockIdx.x * kFinishWarps + warp : blockIdx.x;
     if (q >= G.nq) return;
     const int gtid = WPQ == 1 ? lane : tid;                             // index within the query's thread group
@@ -344,8 +346,8 @@ void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtr
 void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream)
 {
     if (G.nq < 1) return;
-    if (G.nq >= 256) k_finish<1><<<(G.nq + kFinishWarps - 1) / kFinishWarps, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
-    else k_finish<kFinishWarps><<<G.nq, kFinishThreads, 0, stream>>>(T, G, P, scan_records ? 1 : 0);
+    if (G.nq >= 256) launch_dependent(k_finish<1>, dim3((G.nq + kFinishWarps - 1) / kFinishWarps), dim3(kFinishThreads), 0, stream, T, G, P, scan_records ? 1 : 0);
+    else launch_dependent(k_finish<kFinishWarps>, dim3(G.nq), dim3(kFinishThreads), 0, stream, T, G, P, scan_records ? 1 : 0);
 }
 
 } // namespace psa

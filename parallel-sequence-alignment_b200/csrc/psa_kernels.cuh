@@ -55,6 +55,24 @@ void launch_scan(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, i
 // batch mode (window shared by many queries, tile = 1024) applies when every query fits one window
 bool scan_batch_mode(const BatchGeom& G, int64_t max_len2, int sm_count);
 
+// Launch `kernel` so that it may overlap the tail of the previous kernel in `stream` (programmatic dependent
+// launch); the kernel itself orders its reads with pdl_wait().
+template <class... KArgs, class... Args>
+inline void launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // scan engine limits
 constexpr int kDefaultEngine = 2;                   // engine picked by "auto" (1 scalar, 2 bit-sliced scan)
 constexpr int kScanWarps = 4;                       // max warps per block; a warp owns 1024 offsets

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kProfileThreads)
 k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P)
 {
     __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
+    pdl_launch_dependents();                                        // the scan may set itself up while we run
     if (threadIdx.x < 32) {
         const int c = threadIdx.x;
         uint32_t b0 = 0, b1 = 0, rk[K > 0 ? K : 1] = {};
@@ -459,6 +460,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
     racc[0] = ~vmask;                       // offsets outside the range count as saturated
     uint32_t parity = 0;
+    pdl_wait();                                                     // the bit planes come from k_profile
     const int steps_all = (len2 + 31) & ~31;
     const int step_begin = SLICE ? int(blockIdx.y) * slice_len : 0;                    // multiple of 128
     const int steps_total = SLICE ? ((step_begin + slice_len) < steps_all ? (step_begin + slice_len) : steps_all) : steps_all;
@@ -534,6 +536,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
 
     // ---- epilogue -------------------------------------------------------------------------------------
+    pdl_launch_dependents();
     if (SLICE) {
         // partial counts of this slice, one uint2 per offset: {N(b0) | N(b1) << 16, N(b0&b1) | rank bits << 16}
         if (warp_active) {
@@ -611,6 +614,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (T.exact)            // only the settle path reads it
         for (int k = tid; k < kSymbols * kRowPad; k += kCombineThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    pdl_wait();                                                     // partial counts come from the scan slices
     const int len2 = G.uniform_len2;
     const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
     const int64_t rel = int64_t(blockIdx.x) * kCombineThreads + tid;
@@ -643,6 +647,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     }
     Cand mine{ unresolved ? kKeyNone : key, unresolved || key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
     Cand best = block_best<kCombineThreads>(mine, s_part);          // also orders the s_code writes
+    pdl_launch_dependents();
     if (T.exact) {
         // settle: any unresolved offset whose bound could beat the block's best looks up its true rank
         int again = __syncthreads_or(unresolved && !better(best.key, best.off, key, int32_t(n)));
@@ -722,6 +727,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     if (T.exact)
         for (int k = tid; k < kSymbols * kRowPad; k += blockDim.x) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     __syncthreads();
+    pdl_wait();                                                     // the bit planes come from k_profile
     if (warp == 0 && lane < kPlaneRows) {
         const int64_t g0 = tb >> 5;
         tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(nwords) * 8u, &s_bar);
@@ -794,6 +800,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         if (lane == 0) P.tiles[rec_id] = rec;
     }
     if (!staged) mbar_wait(&s_bar, 0);      // never leave with a bulk copy in flight
+    pdl_launch_dependents();
 }
 
 // The bit-sliced epilogue applies when keys are small integers: exact mode, |multipliers| < 2^kSlicedMaxBits, rank
@@ -848,9 +855,9 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         static bool done[64];
         allow_big_smem(k_scan<NB, K, false, true>, done);
-        k_scan<NB, K, false, true><<<dim3(Gs.total_tiles, SG.slices), warps * 32, smem, stream>>>(T, Gs, P, nwords, chunk, 0, 0,
-                                                                                                 SG.slice_len);
-        k_combine<K><<<G.total_tiles, kCombineThreads, 0, stream>>>(T, G, P, SG.slices);
+        launch_dependent(k_scan<NB, K, false, true>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P, nwords, chunk, 0,
+                         int64_t(0), SG.slice_len);
+        launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
         return;
     }
     if (batch) {
@@ -866,14 +873,14 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         dim3 grid((G.nq + qpb - 1) / qpb, tiles);
         static bool done[64];
         allow_big_smem(k_scan_batch<NB, K, BS>, done);
-        k_scan_batch<NB, K, BS><<<grid, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
+        launch_dependent(k_scan_batch<NB, K, BS>, grid, dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
     } else {
         const int warps = G.tile / 1024;
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         static bool done[64];
         allow_big_smem(k_scan<NB, K, BS, false>, done);
-        k_scan<NB, K, BS, false><<<G.total_tiles, warps * 32, smem, stream>>>(T, G, P, nwords, chunk, key_planes, key_bias, 0);
+        launch_dependent(k_scan<NB, K, BS, false>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, key_planes, key_bias, 0);
     }
 }
 

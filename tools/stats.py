@@ -3,6 +3,7 @@ sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(_
 psa = importlib.import_module("parallel-sequence-alignment_b200")
 synth = importlib.import_module("parallel-sequence-alignment_b200.synth")
 ctx = psa.Context(1)
+ctx.set_option("kernel_events", 1)
 for name in ("c3","c5","c4","c1"):
     wl = synth.workload(name, nq=(4096 if name=="c5" else None)) if name!="c1" else None
     if wl is None:
