@@ -45,9 +45,9 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, flags, cls_planes, rank_planes, partial;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial;
     SliceGeom SG{};
-    PinBuf h_qoff, h_tile_start, h_out, h_flags;
+    PinBuf h_qoff, h_tile_start, h_out;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
     BatchGeom G{};
@@ -133,10 +133,10 @@ int ensure_pin(psa_context* ctx, PinBuf& b, size_t bytes)
 void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
-    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.flags, &d.partial,
+    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial,
                        &d.cls_planes, &d.rank_planes })
         if (b->p) cudaFree(b->p);
-    for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out, &d.h_flags })
+    for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -172,8 +172,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     const bool scan = ctx->engine == 2;
     const int tile = scan ? ctx->scan_tile : kExactTile;
     int rc;
-    if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq))) return rc;
-    if ((rc = ensure_pin(ctx, d.h_flags, sizeof(int32_t) * 4))) return rc;
+    if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq + 16))) return rc;     // + the 4 flag words, one copy back
     const int64_t byte0 = q_off[q_begin];
     const int64_t seq2_bytes = q_off[q_end] - byte0;
     const bool uniform_len = ctx->uniform_len2 > 0;       // every query of the batch has the same length
@@ -237,10 +236,9 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         if ((rc = ensure_dev(ctx, d.tile_start, sizeof(int32_t) * (nq + 1)))) return rc;
     }
     if ((rc = ensure_dev(ctx, d.tiles, sizeof(TileRec) * (size_t)tiles))) return rc;
-    if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq))) return rc;
+    if ((rc = ensure_dev(ctx, d.out, sizeof(QueryRec) * nq + 16))) return rc;
     if (scan && !ctx->table.exact)
         if ((rc = ensure_dev(ctx, d.lane_keys, sizeof(int64_t) * (size_t)tiles * (fin_tile / 32)))) return rc;
-    if ((rc = ensure_dev(ctx, d.flags, sizeof(int32_t) * 4))) return rc;
     if (scan) {
         if ((rc = ensure_dev(ctx, d.cls_planes, sizeof(uint2) * (size_t)plane_words * kPlaneRows))) return rc;
         if ((rc = ensure_dev(ctx, d.rank_planes,
@@ -272,8 +270,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
     d.P.partial = (uint2*)d.partial.p;
     d.P.partial_stride = int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
-    d.P.cand_count = (int32_t*)d.flags.p;
-    d.P.err_flag = (int32_t*)d.flags.p + 1;
+    d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // flags sit behind the records
+    d.P.err_flag = d.P.cand_count + 1;
     d.P.cls_planes = (uint2*)d.cls_planes.p;
     d.P.rank_planes = (uint32_t*)d.rank_planes.p;
     d.P.plane_words = plane_words;
@@ -285,7 +283,7 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
-    PSA_CUDA(ctx, cudaMemsetAsync(d.flags.p, 0, sizeof(int32_t) * 4, d.stream));
+    PSA_CUDA(ctx, cudaMemsetAsync(d.P.cand_count, 0, sizeof(int32_t) * 4, d.stream));
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
@@ -657,15 +655,14 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
     for (DeviceState& d : ctx->devs) {
         if (!d.active) continue;
         PSA_CUDA(ctx, cudaSetDevice(d.dev));
-        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, sizeof(QueryRec) * d.G.nq, cudaMemcpyDeviceToHost, d.stream));
-        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_flags.p, d.flags.p, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, d.stream));
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, sizeof(QueryRec) * d.G.nq + 16, cudaMemcpyDeviceToHost, d.stream));
     }
     bool bad_symbol = false;
     for (DeviceState& d : ctx->devs) {
         if (!d.active) continue;
         PSA_CUDA(ctx, cudaSetDevice(d.dev));
         PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        const int32_t* fl = (const int32_t*)d.h_flags.p;
+        const int32_t* fl = (const int32_t*)((const char*)d.h_out.p + sizeof(QueryRec) * d.G.nq);
         ctx->st_cand += fl[0];
         if (fl[1]) bad_symbol = true;
     }
