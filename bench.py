@@ -152,6 +152,25 @@ def reference_sample(synth, name, seconds=12.0):
                     f"(-O3 build, table filled single-threaded){cap_note}", "wl": wl}
 
 
+def reference_gpu_probe(workload):
+    """The reference's OWN CUDA path (gpu_run_program and its kernels from cuda_funcs.cu, recompiled for sm_100a in
+    oracle/_ref) timed on a few queries of the workload, in a child process with a timeout -- "the reference's kernel
+    on the same box" of SURVEY 8(d).  Reported baseline only; that path races across blocks."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_probe.py"), workload, "16"],
+                           capture_output=True, text=True, timeout=180)
+        last = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode == 0 and last:
+            d = json.loads(last[-1])
+            return {"value": d["pair_evals_per_s"], "unit": UNIT, "queries": d["queries"], "seconds": d["seconds"],
+                    "answers_differing_from_cpu_reference": d["answers_differing_from_cpu_reference"],
+                    "what": "reference gpu_run_program (cudaMalloc + 4 kernels + cudaFree per query), one GPU, "
+                            "Seq1 truncated to its 10000 capacity where longer"}
+        return {"unavailable": (p.stderr or "no output")[-200:]}
+    except Exception as e:       # noqa: BLE001 - a baseline must never take the benchmark down
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference_arm(args, synth, rank, world):
     if rank != 0:
         return
@@ -336,6 +355,7 @@ def run_ours(args, synth, rank, local_rank, world):
             t = s["run"](s["sample"])
             line["cpu_baseline"] = {"value": s["pair_evals"] / t, "unit": UNIT, "cores": s["threads"], "kind": s["kind"],
                                     "sample": s["desc"], "seconds": t}
+            line["reference_gpu"] = reference_gpu_probe(args.workload)
         print(json.dumps(line), flush=True)
     ctx.close()
     if use_dist:
