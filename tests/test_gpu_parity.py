@@ -277,3 +277,31 @@ def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes)
     finally:
         ctx.set_option("slices", 0)
         _set_engine(ctx, 0)
+
+
+WEIGHT_ZOO = [[10, 20, 15, 5], [16, 16, 16, 1], [31, 1, 1, 1], [33, 2, 1, 1], [1.5, 0.25, 4, 2], [0.125, 0.5, 0.25, 8],
+              [-1, 2, -3, 0.5], [-2, -2, -2, -2], [1e6, 3, 1e-3, 2], [2.0 ** 40, 1, 1, 1], [1e-9, 2e-9, 3e-9, 4e-9],
+              [1000, 1, 1, 1], [0, 5, 0, 5], [3, 3, 3, 3]]
+
+
+@pytest.mark.parametrize("w", WEIGHT_ZOO, ids=[str(w) for w in WEIGHT_ZOO])
+def test_weight_zoo(ctx, engine, port, synth, w):
+    """Weights on both sides of every internal switch: sliced / transposed epilogue (multiplier limit 31),
+    dyadic fixed point, negative and zero weights, exact / re-scored ordering, huge and tiny magnitudes."""
+    s1 = synth.letters(301, 2600)
+    qs = [synth.letters(302, 40), synth.letters(303, 200), synth.letters(304, 1100), s1[700:760], s1[10:1500]]
+    for is_max in (True, False):
+        got = ctx.search_batch(w, is_max, s1, qs)
+        exp = port.search_batch(w, is_max, s1, qs)
+        for k, (g, e) in enumerate(zip(got, exp)):
+            assert same_answer(g, e), (w, is_max, k, g, e)
+
+
+def test_very_long_query_falls_back_to_scalar_engine(ctx, port, synth):
+    """len2 > 32767 is beyond the 15 counter planes of the scan engine: the scalar engine takes over."""
+    _set_engine(ctx, 0)
+    s1, s2 = synth.letters(311, 45000), synth.letters(312, 40000)
+    for w, is_max in (([1, 3, 4, 2], False), ([1.5, 2.6, 0.1, 0.2], True)):
+        r = ctx.search(w, is_max, s1, s2)
+        assert ctx.stat("engine") == 1
+        assert same_answer(r, port.search(w, is_max, s1, s2, nthreads=8))
