@@ -45,7 +45,7 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table;
     SliceGeom SG{};
     PinBuf h_qoff, h_tile_start, h_out;
     // slice of the current batch owned by this GPU
@@ -133,7 +133,7 @@ int ensure_pin(psa_context* ctx, PinBuf& b, size_t bytes)
 void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
-    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial,
+    for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
                        &d.cls_planes, &d.rank_planes })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
@@ -229,6 +229,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     }
 
     const int64_t plane_words = scan_plane_words(len1);
+    if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
     if (!uniform_len) {
@@ -268,6 +269,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.tiles = (TileRec*)d.tiles.p;
     d.P.out = (QueryRec*)d.out.p;
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
+    d.P.code_table = (uint8_t*)d.code_table.p;
     d.P.partial = (uint2*)d.partial.p;
     d.P.partial_stride = int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
     d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // flags sit behind the records

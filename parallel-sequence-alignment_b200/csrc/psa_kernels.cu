@@ -48,6 +48,8 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
         s_tab[k] = e;
     }
     if (tid < 4) s_w[tid] = T.wcls[tid];
+    if (blockIdx.x == 0)            // the finish kernel reads the pair table from global memory
+        for (int k = tid; k < kSymbols * kRowPad; k += kExactThreads) P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
     __syncthreads();
 
     for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {
@@ -165,19 +167,20 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     __shared__ Cand s_part[kFinishWarps];
     __shared__ unsigned long long s_pos;
     __shared__ int s_cnt[4];
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ __align__(16) uint8_t s_code[kSymbols * kRowPad];
     __shared__ double s_w[4];
     __shared__ int s_list[kFinishWarps][kFinishList];
     __shared__ int s_nlist[kFinishWarps];
     __shared__ uint16_t s_q[kFinishWarps][kFinishChunk];               // Seq2 symbol * kRowPad
     __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     if (tid < 4) s_w[tid] = T.wcls[tid];
     if (tid == 0) s_pos = 0ull;
     if (tid < 4) s_cnt[tid] = 0;
+    pdl_wait();                                                         // tile records and the pair table come from the kernels before us
+    for (int k = tid; k < kSymbols * kRowPad / 4; k += kFinishThreads)
+        reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(P.code_table)[k];
     __syncthreads();
-    pdl_wait();                                                         // tile records come from the kernel before us
     const int q = WPQ == 1 ? blockIdx.x * kFinishWarps + warp : blockIdx.x;
     if (q >= G.nq) return;
     const int gtid = WPQ == 1 ? lane : tid;                             // index within the query's thread group

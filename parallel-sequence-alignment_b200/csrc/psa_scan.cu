@@ -45,6 +45,9 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 {
     __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
     pdl_launch_dependents();                                        // the scan may set itself up while we run
+    if (blockIdx.x == 0)            // the pair table for the kernels after us: divergent reads of a kernel parameter are
+        for (int k = threadIdx.x; k < kSymbols * kRowPad; k += kProfileThreads)       // slow, a global copy is not
+            P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
     if (threadIdx.x < 32) {
         const int c = threadIdx.x;
         uint32_t b0 = 0, b1 = 0, rk[K > 0 ? K : 1] = {};
@@ -371,7 +374,7 @@ struct SlicedKeys {
 // striding i; the counts, hence the key without the difference term, are already exact).  Returns the
 // warp's exact best.  All 32 lanes must call.
 template <class Keys>
-__device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_code,
+__device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const BatchPtrs& P,
                                                   const Keys& keys, Cand mine, Cand ub, uint32_t umask,
                                                   int64_t ln0, int64_t qbeg, int len2)
 {
@@ -390,7 +393,7 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
         for (int i = int(threadIdx.x & 31); i < len2; i += 32) {
             uint32_t c1 = symbol_of(P.seq1[off + i]), c2 = symbol_of(P.seq2s[qbeg + i]);
             if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-            rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
+            rmax = max(rmax, uint32_t(__ldg(P.code_table + c2 * kRowPad + c1)) >> 2);
         }
         rmax = __reduce_max_sync(0xFFFFFFFFu, rmax);
         if (rmax) {
@@ -434,13 +437,10 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     uint32_t* s_ro = reinterpret_cast<uint32_t*>(smem + size_t(kPlaneRows) * nwords * kEntry);
     __shared__ Cand s_res[4];
     __shared__ int64_t s_top[4];
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
     const int tile_id = blockIdx.x;
-    if (T.exact)            // only the settle path reads it
-        for (int k = tid; k < kSymbols * kRowPad; k += nthreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     const int q = query_of_tile(P.tile_start, G.nq, tile_id, G.tiles_per_query);
     const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
     const int t = tile_id - qg.tile0;
@@ -565,7 +565,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     }
     if (T.exact) {
         Cand wbest{ kKeyNone, 0x7FFFFFFF };
-        if (warp_active) wbest = settle_unresolved(T, P, s_code, keys, mine, ub, umask, ln0, qbeg, len2);
+        if (warp_active) wbest = settle_unresolved(T, P, keys, mine, ub, umask, ln0, qbeg, len2);
         if (lane == 0) { s_res[warp] = wbest; s_top[warp] = kKeyNone; }
     } else {
         // Re-score mode: keys only pre-select; record an upper estimate per 32-offset word for k_finish.
@@ -610,10 +610,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 {
     __shared__ Cand s_part[kCombineThreads / 32];
     __shared__ int64_t s_top[kCombineThreads / 32];
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (T.exact)            // only the settle path reads it
-        for (int k = tid; k < kSymbols * kRowPad; k += kCombineThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     pdl_wait();                                                     // partial counts come from the scan slices
     const int len2 = G.uniform_len2;
     const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
@@ -646,7 +643,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
         }
     }
     Cand mine{ unresolved ? kKeyNone : key, unresolved || key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
-    Cand best = block_best<kCombineThreads>(mine, s_part);          // also orders the s_code writes
+    Cand best = block_best<kCombineThreads>(mine, s_part);
     pdl_launch_dependents();
     if (T.exact) {
         // settle: any unresolved offset whose bound could beat the block's best looks up its true rank
@@ -657,7 +654,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
                 for (int i = 0; i < len2; i++) {
                     uint32_t c1 = symbol_of(P.seq1[n + i]), c2 = symbol_of(P.seq2s[i]);
                     if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-                    rmax = max(rmax, uint32_t(s_code[c2 * kRowPad + c1]) >> 2);
+                    rmax = max(rmax, uint32_t(__ldg(P.code_table + c2 * kRowPad + c1)) >> 2);
                 }
                 key = rmax ? key - kfloor + T.kdiff[rmax] : kKeyNone;
                 unresolved = false;
@@ -711,7 +708,6 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     unsigned char* s_cls = smem;
     unsigned char* s_rnk = smem + size_t(kPlaneRows) * nwords * 8;
     uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + size_t(kPlaneRows) * nwords * 4 * K);
-    __shared__ uint8_t s_code[kSymbols * kRowPad];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
@@ -724,8 +720,6 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         mbar_init(&s_bar, 1);
         mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(nwords) * uint32_t(8 + 4 * K));
     }
-    if (T.exact)
-        for (int k = tid; k < kSymbols * kRowPad; k += blockDim.x) s_code[k] = T.code[k / kRowPad][k % kRowPad];
     __syncthreads();
     pdl_wait();                                                     // the bit planes come from k_profile
     if (warp == 0 && lane < kPlaneRows) {
@@ -783,7 +777,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         TileRec rec;
         rec.score = 0.0; rec.flags = 0; rec.pad = 0; rec.ub_offset = 0x7FFFFFFF;
         if (T.exact) {
-            const Cand wbest = settle_unresolved(T, P, s_code, keys, mine, ub, umask, ln0, qbeg, len2);
+            const Cand wbest = settle_unresolved(T, P, keys, mine, ub, umask, ln0, qbeg, len2);
             rec.key = wbest.key; rec.offset = wbest.off; rec.ub_key = kKeyNone;
         } else {
             const int64_t top = mine.key > ub.key ? mine.key : ub.key;
