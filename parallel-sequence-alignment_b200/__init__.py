@@ -328,8 +328,16 @@ class Context:
                                           batch.seq2s_ptr, batch.q_off_ptr, batch.nq, out))
 
     @staticmethod
-    def new_result_array(nq: int):
-        return (_CResult * max(nq, 1))()
+    def new_result_array(nq: int, pinned: bool = False):
+        """Result array for search_batch_raw; pinned=True puts it in page-locked memory, which the library then
+        fills straight from the device-to-host copy (no staging, no host pass)."""
+        n = max(nq, 1)
+        if not pinned:
+            return (_CResult * n)()
+        buf = PinnedBuffer(C.sizeof(_CResult) * n)
+        arr = (_CResult * n).from_address(buf.ptr)
+        arr._pin = buf          # keep the allocation alive with the array
+        return arr
 
     @staticmethod
     def result_from_array(out, i: int) -> Result:

@@ -46,15 +46,15 @@ struct TileRec {
 };
 constexpr int kTileExact = 1;
 
-// One record per query, written by the final kernel and copied back to the host.
+// One record per query, written by the finish kernel.  Same layout as the public psa_result (psa_b200.h;
+// static_asserts in psa_engine.cu), so the device-to-host copy lands in the caller's array unchanged.
 struct QueryRec {
-    int64_t key;
-    double  score;        // valid when !exact (re-score mode); host derives it from counts otherwise
-    int32_t offset;
+    int32_t offset;       // -1: no mutation possible at any offset
     int32_t char_offset;
-    int32_t ch;
+    int32_t ch;           // replacement letter in the low byte (psa_mutant::ch + its padding)
     int32_t rank;
-    int32_t counts[4];
+    double  score;        // the reference's double: exact mode from the integer counts, else the re-scored sum
+    int64_t counts[4];
 };
 
 // Launch geometry shared by all kernels of one batch.

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -314,31 +315,10 @@ inline bool swapable(int is_max, double s_old, int off_old, double s_new, int of
     return s_new == s_old && off_new < off_old;
 }
 
-double score_from_counts(const psa_context* ctx, const QueryRec& r)
-{
-    // exact mode: every product and partial sum below is exactly representable, so this equals the
-    // reference's sequential sum + difference bit for bit
-    const double* w = ctx->table.wcls;
-    double s = 0.0;
-    for (int c = 0; c < 4; c++) s += double(r.counts[c]) * w[c];
-    return s + ctx->table.wdiff[r.rank] + 0.0;
-}
-
-void to_result(const psa_context* ctx, const QueryRec& r, psa_result* out)
-{
-    std::memset(out, 0, sizeof(*out));
-    if (r.offset < 0 || r.rank <= 0) {
-        out->mutant.offset = -1; out->mutant.char_offset = -1; out->mutant.ch = '\0';
-        out->score = ctx->is_max ? -INFINITY : INFINITY;
-        return;
-    }
-    out->mutant.offset = r.offset;
-    out->mutant.char_offset = r.char_offset;
-    out->mutant.ch = (char)r.ch;
-    out->rank = r.rank;
-    for (int c = 0; c < 4; c++) out->counts[c] = r.counts[c];
-    out->score = ctx->table.exact ? score_from_counts(ctx, r) : r.score + 0.0;
-}
+static_assert(sizeof(QueryRec) == sizeof(psa_result), "device record == public result");
+static_assert(offsetof(QueryRec, ch) == offsetof(psa_result, mutant) + offsetof(psa_mutant, ch), "ch");
+static_assert(offsetof(QueryRec, rank) == offsetof(psa_result, rank) && offsetof(QueryRec, score) == offsetof(psa_result, score) &&
+              offsetof(QueryRec, counts) == offsetof(psa_result, counts), "device record == public result");
 
 } // namespace
 
@@ -654,10 +634,24 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
     if (!ctx || !ctx->prepared || !ctx->ran) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch has run") : PSA_ERR_ARG;
     if (ctx->nq == 0) return PSA_OK;
     if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
+    // Records have the caller's layout.  A page-locked result array is filled by the copy engine directly; a pageable
+    // one goes through the context's pinned buffer and one memcpy.  The single-query case always stages (merge below).
+    bool direct = false;
+    if (ctx->nq > 1) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) direct = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     for (DeviceState& d : ctx->devs) {
         if (!d.active) continue;
         PSA_CUDA(ctx, cudaSetDevice(d.dev));
-        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, sizeof(QueryRec) * d.G.nq + 16, cudaMemcpyDeviceToHost, d.stream));
+        const size_t bytes = sizeof(QueryRec) * d.G.nq;
+        if (direct) {
+            PSA_CUDA(ctx, cudaMemcpyAsync(out + d.q_begin, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+            PSA_CUDA(ctx, cudaMemcpyAsync((char*)d.h_out.p + bytes, (const char*)d.out.p + bytes, 16, cudaMemcpyDeviceToHost, d.stream));
+        } else {
+            PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, bytes + 16, cudaMemcpyDeviceToHost, d.stream));
+        }
     }
     bool bad_symbol = false;
     for (DeviceState& d : ctx->devs) {
@@ -676,16 +670,14 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
         for (DeviceState& d : ctx->devs) {
             if (!d.active) continue;
             psa_result cur;
-            to_result(ctx, ((const QueryRec*)d.h_out.p)[0], &cur);
+            std::memcpy(&cur, d.h_out.p, sizeof(cur));
             parts.push_back(cur);
         }
         return psa_merge_results(ctx->is_max, parts.data(), (int)parts.size(), out);
     }
-    for (DeviceState& d : ctx->devs) {
-        if (!d.active) continue;
-        const QueryRec* recs = (const QueryRec*)d.h_out.p;
-        for (int k = 0; k < d.G.nq; k++) to_result(ctx, recs[k], &out[d.q_begin + k]);
-    }
+    if (!direct)
+        for (DeviceState& d : ctx->devs)
+            if (d.active) std::memcpy(out + d.q_begin, d.h_out.p, sizeof(QueryRec) * d.G.nq);
     return PSA_OK;
 }
 

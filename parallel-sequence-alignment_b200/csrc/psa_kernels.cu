@@ -283,7 +283,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     }
 
     QueryRec out;
-    out.key = win.key; out.score = 0.0;
+    out.score = T.is_max ? -INFINITY : INFINITY;      // what the reference returns when nothing can be mutated
     out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
     out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
     if (win.key == kKeyNone) {            // no mutation possible at any offset (never seen in practice)
@@ -331,8 +331,18 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
         out.ch = T.sub[c2][c1];
         out.rank = rank;
         for (int c = 0; c < 4; c++) out.counts[c] = cnt[c];
-        const bool key_is_double = !T.exact;     // engine 1 tile keys and re-scored keys are sortable doubles
-        if (key_is_double) out.score = (T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key);
+        if (T.exact) {
+            // every product and partial sum is exactly representable (psa_table.cpp), so this IS the reference's
+            // sequential sum + difference, bit for bit; explicit _rn ops keep the compiler from contracting to FMA
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) s = __dadd_rn(s, __dmul_rn(double(cnt[c]), T.wcls[c]));
+            out.score = __dadd_rn(__dadd_rn(s, T.wdiff[rank]), 0.0);
+        } else {
+            // engine 1 tile keys and re-scored keys are sortable images of the reference's double
+            out.score = __dadd_rn((T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key), 0.0);
+        }
+        if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
         P.out[q] = out;
     }
 }
