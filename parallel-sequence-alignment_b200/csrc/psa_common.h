@@ -30,6 +30,8 @@ struct DeviceTable {
     int32_t is_max;
     int32_t exact;
     int32_t has_none;                 // some pair has no substitute (never observed; handled anyway)
+    int32_t top_rank_lut;             // >= 0: "pair carries the best rank" is a function of its sign class alone (bit c = class c);
+                                      // -1: it is not (then the scan reads it from a rank bit plane)
 };
 
 constexpr int64_t kKeyNone = INT64_MIN;       // key of an offset with no possible mutation / no data

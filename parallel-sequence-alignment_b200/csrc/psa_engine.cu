@@ -65,6 +65,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
@@ -205,6 +206,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     // Slice mode: one query whose warp-tiles cannot fill the GPU is also cut along the alignment steps
     d.SG = SliceGeom{};
+    d.SG.allow_derive = ctx->opt_derive_rank != 0;
     int fin_tile = tile;
     if (scan && !ctx->batch_mode && nq == 1 && last >= 0 && ctx->opt_slices != 1 && ctx->max_len2 >= 256) {
         const int64_t span = last - tile_base(first);
@@ -225,6 +227,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
                 if ((rc = ensure_dev(ctx, d.partial, sizeof(uint2) * (size_t)d.SG.slices * d.SG.scan_tiles * d.SG.scan_tile))) return rc;
             } else {
                 d.SG = SliceGeom{};
+                d.SG.allow_derive = ctx->opt_derive_rank != 0;
             }
         }
     }
@@ -403,6 +406,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "derive_rank") && value >= 0 && value <= 1) { ctx->opt_derive_rank = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }

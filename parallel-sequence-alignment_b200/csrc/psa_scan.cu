@@ -137,6 +137,39 @@ __device__ __forceinline__ void class_group(VCounter<NUP>& A, VCounter<NUP>& B, 
     }
 }
 
+// Same, while the top-rank bit of a pair is a function of its sign class (DeviceTable::top_rank_lut): the bit is
+// derived from the two class words and OR-ed into racc0 -- no rank plane, no second pass.  m[c] = all-ones if class c
+// carries the top rank.
+template <int NUP>
+__device__ __forceinline__ void class_group_derive(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, uint32_t& racc0,
+                                                   const uint32_t (&m)[4], const char* pw, const uint32_t* ro)
+{
+    uint32_t pa[5], pb[5], pn[5];
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s4 + u;
+            const uint32_t off = offs[u];
+            const uint2 lo = *reinterpret_cast<const uint2*>(pw + off);
+            uint32_t x0 = lo.x, x1 = lo.y;
+            if (s != 0) {
+                const uint2 hi = *reinterpret_cast<const uint2*>(pw + off + 8);
+                x0 = __funnelshift_r(lo.x, hi.x, s);
+                x1 = __funnelshift_r(lo.y, hi.y, s);
+            }
+            vc_feed(A, pa, x0, s);
+            vc_feed(B, pb, x1, s);
+            vc_feed(C, pn, x0 & x1, s);
+            const uint32_t lo_cls = (x1 & m[2]) | (~x1 & m[0]);        // class has bit0 = 0: '*' or '.'
+            const uint32_t hi_cls = (x1 & m[3]) | (~x1 & m[1]);        // class has bit0 = 1: ':' or '_'
+            racc0 |= (x0 & hi_cls) | (~x0 & lo_cls);
+        }
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void rank_group(uint32_t (&racc)[K > 0 ? K : 1], const char* pw, const uint32_t* ro)
 {
@@ -426,7 +459,8 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 // SLICE = true (single query, few warp-tiles): blockIdx.y selects a slice of the alignment steps
 // [slice * slice_len, ...); the block leaves its partial counts and rank bits per offset in P.partial and
 // k_combine adds the slices up -- this multiplies the warps in flight when one query cannot fill the GPU.
-template <int NB, int K, bool BS, bool SLICE>
+// DR = true (K = 1 only): the rank plane is derived from the class planes (class_group_derive), pass R is skipped.
+template <int NB, int K, bool BS, bool SLICE, bool DR>
 __global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
        const int key_planes, const int64_t key_bias, const int slice_len)
@@ -479,7 +513,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     };
 
     // ---- pass R: best rank per offset -----------------------------------------------------------------
-    if (K > 0) {
+    if (K > 0 && !DR) {
         bool rank_on = warp_active;
         for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
             const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
@@ -512,6 +546,10 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     // ---- pass C: sign-class counts --------------------------------------------------------------------
     VCounter<NUP> A, B, C;
     A.clear(); B.clear(); C.clear();
+    bool derive_on = DR;
+    uint32_t dmask[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) dmask[c] = (DR && ((T.top_rank_lut >> c) & 1)) ? 0xFFFFFFFFu : 0u;
     for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
         const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
         const int need = round_up4(warps * 32 + (cl >> 5));
@@ -530,8 +568,15 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
         parity ^= 1u;
         if (warp_active) {
             const int groups = cl >> 5;
-            for (int g = 0; g < groups; g++)
-                class_group<NUP>(A, B, C, reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 8, s_ro + g * 32);
+            for (int g = 0; g < groups; g++) {
+                const char* pw = reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 8;
+                if (DR && derive_on) {
+                    class_group_derive<NUP>(A, B, C, racc[0], dmask, pw, s_ro + g * 32);
+                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) derive_on = false;
+                } else {
+                    class_group<NUP>(A, B, C, pw, s_ro + g * 32);
+                }
+            }
         }
     }
 
@@ -698,7 +743,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 //   shared memory: [28][nwords] uint2 | [28][nwords][K] uint32 | per warp [chunk] uint32 row offsets
 // One TileRec per (query, tile) is written by the warp that computed it.
 // -------------------------------------------------------------------------------------------------
-template <int NB, int K, bool BS>
+template <int NB, int K, bool BS, bool DR>
 __global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
              const int queries_per_block, const int key_planes, const int64_t key_bias)
@@ -718,18 +763,21 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
-        mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(nwords) * uint32_t(8 + 4 * K));
+        mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(nwords) * uint32_t(8 + (DR ? 0 : 4 * K)));
     }
     __syncthreads();
     pdl_wait();                                                     // the bit planes come from k_profile
     if (warp == 0 && lane < kPlaneRows) {
         const int64_t g0 = tb >> 5;
         tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(nwords) * 8u, &s_bar);
-        if (K > 0)
+        if (K > 0 && !DR)
             tma_load_1d(s_rnk + size_t(lane) * nwords * 4 * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
                         uint32_t(nwords) * 4u * K, &s_bar);
     }
     bool staged = false;
+    uint32_t dmask[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) dmask[c] = (DR && ((T.top_rank_lut >> c) & 1)) ? 0xFFFFFFFFu : 0u;
 
     const int q_begin = blockIdx.x * queries_per_block;
     const int q_end = (q_begin + queries_per_block) < G.nq ? (q_begin + queries_per_block) : G.nq;
@@ -758,7 +806,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
         racc[0] = ~vmask;
         const int groups = steps_total >> 5;
-        if (K > 0) {
+        if (K > 0 && !DR) {
             for (int g = 0; g < groups; g++) {
                 rank_group<K>(racc, reinterpret_cast<const char*>(s_rnk) + size_t(lane + g) * 4 * K, s_ro + g * 32);
                 if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
@@ -766,8 +814,16 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         }
         VCounter<NUP> A, B, C;
         A.clear(); B.clear(); C.clear();
-        for (int g = 0; g < groups; g++)
-            class_group<NUP>(A, B, C, reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8, s_ro + g * 32);
+        bool derive_on = DR;
+        for (int g = 0; g < groups; g++) {
+            const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8;
+            if (DR && derive_on) {
+                class_group_derive<NUP>(A, B, C, racc[0], dmask, pw, s_ro + g * 32);
+                if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) derive_on = false;
+            } else {
+                class_group<NUP>(A, B, C, pw, s_ro + g * 32);
+            }
+        }
 
         Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
         typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
@@ -838,6 +894,9 @@ template <int NB, int K, bool BS>
 void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int chunk, bool batch, int sm_count,
                       int key_planes, int64_t key_bias, const SliceGeom& SG, cudaStream_t stream)
 {
+    // the top-rank bit can be derived from the class planes when it is a function of the sign class that excludes
+    // class 0 (the all-zero padding row reads as class 0 and must never count as a hit)
+    const bool derive = K == 1 && T.top_rank_lut > 0 && (T.top_rank_lut & 1) == 0 && SG.allow_derive;
     if (SG.slices > 1) {
         // G is the finish geometry (256-offset tiles); the scan runs on its own warp tiles
         BatchGeom Gs = G;
@@ -848,8 +907,18 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         static bool done[64];
-        allow_big_smem(k_scan<NB, K, false, true>, done);
-        launch_dependent(k_scan<NB, K, false, true>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P, nwords, chunk, 0,
+        if constexpr (K == 1) {
+            if (derive) {
+                static bool done_dr[64];
+                allow_big_smem(k_scan<NB, K, false, true, true>, done_dr);
+                launch_dependent(k_scan<NB, K, false, true, true>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P,
+                                 nwords, chunk, 0, int64_t(0), SG.slice_len);
+                launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
+                return;
+            }
+        }
+        allow_big_smem(k_scan<NB, K, false, true, false>, done);
+        launch_dependent(k_scan<NB, K, false, true, false>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P, nwords, chunk, 0,
                          int64_t(0), SG.slice_len);
         launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
         return;
@@ -866,15 +935,33 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
         if (qpb > 4096) qpb = 4096;
         dim3 grid((G.nq + qpb - 1) / qpb, tiles);
         static bool done[64];
-        allow_big_smem(k_scan_batch<NB, K, BS>, done);
-        launch_dependent(k_scan_batch<NB, K, BS>, grid, dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
+        if constexpr (K == 1) {
+            if (derive) {
+                static bool done_dr[64];
+                allow_big_smem(k_scan_batch<NB, K, BS, true>, done_dr);
+                launch_dependent(k_scan_batch<NB, K, BS, true>, grid, dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, int(qpb), key_planes,
+                                 key_bias);
+                return;
+            }
+        }
+        allow_big_smem(k_scan_batch<NB, K, BS, false>, done);
+        launch_dependent(k_scan_batch<NB, K, BS, false>, grid, dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, int(qpb), key_planes, key_bias);
     } else {
         const int warps = G.tile / 1024;
         const int nwords = round_up4(warps * 32 + chunk / 32);
         const size_t smem = scan_smem_bytes(K, chunk, warps);
         static bool done[64];
-        allow_big_smem(k_scan<NB, K, BS, false>, done);
-        launch_dependent(k_scan<NB, K, BS, false>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, key_planes, key_bias, 0);
+        if constexpr (K == 1) {
+            if (derive) {
+                static bool done_dr[64];
+                allow_big_smem(k_scan<NB, K, BS, false, true>, done_dr);
+                launch_dependent(k_scan<NB, K, BS, false, true>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk,
+                                 key_planes, key_bias, 0);
+                return;
+            }
+        }
+        allow_big_smem(k_scan<NB, K, BS, false, false>, done);
+        launch_dependent(k_scan<NB, K, BS, false, false>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, key_planes, key_bias, 0);
     }
 }
 

@@ -221,6 +221,18 @@ int build_tables(const double* w, int is_max, long long max_len2, psa_pair_table
         dev->is_max = is_max ? 1 : 0;
         dev->exact = t.exact;
         dev->has_none = has_none ? 1 : 0;
+        // Is "this pair's substitution has the best rank" decided by the pair's sign class alone?  (True for a
+        // maximum: replacing by the Seq1 letter itself is best exactly on '.' or '_' pairs.)  Then the scan needs no
+        // rank plane: it derives the bit from the two class planes it reads anyway.
+        {
+            int yes = 0, no = 0;
+            for (int c2 = 0; c2 < kSymbols; c2++)
+                for (int c1 = 0; c1 < kSymbols; c1++) {
+                    const int cls = class_of(t.sign[c2][c1]);
+                    (t.rank[c2][c1] == t.nranks ? yes : no) |= 1 << cls;
+                }
+            dev->top_rank_lut = (yes & no) == 0 ? yes : -1;
+        }
     }
     return PSA_OK;
 }

@@ -17,20 +17,22 @@ ALPHA = [chr(65 + i) for i in range(26)] + ["-"]
 # (engine, rank planes, warps per block, batch mode, bit-sliced epilogue): the scalar engine, and the bit-sliced
 # scan with every plane count (0 planes = every offset unresolved -> the in-kernel settle path carries the result),
 # both tile shapes and both epilogues
-ENGINES = [(1, -1, 0, -1, 1), (2, -1, 0, -1, 1), (2, 0, 1, 0, 1), (2, 1, 2, 0, 0), (2, 4, 3, 0, 1), (2, 2, 4, 0, 0),
-           (2, 0, 0, 1, 0), (2, 2, 0, 1, 1), (2, 4, 0, 1, 0), (2, 1, 0, 1, 1)]
+# The last field switches off deriving the top-rank bit from the class planes (default on when the table allows it).
+ENGINES = [(1, -1, 0, -1, 1, 1), (2, -1, 0, -1, 1, 1), (2, 0, 1, 0, 1, 1), (2, 1, 2, 0, 0, 1), (2, 4, 3, 0, 1, 1), (2, 2, 4, 0, 0, 1),
+           (2, 0, 0, 1, 0, 1), (2, 2, 0, 1, 1, 1), (2, 4, 0, 1, 0, 1), (2, 1, 0, 1, 1, 1), (2, 1, 0, 0, 1, 0), (2, 1, 0, 1, 1, 0)]
 
 
-def _set_engine(ctx, engine, planes=-1, warps=0, batch=-1, sliced=1):
+def _set_engine(ctx, engine, planes=-1, warps=0, batch=-1, sliced=1, derive=1):
     ctx.set_option("engine", engine)
     ctx.set_option("rank_planes", planes)
     ctx.set_option("scan_warps", warps)
     ctx.set_option("batch_mode", batch)
     ctx.set_option("sliced_keys", sliced)
+    ctx.set_option("derive_rank", derive)
 
 
 @pytest.fixture(params=ENGINES, ids=["scalar", "scan", "scan-k0-w1-bs", "scan-k1-w2", "scan-k4-w3-bs", "scan-k2-w4", "batch-k0",
-                                     "batch-k2-bs", "batch-k4", "batch-k1-bs"])
+                                     "batch-k2-bs", "batch-k4", "batch-k1-bs", "scan-k1-planes", "batch-k1-planes"])
 def engine(request, ctx):
     _set_engine(ctx, *request.param)
     yield request.param[0]
