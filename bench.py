@@ -203,6 +203,32 @@ def workload_name(name, wl):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def quick_measure(psa, synth, ctx, name, flush_l2, steps):
+    wl = make_workload(synth, name, 0)
+    batch = psa.Batch(wl.seq1, wl.queries, pinned=True)
+    ctx.prepare(wl.weights, wl.is_max, batch)
+    for _ in range(3):
+        ctx.run()
+    ms = 0.0
+    for _ in range(steps):
+        flush_l2()
+        ms += ctx.run()
+    wc = psa.c_weights(wl.weights)
+    out = ctx.new_result_array(batch.nq, pinned=True)
+    ctx.search_batch_raw(wc, wl.is_max, batch, out)
+    e2e = 0.0
+    for _ in range(steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        ctx.search_batch_raw(wc, wl.is_max, batch, out)
+        e2e += time.perf_counter() - t0
+    return {"workload": workload_name(name, wl), "pair_evals": batch.pair_evals, "steps": steps,
+            "value": batch.pair_evals * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "e2e": batch.pair_evals * steps / e2e, "e2e_ms_per_step": 1e3 * e2e / steps,
+            "engine": {1: "scalar", 2: "bitsliced-scan"}.get(ctx.stat("engine")), "batch_mode": bool(ctx.stat("batch_mode")),
+            "slices": ctx.stat("slices"), "exact_integer_keys": bool(ctx.stat("exact"))}
+
+
 def run_ours(args, synth, rank, local_rank, world):
     import torch
     psa = importlib.import_module(PKG)
@@ -356,6 +382,12 @@ def run_ours(args, synth, rank, local_rank, world):
             line["cpu_baseline"] = {"value": s["pair_evals"] / t, "unit": UNIT, "cores": s["threads"], "kind": s["kind"],
                                     "sample": s["desc"], "seconds": t}
             line["reference_gpu"] = reference_gpu_probe(args.workload)
+        if world == 1 and not args.no_others:
+            # the other BASELINE.json configs, same method (resident value + host-buffer e2e), fewer steps
+            line["other_workloads"] = {}
+            for name in ("c1", "c2", "c4", "c5"):
+                if name != args.workload:
+                    line["other_workloads"][name] = quick_measure(psa, synth, ctx, name, flush_l2, steps=max(3, args.steps // 4))
         print(json.dumps(line), flush=True)
     ctx.close()
     if use_dist:
@@ -372,6 +404,7 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 scalar, 2 bit-sliced scan")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the quick measurements of the other BASELINE configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = dist_env()
