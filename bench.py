@@ -21,6 +21,8 @@ shape.  Weak scaling: every rank owns a full batch (different seed per rank), no
 from __future__ import annotations
 
 import argparse
+import contextlib
+import ctypes
 import importlib
 import json
 import os
@@ -150,6 +152,50 @@ def reference_sample(synth, name, seconds=12.0):
     return {"kind": kind, "threads": threads, "run": run, "sample": sample, "pair_evals": pe(sample),
             "desc": f"{n} of the workload's queries, {kind} find_best_mutant_cpu split over {threads} threads "
                     f"(-O3 build, table filled single-threaded){cap_note}", "wl": wl}
+
+
+@contextlib.contextmanager
+def silence_c_stdout():
+    """The reference printf()s from C ("CUDA percentage set to ..."); keep that out of our one-JSON-line stdout,
+    including whatever libc still holds in its buffer."""
+    libc = ctypes.CDLL(None)
+    sys.stdout.flush()
+    libc.fflush(None)
+    saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        yield
+    finally:
+        libc.fflush(None)
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+def as_shipped_baseline(synth, name, seconds=3.0):
+    """The reference exactly as its Makefile builds it (no -O flag) and as main.c runs it (4 OpenMP threads,
+    divide_execute_tasks with the CUDA percentage forced to 0).  Timing only: with more than one thread the
+    reference's fill_hash races, so its answers are not checked."""
+    try:
+        import oracle
+        if not os.path.exists(oracle.REF_O0_SO):
+            return {"unavailable": "oracle/_ref/libpsa_ref_O0.so not built"}
+        eng = oracle.Ref(oracle.REF_O0_SO)
+        wl = make_workload(synth, name, 0, nq=None if name in ("c1", "c2", "c4") else 256)
+        seq1 = wl.seq1[: eng.cap1]
+        with silence_c_stdout():
+            t0 = time.perf_counter()
+            done = 0
+            for q in wl.queries:
+                eng.divide_execute_tasks(wl.weights, wl.is_max, seq1, q, 1, 0, 0, 4)
+                done += (len(seq1) - len(q) + 1) * len(q)
+                if time.perf_counter() - t0 > seconds:
+                    break
+            dt = time.perf_counter() - t0
+        return {"value": done / dt, "unit": UNIT, "cores": 4, "kind": "reference", "seconds": dt,
+                "sample": "reference divide_execute_tasks, -O0 build, 4 OpenMP threads (as shipped), CUDA percentage 0"}
+    except Exception as e:       # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
 
 
 def reference_gpu_probe(workload):
@@ -381,6 +427,7 @@ def run_ours(args, synth, rank, local_rank, world):
             t = s["run"](s["sample"])
             line["cpu_baseline"] = {"value": s["pair_evals"] / t, "unit": UNIT, "cores": s["threads"], "kind": s["kind"],
                                     "sample": s["desc"], "seconds": t}
+            line["cpu_baseline_as_shipped"] = as_shipped_baseline(synth, args.workload)
             line["reference_gpu"] = reference_gpu_probe(args.workload)
         if world == 1 and not args.no_others:
             # the other BASELINE.json configs, same method (resident value + host-buffer e2e), fewer steps

@@ -25,9 +25,12 @@ def main():
     seq1 = wl.seq1[: ref.cap1]
     qs = wl.queries[:nq]
     ref.divide_execute_tasks(wl.weights, wl.is_max, seq1, qs[0], 1, 0, 100, 1)        # warm-up (context, module load)
-    t0 = time.perf_counter()
-    got = [ref.divide_execute_tasks(wl.weights, wl.is_max, seq1, q, 1, 0, 100, 1) for q in qs]
-    dt = time.perf_counter() - t0
+    dt = None
+    for _ in range(3):                      # best of three passes: the first ones still pay allocator / clock warm-up
+        t0 = time.perf_counter()
+        got = [ref.divide_execute_tasks(wl.weights, wl.is_max, seq1, q, 1, 0, 100, 1) for q in qs]
+        t = time.perf_counter() - t0
+        dt = t if dt is None else min(dt, t)
     exp = [port.search(wl.weights, wl.is_max, seq1, q) for q in qs]
     bad = sum((g.offset, g.char_offset, g.score) != (e.offset, e.char_offset, e.score) for g, e in zip(got, exp))
     pe = sum((len(seq1) - len(q) + 1) * len(q) for q in qs)
