@@ -27,18 +27,23 @@ def num(x):
 
 
 def main(argv):
-    summary_path = os.path.join(ROOT, "profiles", "r01_summary.json")
+    out_dir = os.path.join(ROOT, "profiles")
+    if argv and argv[0] == "--out":          # e.g. gpurun_out/profiles on the GPU box (only gpurun_out/ travels back)
+        out_dir = argv[1]
+        argv = argv[2:]
+        os.makedirs(out_dir, exist_ok=True)
+    summary_path = os.path.join(out_dir, "r01_summary.json")
     summary = json.load(open(summary_path)) if os.path.exists(summary_path) else {}
     for rep, workload in zip(argv[0::2], argv[1::2]):
         stem = os.path.splitext(os.path.basename(rep))[0]
         details = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
-        open(os.path.join(ROOT, "profiles", stem + "_details.txt"), "w").write(details)
+        open(os.path.join(out_dir, stem + "_details.txt"), "w").write(details)
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units, vals = rows[0], rows[1], rows[2]
         rec = dict(zip(hdr, vals))
         unit = dict(zip(hdr, units))
-        with open(os.path.join(ROOT, "profiles", stem + "_metrics.csv"), "w") as f:
+        with open(os.path.join(out_dir, stem + "_metrics.csv"), "w") as f:
             for h in hdr:
                 if any(k in h for k in KEEP) and rec[h] not in ("", "0"):
                     f.write(f"{h},{unit[h]},{rec[h]}\n")
