@@ -140,6 +140,14 @@ int psa_search_range(psa_context* ctx, const double weights[4], int is_max,
                      const char* seq1, int64_t len1, const char* seq2, int64_t len2,
                      int64_t first, int64_t last, psa_result* out);
 
+/* Reporting (the reference only has this as a debug printer, cpu_funcs.c:382-425): the whole score
+   profile of ONE query over absolute offsets [first,last): scores[k] is the reference's score of offset first+k
+   (find_best_mutant_offset, cpu_funcs.c:257-300), char_offsets[k] / letters[k] the single substitution it includes
+   (-1 / '\0' where none exists).  char_offsets and letters may be NULL.  Runs on the context's first GPU. */
+int psa_offset_scores(psa_context* ctx, const double weights[4], int is_max,
+                      const char* seq1, int64_t len1, const char* seq2, int64_t len2,
+                      int64_t first, int64_t last, double* scores, int32_t* char_offsets, char* letters);
+
 /* Split-phase form of psa_search_batch, for callers that keep a batch resident in HBM:
    prepare = validate + H2D + table/profile resolution; run = the kernels only (returns the
    device time in ms measured with CUDA events on the library's streams, max over the

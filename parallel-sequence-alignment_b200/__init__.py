@@ -131,6 +131,8 @@ def _sig():
     _lib.psa_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_CResult)]
     _lib.psa_search_range.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
                                       C.c_int64, C.c_int64, C.POINTER(_CResult)]
+    _lib.psa_offset_scores.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64,
+                                       dp, C.POINTER(C.c_int32), C.c_char_p]
     _lib.psa_alloc_pinned.restype = C.c_void_p
     _lib.psa_alloc_pinned.argtypes = [C.c_size_t]
     _lib.psa_free_pinned.argtypes = [C.c_void_p]
@@ -352,6 +354,20 @@ class Context:
         self._check(_lib.psa_search_range(self._h, _w(weights), int(bool(is_max)), s1, len(s1), s2, len(s2),
                                           first, last, C.byref(out)))
         return _py(out)
+
+    def offset_scores(self, weights, is_max: bool, seq1, seq2, first: int = 0, last: Optional[int] = None):
+        """Score profile of one query: (scores, char_offsets, letters) for offsets [first,last)."""
+        s1, s2 = _b(seq1), _b(seq2)
+        if last is None:
+            last = len(s1) - len(s2) + 1
+        n = max(last - first, 1)
+        scores = (C.c_double * n)()
+        coffs = (C.c_int32 * n)()
+        letters = C.create_string_buffer(n)
+        self._check(_lib.psa_offset_scores(self._h, _w(weights), int(bool(is_max)), s1, len(s1), s2, len(s2), first, last,
+                                           scores, coffs, letters))
+        m = last - first
+        return list(scores)[:m], list(coffs)[:m], letters.raw[:m].decode("latin1")
 
     # -- split phase (resident batch) ------------------------------------------------------------
     def prepare(self, weights, is_max: bool, batch: Batch):

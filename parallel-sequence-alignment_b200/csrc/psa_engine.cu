@@ -715,6 +715,49 @@ int psa_search_range(psa_context* ctx, const double weights[4], int is_max, cons
     return psa_batch_fetch(ctx, out);
 }
 
+int psa_offset_scores(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1, const char* seq2,
+                      int64_t len2, int64_t first, int64_t last, double* scores, int32_t* char_offsets, char* letters)
+{
+    if (!ctx) return PSA_ERR_ARG;
+    if (!weights || !seq1 || !seq2 || !scores) return fail(ctx, PSA_ERR_ARG, "null argument");
+    if (len2 < 1 || len2 > len1 || len1 > 0x7FFF0000ll || len2 > kExactMaxLen2 || first < 0 || first >= last ||
+        last > offsets_of(len1, len2))
+        return fail(ctx, PSA_ERR_ARG, "lengths or offset range invalid");
+    ctx->prepared = ctx->ran = false;
+    DeviceTable T;
+    int rc = build_tables(weights, is_max, len2, nullptr, &T);
+    if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
+    ctx->table_valid = false;                    // the cached table belongs to the batch entry points
+    DeviceState& d = ctx->devs[0];
+    PSA_CUDA(ctx, cudaSetDevice(d.dev));
+    const int64_t n = last - first;
+    if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.seq2s, (size_t)len2 + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.out, 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.partial, (size_t)n * 13 + 64))) return rc;         // scores | char offsets | letters
+    if ((rc = ensure_pin(ctx, d.h_out, 64))) return rc;
+    double* d_scores = (double*)d.partial.p;
+    int32_t* d_coff = (int32_t*)(d_scores + n);
+    uint8_t* d_let = (uint8_t*)(d_coff + n);
+    BatchGeom G{};
+    G.len1 = len1; G.first = first; G.last = last; G.nq = 1; G.uniform_len2 = (int32_t)len2;
+    BatchPtrs P{};
+    P.seq1 = (const uint8_t*)d.seq1.p; P.seq2s = (const uint8_t*)d.seq2s.p;
+    P.cand_count = (int32_t*)d.out.p; P.err_flag = P.cand_count + 1;
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2, (size_t)len2, cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemsetAsync(d.out.p, 0, 16, d.stream));
+    launch_offset_profile(T, G, P, d_scores, d_coff, d_let, d.stream);
+    PSA_CUDA(ctx, cudaGetLastError());
+    PSA_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (char_offsets) PSA_CUDA(ctx, cudaMemcpyAsync(char_offsets, d_coff, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (letters) PSA_CUDA(ctx, cudaMemcpyAsync(letters, d_let, (size_t)n, cudaMemcpyDeviceToHost, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, 16, cudaMemcpyDeviceToHost, d.stream));
+    PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    if (((const int32_t*)d.h_out.p)[1]) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
+    return PSA_OK;
+}
+
 void* psa_alloc_pinned(size_t bytes)
 {
     void* p = nullptr;

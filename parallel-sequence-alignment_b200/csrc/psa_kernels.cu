@@ -142,6 +142,74 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
 }
 
 // -------------------------------------------------------------------------------------------------
+// Per-offset profile (reporting): for every offset of ONE query the reference's score
+// (find_best_mutant_offset, cpu_funcs.c:257-300: sequential double + best single-substitution difference), the
+// position it would mutate and the replacement letter.  One thread per offset, Seq2 staged in chunks.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kExactThreads)
+k_offset_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, double* __restrict__ scores,
+                 int32_t* __restrict__ char_offsets, uint8_t* __restrict__ letters)
+{
+    __shared__ uint8_t s_code[kSymbols * kRowPad];
+    __shared__ __align__(16) uint8_t s_win[kExactThreads + kExactChunk];
+    __shared__ __align__(16) uint8_t s_q[kExactChunk];
+    __shared__ double s_w[4];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < kSymbols * kRowPad; k += kExactThreads) s_code[k] = T.code[k / kRowPad][k % kRowPad];
+    if (tid < 4) s_w[tid] = T.wcls[tid];
+    const int len2 = G.uniform_len2;
+    const int64_t sub = G.first + int64_t(blockIdx.x) * kExactThreads;
+    const int64_t n = sub + tid;
+    const bool valid = n < G.last;
+    double total = 0.0;
+    uint32_t best_rank = 0;
+    int32_t best_i = -1;
+    for (int c0 = 0; c0 < len2; c0 += kExactChunk) {
+        const int cl = (len2 - c0) < kExactChunk ? (len2 - c0) : kExactChunk;
+        __syncthreads();
+        for (int k = tid; k < cl; k += kExactThreads) {
+            uint32_t c = symbol_of(P.seq2s[c0 + k]);
+            if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
+            s_q[k] = uint8_t(c);
+        }
+        for (int k = tid; k < kExactThreads + cl - 1; k += kExactThreads) {
+            const int64_t p = sub + c0 + k;
+            uint32_t c = 0;
+            if (p < G.len1) {
+                c = symbol_of(P.seq1[p]);
+                if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
+            }
+            s_win[k] = uint8_t(c);
+        }
+        __syncthreads();
+        if (valid) {
+            const uint8_t* w = s_win + tid;
+#pragma unroll 4
+            for (int i = 0; i < cl; i++) {
+                const uint32_t code = s_code[uint32_t(s_q[i]) * kRowPad + w[i]];
+                total += s_w[code & 3u];
+                const uint32_t r = code >> 2;
+                if (r > best_rank) { best_rank = r; best_i = c0 + i; }          // strict: the first position wins ties
+            }
+        }
+    }
+    if (valid) {
+        const int64_t k = n - G.first;
+        if (best_rank) {
+            scores[k] = __dadd_rn(__dadd_rn(total, T.wdiff[best_rank]), 0.0);
+            char_offsets[k] = best_i;
+            uint32_t c1 = symbol_of(P.seq1[n + best_i]), c2 = symbol_of(P.seq2s[best_i]);
+            if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+            letters[k] = T.sub[c2][c1];
+        } else {
+            scores[k] = T.is_max ? -INFINITY : INFINITY;
+            char_offsets[k] = -1;
+            letters[k] = 0;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Finish: one warp per query, 8 queries per block (WPQ = 1), or -- for small batches, where a single warp
 // would crawl through dependent global loads -- the whole block on one query (WPQ = 8).
 //  (1) winner over the query's tile records under (key desc, offset asc);
@@ -354,6 +422,15 @@ void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtr
     if (G.total_tiles < 1) return;
     if (T.exact) k_exact_tiles<true><<<G.total_tiles, kExactThreads, 0, stream>>>(T, G, P);
     else k_exact_tiles<false><<<G.total_tiles, kExactThreads, 0, stream>>>(T, G, P);
+}
+
+void launch_offset_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, double* scores, int32_t* char_offsets,
+                           uint8_t* letters, cudaStream_t stream)
+{
+    const int64_t n = G.last - G.first;
+    if (n < 1) return;
+    k_offset_profile<<<(unsigned)((n + kExactThreads - 1) / kExactThreads), kExactThreads, 0, stream>>>(T, G, P, scores, char_offsets,
+                                                                                                        letters);
 }
 
 void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream)

@@ -48,6 +48,9 @@ void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtr
 // per-query finish: winner over the tile records (re-scored in reference order when the weights are not
 // exactly summable and the records come from the scan), then char_offset + counts + substitute letter
 void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream);
+// per-offset scores / mutated position / letter of one query over [G.first, G.last)
+void launch_offset_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, double* scores, int32_t* char_offsets,
+                           uint8_t* letters, cudaStream_t stream);
 // bit-plane profile of Seq1 for the scan engine
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
                     cudaStream_t stream);

@@ -307,3 +307,22 @@ def test_very_long_query_falls_back_to_scalar_engine(ctx, port, synth):
         r = ctx.search(w, is_max, s1, s2)
         assert ctx.stat("engine") == 1
         assert same_answer(r, port.search(w, is_max, s1, s2, nthreads=8))
+
+
+def test_offset_score_profile(ctx, port, synth):
+    """psa_offset_scores: the reference's score of EVERY offset (find_best_mutant_offset), not just the best."""
+    s1, s2 = synth.letters(401, 5000), synth.letters(402, 333)
+    for w in ([1, 3, 4, 2], [1.5, 2.6, 0.1, 0.2]):
+        for is_max in (True, False):
+            scores, coffs, letters = ctx.offset_scores(w, is_max, s1, s2)
+            assert scores == port.scores(w, is_max, s1, s2)
+            for n in (0, 17, 2500, 4667):
+                o = port.offset_naive(w, is_max, s1, s2, n)
+                assert (scores[n], coffs[n], letters[n]) == (o.score, o.char_offset, o.ch)
+            best = ctx.search(w, is_max, s1, s2)
+            pick = max if is_max else min
+            assert best.score == pick(scores) and best.offset == scores.index(best.score)
+    sc, _, _ = ctx.offset_scores([1, 3, 4, 2], True, s1, s2, 100, 164)
+    assert sc == port.scores([1, 3, 4, 2], True, s1, s2, 100, 164)
+    _set_engine(ctx, 0)
+    assert ctx.search([1, 3, 4, 2], True, s1, s2).offset >= 0          # the context is still good for searches
