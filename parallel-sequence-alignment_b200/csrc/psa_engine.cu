@@ -23,8 +23,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -54,12 +58,28 @@ struct DeviceState {
     BatchGeom G{};
     BatchPtrs P{};
     bool active = false;
+    long long st_launches = 0, st_cand = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
+    float run_ms = 0.f;
+};
+
+// One host thread per additional GPU: enqueueing copies and launches for 8 devices one after the other from a
+// single thread costs more than the work itself on small problems (every device would wait for its turn).
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool pending = false, quit = false;
+    int rc = 0;
 };
 
 } // namespace
 
 struct psa_context {
     std::vector<DeviceState> devs;
+    std::vector<std::unique_ptr<Worker>> workers;     // workers[g-1] serves devs[g]
+    std::vector<psa_shard> plan;                      // shard of the current batch per GPU
+    std::mutex err_mu;
     std::string err;
     // options
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
@@ -85,8 +105,10 @@ struct psa_context {
     bool batch_mode = false;     // scan engine: queries share staged windows (k_scan_batch)
     int64_t max_len2 = 0;
     int64_t uniform_len2 = 0;    // > 0: all queries of the batch have this length
-    // stats of the last run
-    long long st_launches = 0, st_cand = 0, st_tiles = 0, st_main_ns = 0;
+    const char* in_seq1 = nullptr;       // the caller's buffers of the batch being prepared (read by the per-GPU copies)
+    const char* in_seq2s = nullptr;
+    const int64_t* in_qoff = nullptr;
+    int64_t in_len1 = 0;
 };
 
 namespace {
@@ -98,7 +120,10 @@ int fail(psa_context* ctx, int code, const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        ctx->err = buf;
+    }
     return code;
 }
 
@@ -159,6 +184,43 @@ int pick_rank_planes(const psa_context* ctx)
     int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : 1;
     if (want > 2) want = 4;                                          // supported widths: 0,1,2,4
     return std::min(want, std::max(avail, 0));
+}
+
+// Run fn(device) for every GPU of the context: GPU 0 on the calling thread, the others on their worker threads.
+template <class F>
+int for_each_device(psa_context* ctx, F fn)
+{
+    const int ndev = (int)ctx->devs.size();
+    for (int g = 1; g < ndev; g++) {
+        Worker& w = *ctx->workers[g - 1];
+        std::lock_guard<std::mutex> lk(w.mu);
+        w.job = [ctx, g, &fn]() { return fn(ctx->devs[g]); };
+        w.pending = true;
+        w.cv.notify_one();
+    }
+    int rc = fn(ctx->devs[0]);
+    for (int g = 1; g < ndev; g++) {
+        Worker& w = *ctx->workers[g - 1];
+        std::unique_lock<std::mutex> lk(w.mu);
+        w.cv.wait(lk, [&w] { return !w.pending; });
+        if (!rc) rc = w.rc;
+    }
+    return rc;
+}
+
+void worker_loop(Worker* w)
+{
+    std::unique_lock<std::mutex> lk(w->mu);
+    for (;;) {
+        w->cv.wait(lk, [w] { return w->pending || w->quit; });
+        if (w->quit) return;
+        lk.unlock();
+        const int rc = w->job();
+        lk.lock();
+        w->rc = rc;
+        w->pending = false;
+        w->cv.notify_all();
+    }
 }
 
 // Enqueue H2D copies and geometry for one GPU's slice. first/last >= 0 selects range mode (nq == 1).
@@ -286,6 +348,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
 int run_device(psa_context* ctx, DeviceState& d, bool timed)
 {
+    d.st_launches = d.st_cand = d.st_tiles = d.st_main_ns = 0;
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
@@ -294,20 +357,20 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_scan(ctx->table, d.G, d.P, ctx->rank_planes, ctx->max_len2, ctx->batch_mode, ctx->opt_sliced_keys != 0, d.sm_count, d.SG, d.stream);
-        if (d.SG.slices > 1) ctx->st_launches += 1;
+        if (d.SG.slices > 1) d.st_launches += 1;
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
-        ctx->st_launches += 2;
+        d.st_launches += 2;
     } else {
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_exact_tiles(ctx->table, d.G, d.P, d.stream);
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
-        ctx->st_launches += 1;
+        d.st_launches += 1;
     }
     launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
-    ctx->st_launches += 1;
+    d.st_launches += 1;
     PSA_CUDA(ctx, cudaGetLastError());
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
-    ctx->st_tiles += d.G.total_tiles;
+    d.st_tiles += d.G.total_tiles;
     return PSA_OK;
 }
 
@@ -384,6 +447,11 @@ int psa_create(psa_context** out, const int* devices, int ndevices)
             return PSA_ERR_CUDA;     // the kernels are sm_100a only: no other device can run them
         }
     }
+    for (int i = 1; i < ndevices; i++) {
+        ctx->workers.emplace_back(new Worker());
+        Worker* w = ctx->workers.back().get();
+        w->th = std::thread(worker_loop, w);
+    }
     *out = ctx;
     return PSA_OK;
 }
@@ -391,6 +459,11 @@ int psa_create(psa_context** out, const int* devices, int ndevices)
 void psa_destroy(psa_context* ctx)
 {
     if (!ctx) return;
+    for (auto& w : ctx->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
     for (DeviceState& d : ctx->devs) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -418,10 +491,15 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
 long long psa_get_stat(const psa_context* ctx, const char* name)
 {
     if (!ctx || !name) return -1;
-    if (!std::strcmp(name, "kernel_launches")) return ctx->st_launches;
-    if (!std::strcmp(name, "candidate_tiles")) return ctx->st_cand;
-    if (!std::strcmp(name, "tiles")) return ctx->st_tiles;
-    if (!std::strcmp(name, "main_kernel_ns")) return ctx->st_main_ns;   // dominant kernel of the last psa_batch_run
+    long long launches = 0, cand = 0, tiles = 0, main_ns = 0;
+    for (const DeviceState& d : ctx->devs) {
+        launches += d.st_launches; cand += d.st_cand; tiles += d.st_tiles;
+        main_ns = std::max(main_ns, d.st_main_ns);
+    }
+    if (!std::strcmp(name, "kernel_launches")) return launches;
+    if (!std::strcmp(name, "candidate_tiles")) return cand;
+    if (!std::strcmp(name, "tiles")) return tiles;
+    if (!std::strcmp(name, "main_kernel_ns")) return main_ns;           // dominant kernel of the last psa_batch_run
     if (!std::strcmp(name, "engine")) return ctx->engine;
     if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
@@ -571,105 +649,52 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
     if (nq == 0) { ctx->prepared = true; return PSA_OK; }
 
     const int64_t granule = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
-    std::vector<psa_shard> plan(ndev);
-    if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, plan.data())))
+    ctx->plan.assign(ndev, psa_shard{ 0, 0, -1, -1 });
+    if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, ctx->plan.data())))
         return fail(ctx, rc, "cannot partition the batch");
     int used = 0;
-    for (int g = 0; g < ndev; g++) {
-        const psa_shard& sh = plan[g];
-        if (sh.q_begin == sh.q_end) continue;
-        used++;
-        if ((rc = prepare_device(ctx, ctx->devs[g], seq1, len1, seq2s, q_off, sh.q_begin, sh.q_end,
-                                 nq == 1 ? sh.first : -1, nq == 1 ? sh.last : -1)))
-            return rc;
-    }
+    for (int g = 0; g < ndev; g++) used += ctx->plan[g].q_begin != ctx->plan[g].q_end;
     ctx->range_split = nq == 1 && used > 1;
+    ctx->in_seq1 = seq1; ctx->in_len1 = len1; ctx->in_seq2s = seq2s; ctx->in_qoff = q_off;
     ctx->prepared = true;
     return PSA_OK;
 }
 
-int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
-                      const char* seq2s, const int64_t* q_off, int32_t nq)
+// the device-side half of prepare: copies and geometry of this GPU's shard (inputs must still be alive)
+static int prepare_shard(psa_context* ctx, DeviceState& d)
 {
-    int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
-    if (rc) return rc;
-    // the split-phase form promises a resident batch: wait for the copies here
+    const psa_shard& sh = ctx->plan[&d - ctx->devs.data()];
+    if (sh.q_begin == sh.q_end) { d.active = false; return PSA_OK; }
+    return prepare_device(ctx, d, ctx->in_seq1, ctx->in_len1, ctx->in_seq2s, ctx->in_qoff, sh.q_begin, sh.q_end,
+                          ctx->nq == 1 ? sh.first : -1, ctx->nq == 1 ? sh.last : -1);
+}
+
+// device-to-host copy of this GPU's records (+ flags) and the wait for everything enqueued before it
+static int fetch_shard(psa_context* ctx, DeviceState& d, psa_result* out, bool direct)
+{
+    if (!d.active) return PSA_OK;
+    PSA_CUDA(ctx, cudaSetDevice(d.dev));
+    const size_t bytes = sizeof(QueryRec) * d.G.nq;
+    if (direct) {
+        PSA_CUDA(ctx, cudaMemcpyAsync(out + d.q_begin, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+        PSA_CUDA(ctx, cudaMemcpyAsync((char*)d.h_out.p + bytes, (const char*)d.out.p + bytes, 16, cudaMemcpyDeviceToHost, d.stream));
+    } else {
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, bytes + 16, cudaMemcpyDeviceToHost, d.stream));
+    }
+    PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    d.st_cand = ((const int32_t*)((const char*)d.h_out.p + bytes))[0];
+    if (!direct && ctx->nq > 1) std::memcpy(out + d.q_begin, d.h_out.p, bytes);
+    return PSA_OK;
+}
+
+// after every shard has been fetched: alphabet check and, for a single query, the merge of the per-GPU answers
+static int finish_fetch(psa_context* ctx, psa_result* out)
+{
     for (DeviceState& d : ctx->devs)
-        if (d.active) { PSA_CUDA(ctx, cudaSetDevice(d.dev)); PSA_CUDA(ctx, cudaStreamSynchronize(d.stream)); }
-    return PSA_OK;
-}
-
-static int run_async(psa_context* ctx, bool timed)
-{
-    if (!ctx || !ctx->prepared) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch prepared") : PSA_ERR_ARG;
-    ctx->st_launches = ctx->st_cand = ctx->st_tiles = ctx->st_main_ns = 0;
-    for (DeviceState& d : ctx->devs) {
-        int rc = run_device(ctx, d, timed);
-        if (rc) return rc;
-    }
-    ctx->ran = true;
-    return PSA_OK;
-}
-
-int psa_batch_run(psa_context* ctx, float* device_ms)
-{
-    int rc = run_async(ctx, true);
-    if (rc) return rc;
-    float worst = 0.f;
-    for (DeviceState& d : ctx->devs) {
-        if (!d.active) continue;
-        PSA_CUDA(ctx, cudaSetDevice(d.dev));
-        PSA_CUDA(ctx, cudaEventSynchronize(d.ev1));
-        float ms = 0.f;
-        PSA_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
-        worst = std::max(worst, ms);
-        if (ctx->opt_kernel_events) {
-            float kms = 0.f;
-            PSA_CUDA(ctx, cudaEventElapsedTime(&kms, d.evk0, d.evk1));
-            ctx->st_main_ns = std::max(ctx->st_main_ns, (long long)(kms * 1e6));
-        }
-    }
-    if (device_ms) *device_ms = worst;
-    return PSA_OK;
-}
-
-int psa_batch_fetch(psa_context* ctx, psa_result* out)
-{
-    if (!ctx || !ctx->prepared || !ctx->ran) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch has run") : PSA_ERR_ARG;
-    if (ctx->nq == 0) return PSA_OK;
-    if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
-    // Records have the caller's layout.  A page-locked result array is filled by the copy engine directly; a pageable
-    // one goes through the context's pinned buffer and one memcpy.  The single-query case always stages (merge below).
-    bool direct = false;
-    if (ctx->nq > 1) {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) direct = attr.type == cudaMemoryTypeHost;
-        else cudaGetLastError();
-    }
-    for (DeviceState& d : ctx->devs) {
-        if (!d.active) continue;
-        PSA_CUDA(ctx, cudaSetDevice(d.dev));
-        const size_t bytes = sizeof(QueryRec) * d.G.nq;
-        if (direct) {
-            PSA_CUDA(ctx, cudaMemcpyAsync(out + d.q_begin, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
-            PSA_CUDA(ctx, cudaMemcpyAsync((char*)d.h_out.p + bytes, (const char*)d.out.p + bytes, 16, cudaMemcpyDeviceToHost, d.stream));
-        } else {
-            PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, bytes + 16, cudaMemcpyDeviceToHost, d.stream));
-        }
-    }
-    bool bad_symbol = false;
-    for (DeviceState& d : ctx->devs) {
-        if (!d.active) continue;
-        PSA_CUDA(ctx, cudaSetDevice(d.dev));
-        PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        const int32_t* fl = (const int32_t*)((const char*)d.h_out.p + sizeof(QueryRec) * d.G.nq);
-        ctx->st_cand += fl[0];
-        if (fl[1]) bad_symbol = true;
-    }
-    if (bad_symbol) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
-
+        if (d.active && ((const int32_t*)((const char*)d.h_out.p + sizeof(QueryRec) * d.G.nq))[1])
+            return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
     if (ctx->nq == 1) {
-        // merge the per-GPU candidates of the single query in ascending offset order
+        // per-GPU candidates of the single query in ascending offset order
         std::vector<psa_result> parts;
         for (DeviceState& d : ctx->devs) {
             if (!d.active) continue;
@@ -679,10 +704,83 @@ int psa_batch_fetch(psa_context* ctx, psa_result* out)
         }
         return psa_merge_results(ctx->is_max, parts.data(), (int)parts.size(), out);
     }
-    if (!direct)
-        for (DeviceState& d : ctx->devs)
-            if (d.active) std::memcpy(out + d.q_begin, d.h_out.p, sizeof(QueryRec) * d.G.nq);
     return PSA_OK;
+}
+
+static bool result_array_is_pinned(const psa_context* ctx, const psa_result* out)
+{
+    // Records have the caller's layout.  A page-locked result array is filled by the copy engine directly; a pageable
+    // one goes through the context's pinned buffer and one memcpy.  The single-query case always stages (merge).
+    if (ctx->nq <= 1) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return false;
+}
+
+int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
+                      const char* seq2s, const int64_t* q_off, int32_t nq)
+{
+    int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
+    if (rc) return rc;
+    if (nq == 0) return PSA_OK;
+    // the split-phase form promises a resident batch: wait for the copies here
+    return for_each_device(ctx, [ctx](DeviceState& d) {
+        int r = prepare_shard(ctx, d);
+        if (r || !d.active) return r;
+        PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        return (int)PSA_OK;
+    });
+}
+
+int psa_batch_run(psa_context* ctx, float* device_ms)
+{
+    if (!ctx || !ctx->prepared) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch prepared") : PSA_ERR_ARG;
+    int rc = for_each_device(ctx, [ctx](DeviceState& d) {
+        int r = run_device(ctx, d, true);
+        d.run_ms = 0.f;
+        if (r || !d.active) return r;
+        PSA_CUDA(ctx, cudaEventSynchronize(d.ev1));
+        PSA_CUDA(ctx, cudaEventElapsedTime(&d.run_ms, d.ev0, d.ev1));
+        if (ctx->opt_kernel_events) {
+            float kms = 0.f;
+            PSA_CUDA(ctx, cudaEventElapsedTime(&kms, d.evk0, d.evk1));
+            d.st_main_ns = (long long)(kms * 1e6);
+        }
+        return (int)PSA_OK;
+    });
+    if (rc) return rc;
+    ctx->ran = true;
+    float worst = 0.f;
+    for (const DeviceState& d : ctx->devs) worst = std::max(worst, d.run_ms);
+    if (device_ms) *device_ms = worst;
+    return PSA_OK;
+}
+
+int psa_batch_fetch(psa_context* ctx, psa_result* out)
+{
+    if (!ctx || !ctx->prepared || !ctx->ran) return ctx ? fail(ctx, PSA_ERR_STATE, "no batch has run") : PSA_ERR_ARG;
+    if (ctx->nq == 0) return PSA_OK;
+    if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
+    const bool direct = result_array_is_pinned(ctx, out);
+    int rc = for_each_device(ctx, [ctx, out, direct](DeviceState& d) { return fetch_shard(ctx, d, out, direct); });
+    return rc ? rc : finish_fetch(ctx, out);
+}
+
+// prepare + run + fetch in one round per GPU (what psa_search_batch / psa_search_range do)
+static int search_prepared(psa_context* ctx, psa_result* out)
+{
+    if (ctx->nq == 0) return PSA_OK;
+    if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
+    const bool direct = result_array_is_pinned(ctx, out);
+    int rc = for_each_device(ctx, [ctx, out, direct](DeviceState& d) {
+        int r = prepare_shard(ctx, d);
+        if (!r) r = run_device(ctx, d, false);
+        if (!r) r = fetch_shard(ctx, d, out, direct);
+        return r;
+    });
+    ctx->ran = rc == PSA_OK;
+    return rc ? rc : finish_fetch(ctx, out);
 }
 
 int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
@@ -693,13 +791,11 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, cons
     int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, -1, -1);
     if (rc) return rc;
     const auto t1 = std::chrono::steady_clock::now();
-    if ((rc = run_async(ctx, false))) return rc;
-    const auto t2 = std::chrono::steady_clock::now();
-    rc = psa_batch_fetch(ctx, out);
+    rc = search_prepared(ctx, out);
     if (trace) {
-        const auto t3 = std::chrono::steady_clock::now();
+        const auto t2 = std::chrono::steady_clock::now();
         auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-        std::fprintf(stderr, "[psa] prepare+H2D enqueue %.1f us, launch %.1f us, wait+D2H+host %.1f us\n", us(t0, t1), us(t1, t2), us(t2, t3));
+        std::fprintf(stderr, "[psa] host planning %.1f us, copies + kernels + copy back %.1f us\n", us(t0, t1), us(t1, t2));
     }
     return rc;
 }
@@ -711,8 +807,7 @@ int psa_search_range(psa_context* ctx, const double weights[4], int is_max, cons
     const int64_t q_off[2] = { 0, len2 };
     int rc = prepare_common(ctx, weights, is_max, seq1, len1, seq2, q_off, 1, first, last);
     if (rc) return rc;
-    if ((rc = run_async(ctx, false))) return rc;
-    return psa_batch_fetch(ctx, out);
+    return search_prepared(ctx, out);
 }
 
 int psa_offset_scores(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1, const char* seq2,
