@@ -88,11 +88,18 @@ int  psa_create(psa_context** ctx, const int* devices, int ndevices);
 void psa_destroy(psa_context* ctx);
 const char* psa_last_error(const psa_context* ctx);
 
-/* Tuning knobs (for tests / benchmarks). name: "engine" 0 = auto, 1 = exact scalar kernel only,
-   2 = bit-sliced scan kernel; "rank_planes" = -1 auto / 0..8. Unknown name -> PSA_ERR_ARG. */
+/* Tuning knobs (for tests / benchmarks); every setting gives the same answers.  Unknown name -> PSA_ERR_ARG.
+     "engine"        0 auto | 1 exact scalar kernel only | 2 bit-sliced scan
+     "rank_planes"   -1 auto | 0,1,2,4 rank bit planes tracked by the scan (the rest is settled in-kernel)
+     "scan_warps"    0 auto | 1..4 warps (x1024 offsets) per scan block in long mode
+     "batch_mode"    -1 auto | 0 never | 1 whenever every query fits one window (len2 <= 1023)
+     "slices"        0 auto | 1 never | n>=2 cut a single query into n ranges of alignment steps
+     "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
+     "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
+     "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
-/* Counters of the last run. name: "kernel_launches", "candidate_tiles", "tiles",
-   "fallback_queries", "engine". Unknown -> -1. */
+/* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
+   order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "exact".  Unknown -> -1. */
 long long psa_get_stat(const psa_context* ctx, const char* name);
 
 /* ---- host-side table resolution (no GPU needed) ------------------------------------------ */
