@@ -326,3 +326,19 @@ def test_offset_score_profile(ctx, port, synth):
     assert sc == port.scores([1, 3, 4, 2], True, s1, s2, 100, 164)
     _set_engine(ctx, 0)
     assert ctx.search([1, 3, 4, 2], True, s1, s2).offset >= 0          # the context is still good for searches
+
+
+def test_many_tiny_ragged_queries(ctx, port, synth):
+    """200 000 ragged queries of 1..48 letters against a short Seq1 (some as long as Seq1): per-query bookkeeping at scale."""
+    import numpy as np
+    _set_engine(ctx, 0)
+    s1 = synth.letters(501, 48)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 49, size=200_000)
+    pool = np.frombuffer(synth.letters(502, int(lens.sum())), dtype=np.uint8)
+    cuts = np.concatenate(([0], np.cumsum(lens)))
+    qs = [pool[cuts[k]:cuts[k + 1]].tobytes() for k in range(len(lens))]
+    got = ctx.search_batch([1, 3, 4, 2], False, s1, qs)
+    exp = port.search_batch([1, 3, 4, 2], False, s1, qs)
+    bad = [k for k, (g, e) in enumerate(zip(got, exp)) if not same_answer(g, e)]
+    assert not bad, (len(bad), bad[:5])
