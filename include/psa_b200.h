@@ -95,6 +95,7 @@ const char* psa_last_error(const psa_context* ctx);
      "batch_mode"    -1 auto | 0 never | 1 whenever every query fits one window (len2 <= 1023)
      "slices"        0 auto | 1 never | n>=2 cut a single query into n ranges of alignment steps
      "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
+     "fused_finish"  1 the scan block also finishes its query when the query is a single tile (exact order) | 0 never
      "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);

@@ -85,6 +85,7 @@ struct psa_context {
     int opt_engine = 0;        // 0 auto, 1 exact scalar, 2 bit-sliced scan
     int opt_rank_planes = -1;  // -1 auto
     int opt_scan_warps = 0;    // 0 auto, 1..4
+    int opt_fused_finish = 1;  // 0: always run k_finish as its own kernel
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
@@ -294,6 +295,9 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         }
     }
 
+    d.SG.fused_finish = scan && !ctx->batch_mode && d.SG.slices <= 1 && ctx->table.exact && uniform == 1 &&
+                        ctx->opt_fused_finish != 0;
+
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
@@ -366,8 +370,10 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         d.st_launches += 1;
     }
-    launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
-    d.st_launches += 1;
+    if (!d.SG.fused_finish) {
+        launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
+        d.st_launches += 1;
+    }
     PSA_CUDA(ctx, cudaGetLastError());
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     d.st_tiles += d.G.total_tiles;
@@ -479,6 +485,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!ctx || !name) return PSA_ERR_ARG;
     if (!std::strcmp(name, "engine") && value >= 0 && value <= 2) { ctx->opt_engine = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "fused_finish") && value >= 0 && value <= 1) { ctx->opt_fused_finish = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "derive_rank") && value >= 0 && value <= 1) { ctx->opt_derive_rank = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }

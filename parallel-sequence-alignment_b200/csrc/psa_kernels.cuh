@@ -38,6 +38,7 @@ struct SliceGeom {
     int slice_len = 0;     // steps per slice (multiple of 128)
     int scan_tile = 0;     // offsets per scan block (warps x 1024)
     int scan_tiles = 0;    // scan blocks per slice
+    bool fused_finish = false;  // long mode, exact order, one tile per query: the scan block also finishes its query
     bool allow_derive = true;   // option "derive_rank": take the top-rank bit from the class planes when the table allows it
 };
 constexpr int kCombineTile = 256;   // offsets per tile record in slice mode

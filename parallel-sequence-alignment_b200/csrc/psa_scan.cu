@@ -463,7 +463,7 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 template <int NB, int K, bool BS, bool SLICE, bool DR>
 __global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
-       const int key_planes, const int64_t key_bias, const int slice_len)
+       const int key_planes, const int64_t key_bias, const int slice_len, const int fused_finish)
 {
     constexpr int NUP = NB - 5;
     constexpr int kEntry = (4 * K > 8) ? 4 * K : 8;                 // bytes per window word (max of the two passes)
@@ -626,18 +626,82 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
         if (lane == 0) { s_res[warp] = wbest; s_top[warp] = wtop; }
     }
     __syncthreads();
-    if (tid == 0) {
-        Cand r = s_res[0];
-        int64_t top = s_top[0];
-        for (int w = 1; w < warps; w++) {
-            take(r, s_res[w].key, s_res[w].off);
-            top = s_top[w] > top ? s_top[w] : top;
+    Cand r = s_res[0];
+    int64_t top = s_top[0];
+    for (int w = 1; w < warps; w++) {
+        take(r, s_res[w].key, s_res[w].off);
+        top = s_top[w] > top ? s_top[w] : top;
+    }
+    if (!fused_finish) {
+        if (tid == 0) {
+            TileRec rec;
+            rec.key = r.key; rec.offset = r.off;
+            rec.ub_key = top; rec.ub_offset = 0x7FFFFFFF;
+            rec.score = 0.0; rec.flags = 0; rec.pad = 0;
+            P.tiles[tile_id] = rec;
         }
-        TileRec rec;
-        rec.key = r.key; rec.offset = r.off;
-        rec.ub_key = top; rec.ub_offset = 0x7FFFFFFF;
-        rec.score = 0.0; rec.flags = 0; rec.pad = 0;
-        P.tiles[tile_id] = rec;
+        return;
+    }
+    // Fused finish (exact order, one tile per query): this block already holds the query's winner, so it also
+    // does what k_finish would -- sign counts, first position carrying the best rank, replacement letter, score --
+    // and the extra launch disappears.
+    __shared__ unsigned long long s_pos;
+    __shared__ int s_cnt[4];
+    if (tid == 0) s_pos = 0ull;
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    QueryRec out;
+    out.score = T.is_max ? -INFINITY : INFINITY;
+    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
+    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
+    if (r.key == kKeyNone) {
+        if (tid == 0) P.out[q] = out;
+        return;
+    }
+    const uint8_t* a = P.seq1 + r.off;
+    const uint8_t* b = P.seq2s + qbeg;
+    int cnt[4] = { 0, 0, 0, 0 };
+    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
+#pragma unroll 2
+    for (int i = tid; i < len2; i += nthreads) {
+        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        const uint32_t code = __ldg(P.code_table + c2 * kRowPad + c1);
+        cnt[code & 3u]++;
+        const unsigned long long p = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
+        pos = p > pos ? p : pos;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
+        pos = o > pos ? o : pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
+    }
+    if (lane == 0) {
+        atomicMax(&s_pos, pos);
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int rank = int(s_pos >> 32);
+        const int i = int(~uint32_t(s_pos));
+        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        out.offset = r.off;
+        out.char_offset = i;
+        out.ch = T.sub[c2][c1];
+        out.rank = rank;
+        double sc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            out.counts[c] = s_cnt[c];
+            sc = __dadd_rn(sc, __dmul_rn(double(s_cnt[c]), T.wcls[c]));        // exact (psa_table.cpp), same as k_finish
+        }
+        out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
+        if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
+        P.out[q] = out;
     }
 }
 
@@ -912,14 +976,14 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
                 static bool done_dr[64];
                 allow_big_smem(k_scan<NB, K, false, true, true>, done_dr);
                 launch_dependent(k_scan<NB, K, false, true, true>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P,
-                                 nwords, chunk, 0, int64_t(0), SG.slice_len);
+                                 nwords, chunk, 0, int64_t(0), SG.slice_len, 0);
                 launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
                 return;
             }
         }
         allow_big_smem(k_scan<NB, K, false, true, false>, done);
         launch_dependent(k_scan<NB, K, false, true, false>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P, nwords, chunk, 0,
-                         int64_t(0), SG.slice_len);
+                         int64_t(0), SG.slice_len, 0);
         launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
         return;
     }
@@ -956,12 +1020,12 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
                 static bool done_dr[64];
                 allow_big_smem(k_scan<NB, K, BS, false, true>, done_dr);
                 launch_dependent(k_scan<NB, K, BS, false, true>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk,
-                                 key_planes, key_bias, 0);
+                                 key_planes, key_bias, 0, SG.fused_finish ? 1 : 0);
                 return;
             }
         }
         allow_big_smem(k_scan<NB, K, BS, false, false>, done);
-        launch_dependent(k_scan<NB, K, BS, false, false>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, key_planes, key_bias, 0);
+        launch_dependent(k_scan<NB, K, BS, false, false>, dim3(G.total_tiles), dim3(warps * 32), smem, stream, T, G, P, nwords, chunk, key_planes, key_bias, 0, SG.fused_finish ? 1 : 0);
     }
 }
 

@@ -342,3 +342,19 @@ def test_many_tiny_ragged_queries(ctx, port, synth):
     exp = port.search_batch([1, 3, 4, 2], False, s1, qs)
     bad = [k for k, (g, e) in enumerate(zip(got, exp)) if not same_answer(g, e)]
     assert not bad, (len(bad), bad[:5])
+
+
+def test_fused_finish_matches_separate_finish(ctx, port, synth):
+    """Long mode, one tile per query: the scan block finishes its own query (default) or leaves it to k_finish."""
+    wl = synth.workload("c3", nq=96)
+    res = {}
+    for fused in (1, 0):
+        _set_engine(ctx, 2, batch=0)
+        ctx.set_option("fused_finish", fused)
+        res[fused] = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+        assert ctx.stat("kernel_launches") == (2 if fused else 3)
+    ctx.set_option("fused_finish", 1)
+    _set_engine(ctx, 0)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    for a, b, e in zip(res[1], res[0], exp):
+        assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
