@@ -358,3 +358,27 @@ def test_fused_finish_matches_separate_finish(ctx, port, synth):
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     for a, b, e in zip(res[1], res[0], exp):
         assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
+
+
+def test_reference_program_links_against_the_library(tmp_path, input_blocks):
+    """The drop-in proof: the reference's OWN executable -- its unmodified main.c, cpu_funcs.c (file I/O,
+    divide_execute_tasks, the call to gpu_run_program at cpu_funcs.c:180) and mpi_funcs.c, MPI stubbed to one rank --
+    linked against libpsa_b200.so (oracle/Makefile target `ref` builds oracle/_ref/mpiCudaOpenMP_dropin where
+    /root/reference exists).  With every offset on the GPU its output.txt must be byte-identical to the reference's
+    own CPU answer."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "mpiCudaOpenMP_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mpiCudaOpenMP_dropin not built (needs /root/reference)")
+    for k, b in enumerate(input_blocks):
+        d = tmp_path / f"blk{k}"
+        d.mkdir()
+        (d / "input.txt").write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n")
+        e = b["expect"]
+        mut = b["seq2"][: e["char_offset"]] + e["ch"] + b["seq2"][e["char_offset"] + 1:]
+        for argv in (["100"], []) if k in (0, 4, 6) else (["100"],):      # no argument = the reference's auto policy (GPU for big problems)
+            p = subprocess.run([exe] + argv, cwd=d, capture_output=True, text=True, timeout=120)
+            assert p.returncode == 0, (k, argv, p.stderr[-500:])
+            assert "CUDA percentage set to 100" in p.stdout, (k, argv, p.stdout)
+            assert (d / "output.txt").read_text() == "%s\n%d %s" % (mut, e["offset"], e["score_g"]), (k, argv)
