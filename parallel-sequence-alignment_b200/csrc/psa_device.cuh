@@ -3,6 +3,15 @@
 #include <cuda_runtime.h>
 #include "psa_common.h"
 
+// PSA_CHECK: index / range invariants of the kernels, compiled in only by `make DEBUG=1` (device assert).  The pool
+// refuses compute-sanitizer, so a debug run of the GPU tests with these on is the memory-safety net.
+#if defined(PSA_DEBUG)
+#include <assert.h>
+#define PSA_CHECK(cond) assert(cond)
+#else
+#define PSA_CHECK(cond) ((void)0)
+#endif
+
 namespace psa {
 namespace {
 

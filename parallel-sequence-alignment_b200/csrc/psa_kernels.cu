@@ -256,6 +256,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
 
     const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
     const int t0 = qg.tile0, t1 = q + 1 < G.nq ? first_tile_of(G, P.tile_start, q + 1) : G.total_tiles;
+    PSA_CHECK(t0 >= 0 && t0 <= t1 && t1 <= G.total_tiles);
     const int64_t qbeg = qg.qbeg;
     const int len2 = qg.len2;
     const int64_t first = G.last >= 0 ? G.first : 0;
@@ -359,6 +360,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
         return;
     }
 
+    PSA_CHECK(win.off >= first && win.off < last && int64_t(win.off) + len2 <= G.len1);
     const uint8_t* a = P.seq1 + win.off;
     int cnt[4] = { 0, 0, 0, 0 };
     unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i

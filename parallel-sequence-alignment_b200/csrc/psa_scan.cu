@@ -518,6 +518,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
         for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
             const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
             const int need = round_up4(warps * 32 + (cl >> 5));
+            PSA_CHECK(need <= nwords && cl <= chunk && ((tb + c0) >> 5) + need <= P.plane_words && ((tb + c0) & 127) == 0);
             __syncthreads();                                        // previous window consumed / barrier initialised
             if (warp == 0) {
                 const int64_t g0 = (tb + c0) >> 5;                  // multiple of 4: every row starts on 16 bytes
@@ -553,6 +554,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
         const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
         const int need = round_up4(warps * 32 + (cl >> 5));
+        PSA_CHECK(need <= nwords && cl <= chunk && ((tb + c0) >> 5) + need <= P.plane_words && ((tb + c0) & 127) == 0);
         __syncthreads();
         if (warp == 0) {
             const int64_t g0 = (tb + c0) >> 5;
@@ -594,6 +596,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             for (int k = 0; k < K; k++) m2[16 + k] = racc[k];
             transpose32(m);
             transpose32(m2);
+            PSA_CHECK(ln0 - tile_base(first) >= 0 && ln0 - tile_base(first) + 32 <= P.partial_stride);
             uint2* dst = P.partial + int64_t(blockIdx.y) * P.partial_stride + (ln0 - tile_base(first));
 #pragma unroll
             for (int tt = 0; tt < 32; tt++)
@@ -632,6 +635,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
         take(r, s_res[w].key, s_res[w].off);
         top = s_top[w] > top ? s_top[w] : top;
     }
+    PSA_CHECK(tile_id < G.total_tiles && q < G.nq);
     if (!fused_finish) {
         if (tid == 0) {
             TileRec rec;
@@ -724,6 +728,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     const int len2 = G.uniform_len2;
     const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
     const int64_t rel = int64_t(blockIdx.x) * kCombineThreads + tid;
+    PSA_CHECK(int(blockIdx.x) < G.total_tiles && G.uniform_len2 > 0 && G.last >= 0);
     const int64_t n = tile_base(first) + rel;
     const bool valid = n >= first && n < last;
 
@@ -736,6 +741,7 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     if (valid) {
         uint32_t na = 0, nb = 0, nc = 0, rb = 0;
         for (int sl = 0; sl < slices; sl++) {
+            PSA_CHECK(rel < P.partial_stride);
             const uint2 v = P.partial[int64_t(sl) * P.partial_stride + rel];
             na += v.x & 0xFFFFu; nb += v.x >> 16; nc += v.y & 0xFFFFu; rb |= v.y >> 16;
         }
@@ -831,6 +837,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     }
     __syncthreads();
     pdl_wait();                                                     // the bit planes come from k_profile
+    PSA_CHECK((tb >> 5) + nwords <= P.plane_words && (nwords & 3) == 0);
     if (warp == 0 && lane < kPlaneRows) {
         const int64_t g0 = tb >> 5;
         tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(nwords) * 8u, &s_bar);
@@ -853,6 +860,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         if (tb >= last) continue;                                   // this query does not reach the tile
         const uint32_t vmask = valid_mask(ln0, 0, last);
         const int steps_total = (len2 + 31) & ~31;
+        PSA_CHECK(steps_total <= chunk && 32 + (steps_total >> 5) <= nwords && qg.tile0 + tile < G.total_tiles);
         __syncwarp();                                               // previous query's row offsets are no longer read
         for (int s = lane; s < steps_total; s += 32) {
             uint32_t row = kZeroRow;
