@@ -311,6 +311,9 @@ def run_ours(args, synth, rank, local_rank, world):
     ctx = psa.Context(devices=[local_rank])
     if args.engine:
         ctx.set_option("engine", args.engine)
+    for kv in args.opt:                                                   # library tuning knobs (psa_set_option), for A/B runs
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
     batch = psa.Batch(wl.seq1, wl.queries, pinned=True)
     pair_evals = batch.pair_evals
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
@@ -398,7 +401,7 @@ def run_ours(args, synth, rank, local_rank, world):
             "config": {"workload": workload_name(args.workload, wl), "pair_evals_per_gpu_step": pair_evals,
                        "l2": "flushed between timed steps (512 MiB write)", "engine": {1: "scalar", 2: "bitsliced-scan"}.get(engine, engine),
                        "exact_integer_keys": bool(ctx.stat("exact")), "rank_planes": ctx.stat("rank_planes"),
-                       "scan_warps": ctx.stat("scan_warps"), "rescored_words": ctx.stat("candidate_tiles"), "sharding": "one full batch per rank, no collective"},
+                       "scan_warps": ctx.stat("scan_warps"), "packed_queries_per_block": ctx.stat("packed_queries"), "rescored_words": ctx.stat("candidate_tiles"), "sharding": "one full batch per rank, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes,
                     "d2h_bytes_per_step": 56 * batch.nq + 16, "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": launches,
@@ -449,6 +452,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 scalar, 2 bit-sliced scan")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="psa_set_option knob, repeatable (A/B runs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the quick measurements of the other BASELINE configs")

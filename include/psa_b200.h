@@ -97,10 +97,13 @@ const char* psa_last_error(const psa_context* ctx);
      "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
      "fused_finish"  1 the scan block also finishes its query when the query is a single tile (exact order) | 0 never
      "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
+     "pack_queries"  1 auto: equal-length queries that fit one window share blocks lane by lane when whole warps per
+                     query would idle | 0 never | 2..8 force that many queries per block
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
-   order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "exact".  Unknown -> -1. */
+   order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact".
+   Unknown -> -1. */
 long long psa_get_stat(const psa_context* ctx, const char* name);
 
 /* ---- host-side table resolution (no GPU needed) ------------------------------------------ */

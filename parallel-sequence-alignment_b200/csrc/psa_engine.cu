@@ -87,6 +87,7 @@ struct psa_context {
     int opt_scan_warps = 0;    // 0 auto, 1..4
     int opt_fused_finish = 1;  // 0: always run k_finish as its own kernel
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
+    int opt_pack_queries = 1;  // 0 never pack | 1 auto | 2..8 force that many queries per block (tests)
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
@@ -298,6 +299,30 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.SG.fused_finish = scan && !ctx->batch_mode && d.SG.slices <= 1 && ctx->table.exact && uniform == 1 &&
                         ctx->opt_fused_finish != 0;
 
+    // Packed mode: equal-length queries that each fit one window share blocks lane by lane (k_scan_packed) when that
+    // leaves fewer idle lanes than whole warps per query do.
+    if (scan && !ctx->batch_mode && d.SG.slices <= 1 && uniform_len && uniform == 1 && last < 0 && nq >= 2 &&
+        ctx->max_len2 <= 1023 && ctx->opt_pack_queries != 0) {
+        const int64_t lanes = (offsets_of(len1, ctx->uniform_len2) + 31) / 32;      // per query
+        const double plain = double(lanes) / double(32 * ((lanes + 31) / 32));
+        int best_q = 0, best_w = 0;
+        double best_u = 0.0;
+        if (ctx->opt_pack_queries >= 2) {                                            // forced (tests)
+            const int64_t w = (ctx->opt_pack_queries * lanes + 31) / 32;
+            if (w <= kPackMaxWarps && ctx->opt_pack_queries <= kPackMaxQ) { best_q = ctx->opt_pack_queries; best_w = (int)w; }
+        } else if (lanes >= 1) {
+            for (int w = 1; w <= kPackMaxWarps; w++) {
+                const int q = (int)std::min<int64_t>(std::min<int64_t>(kPackMaxQ, nq), (32 * w) / lanes);
+                if (q < 2) continue;
+                const int ww = (int)((q * lanes + 31) / 32);                         // warps those q queries really need
+                const double u = double(q * lanes) / double(32 * ww);
+                if (u > best_u + 1e-9) { best_u = u; best_q = q; best_w = ww; }
+            }
+            if (best_u < plain * 1.05) best_q = 0;                                   // not worth leaving the plain kernel
+        }
+        if (best_q >= 2 && scan_packed_fits(len1, ctx->uniform_len2)) { d.SG.pack_q = best_q; d.SG.pack_warps = best_w; }
+    }
+
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
@@ -487,6 +512,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "rank_planes") && value >= -1 && value <= 8) { ctx->opt_rank_planes = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "fused_finish") && value >= 0 && value <= 1) { ctx->opt_fused_finish = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "derive_rank") && value >= 0 && value <= 1) { ctx->opt_derive_rank = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "pack_queries") && value >= 0 && value <= kPackMaxQ) { ctx->opt_pack_queries = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
@@ -512,6 +538,8 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
     if (!std::strcmp(name, "batch_mode")) return ctx->batch_mode ? 1 : 0;
     if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.slices; return 1; }
+    if (!std::strcmp(name, "packed_queries")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_q; return 0; }
+    if (!std::strcmp(name, "packed_warps")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_warps; return 0; }
     if (!std::strcmp(name, "exact")) return ctx->table.exact;
     return -1;
 }

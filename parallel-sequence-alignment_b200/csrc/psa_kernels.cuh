@@ -40,8 +40,14 @@ struct SliceGeom {
     int scan_tiles = 0;    // scan blocks per slice
     bool fused_finish = false;  // long mode, exact order, one tile per query: the scan block also finishes its query
     bool allow_derive = true;   // option "derive_rank": take the top-rank bit from the class planes when the table allows it
+    int pack_q = 0;             // packed mode (k_scan_packed): queries per block, 0 = off
+    int pack_warps = 0;         //   and warps per block = ceil(pack_q * lanes per query / 32)
 };
 constexpr int kCombineTile = 256;   // offsets per tile record in slice mode
+constexpr int kPackMaxQ = 8;        // packed mode: queries per block
+constexpr int kPackMaxWarps = 8;    //   and warps per block
+// packed mode: does one window hold every offset of a (len1, len2) query, inside the plane buffer?
+bool scan_packed_fits(int64_t len1, int64_t len2);
 
 // ---- launchers (all asynchronous on `stream`) -------------------------------------------------
 // exact scalar kernel over every tile (engine 1)

@@ -137,37 +137,87 @@ __device__ __forceinline__ void class_group(VCounter<NUP>& A, VCounter<NUP>& B, 
     }
 }
 
-// Same, while the top-rank bit of a pair is a function of its sign class (DeviceTable::top_rank_lut): the bit is
-// derived from the two class words and OR-ed into racc0 -- no rank plane, no second pass.  m[c] = all-ones if class c
-// carries the top rank.
-template <int NUP>
-__device__ __forceinline__ void class_group_derive(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, uint32_t& racc0,
-                                                   const uint32_t (&m)[4], const char* pw, const uint32_t* ro)
+// Walk one alignment (Seq1 window `a`, query `b`): sign-class counts and the best (rank, lowest i) packed as
+// (rank << 32) | ~i.  Thread t of nt; the 2U byte loads of a round are issued together, then the U table lookups.
+template <int U>
+__device__ __forceinline__ void walk_alignment(const uint8_t* a, const uint8_t* b, const uint8_t* code_table, int len2, int t, int nt,
+                                               int (&cnt)[4], unsigned long long& pos)
 {
-    uint32_t pa[5], pb[5], pn[5];
+    for (int base = t; base < len2; base += U * nt) {
+        uint8_t va[U], vb[U];
 #pragma unroll
-    for (int s4 = 0; s4 < 32; s4 += 4) {
-        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
-        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * nt;
+            va[u] = i < len2 ? a[i] : uint8_t('A');
+            vb[u] = i < len2 ? b[i] : uint8_t('A');
+        }
+        uint32_t code[U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int s = s4 + u;
-            const uint32_t off = offs[u];
-            const uint2 lo = *reinterpret_cast<const uint2*>(pw + off);
-            uint32_t x0 = lo.x, x1 = lo.y;
-            if (s != 0) {
-                const uint2 hi = *reinterpret_cast<const uint2*>(pw + off + 8);
-                x0 = __funnelshift_r(lo.x, hi.x, s);
-                x1 = __funnelshift_r(lo.y, hi.y, s);
+        for (int u = 0; u < U; u++) {
+            uint32_t c1 = symbol_of(va[u]), c2 = symbol_of(vb[u]);
+            if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+            code[u] = __ldg(code_table + c2 * kRowPad + c1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * nt;
+            if (i < len2) {
+                cnt[code[u] & 3u]++;
+                const unsigned long long p = (uint64_t(code[u] >> 2) << 32) | uint32_t(~uint32_t(i));
+                pos = p > pos ? p : pos;
             }
-            vc_feed(A, pa, x0, s);
-            vc_feed(B, pb, x1, s);
-            vc_feed(C, pn, x0 & x1, s);
-            const uint32_t lo_cls = (x1 & m[2]) | (~x1 & m[0]);        // class has bit0 = 0: '*' or '.'
-            const uint32_t hi_cls = (x1 & m[3]) | (~x1 & m[1]);        // class has bit0 = 1: ':' or '_'
-            racc0 |= (x0 & hi_cls) | (~x0 & lo_cls);
         }
     }
+}
+
+// Per-step row offsets (row * row_bytes) of alignment steps [i0, i0 + n) of the query at `src`; steps at or past len2
+// read the all-zero row.  Thread t of nt; the U byte loads of a round are issued together (one global round trip).
+// Returns true if a byte outside [A-Z-] was met.
+template <int U>
+__device__ __forceinline__ bool fill_rows(uint32_t* dst, const uint8_t* src, int i0, int n, int len2, uint32_t row_bytes, int t, int nt)
+{
+    bool bad = false;
+    for (int base = t; base < n; base += U * nt) {
+        uint8_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int st = base + u * nt;
+            v[u] = (st < n && i0 + st < len2) ? src[i0 + st] : uint8_t('A');
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int st = base + u * nt;
+            if (st < n) {
+                uint32_t row = kZeroRow;
+                if (i0 + st < len2) {
+                    row = symbol_of(v[u]);
+                    if (row == 0xFFu) { bad = true; row = 0; }
+                }
+                dst[st] = row * row_bytes;
+            }
+        }
+    }
+    return bad;
+}
+
+// When the top-rank bit of a pair is a function of its sign class (DeviceTable::top_rank_lut, never class 0), an offset
+// met the top rank iff it met a pair of such a class, i.e. iff that class count is non-zero: N(':') = N(b0) - N(b0&b1),
+// N('.') = N(b1) - N(b0&b1), N('_') = N(b0&b1).  So the bit falls out of the three counters after the scan -- no rank
+// plane, no second pass, nothing per step.
+template <int NB, int NUP>
+__device__ __forceinline__ uint32_t derive_top_rank(const DeviceTable& T, const VCounter<NUP>& A, const VCounter<NUP>& B,
+                                                    const VCounter<NUP>& C)
+{
+    uint32_t nz1 = 0, nz2 = 0, nz3 = 0;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const uint32_t c = C.plane(k);
+        nz1 |= A.plane(k) ^ c;
+        nz2 |= B.plane(k) ^ c;
+        nz3 |= c;
+    }
+    const int lut = T.top_rank_lut;
+    return ((lut & 2) ? nz1 : 0u) | ((lut & 4) ? nz2 : 0u) | ((lut & 8) ? nz3 : 0u);
 }
 
 template <int K>
@@ -459,7 +509,7 @@ __device__ __forceinline__ Cand settle_unresolved(const DeviceTable& T, const Ba
 // SLICE = true (single query, few warp-tiles): blockIdx.y selects a slice of the alignment steps
 // [slice * slice_len, ...); the block leaves its partial counts and rank bits per offset in P.partial and
 // k_combine adds the slices up -- this multiplies the warps in flight when one query cannot fill the GPU.
-// DR = true (K = 1 only): the rank plane is derived from the class planes (class_group_derive), pass R is skipped.
+// DR = true (K = 1 only): the top-rank bit is derived from the class counts (derive_top_rank), pass R is skipped.
 template <int NB, int K, bool BS, bool SLICE, bool DR>
 __global__ void __launch_bounds__(128, NB <= 10 ? 6 : 4)
 k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int chunk,
@@ -501,15 +551,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 
     // Seq2 slice -> per-step row offsets (row * nwords * 8 bytes); padding steps use the all-zero row
     auto fill_row_offsets = [&](int c0, int cl) {
-        for (int s = tid; s < cl; s += nthreads) {
-            const int i = c0 + s;
-            uint32_t row = kZeroRow;
-            if (i < len2) {
-                row = symbol_of(P.seq2s[qbeg + i]);
-                if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
-            }
-            s_ro[s] = row * uint32_t(nwords) * 8u;
-        }
+        if (fill_rows<8>(s_ro, P.seq2s + qbeg, c0, cl, len2, uint32_t(nwords) * 8u, tid, nthreads)) atomicOr(P.err_flag, 1);
     };
 
     // ---- pass R: best rank per offset -----------------------------------------------------------------
@@ -547,10 +589,6 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     // ---- pass C: sign-class counts --------------------------------------------------------------------
     VCounter<NUP> A, B, C;
     A.clear(); B.clear(); C.clear();
-    bool derive_on = DR;
-    uint32_t dmask[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) dmask[c] = (DR && ((T.top_rank_lut >> c) & 1)) ? 0xFFFFFFFFu : 0u;
     for (int c0 = step_begin; c0 < steps_total; c0 += chunk) {
         const int cl = (steps_total - c0) < chunk ? (steps_total - c0) : chunk;
         const int need = round_up4(warps * 32 + (cl >> 5));
@@ -572,15 +610,11 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
             const int groups = cl >> 5;
             for (int g = 0; g < groups; g++) {
                 const char* pw = reinterpret_cast<const char*>(smem) + size_t(warp * 32 + lane + g) * 8;
-                if (DR && derive_on) {
-                    class_group_derive<NUP>(A, B, C, racc[0], dmask, pw, s_ro + g * 32);
-                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) derive_on = false;
-                } else {
-                    class_group<NUP>(A, B, C, pw, s_ro + g * 32);
-                }
+                class_group<NUP>(A, B, C, pw, s_ro + g * 32);
             }
         }
     }
+    if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
 
     // ---- epilogue -------------------------------------------------------------------------------------
     pdl_launch_dependents();
@@ -666,15 +700,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
     const uint8_t* b = P.seq2s + qbeg;
     int cnt[4] = { 0, 0, 0, 0 };
     unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
-#pragma unroll 2
-    for (int i = tid; i < len2; i += nthreads) {
-        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
-        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-        const uint32_t code = __ldg(P.code_table + c2 * kRowPad + c1);
-        cnt[code & 3u]++;
-        const unsigned long long p = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
-        pos = p > pos ? p : pos;
-    }
+    walk_alignment<6>(a, b, P.code_table, len2, tid, nthreads, cnt, pos);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
@@ -846,9 +872,6 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
                         uint32_t(nwords) * 4u * K, &s_bar);
     }
     bool staged = false;
-    uint32_t dmask[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) dmask[c] = (DR && ((T.top_rank_lut >> c) & 1)) ? 0xFFFFFFFFu : 0u;
 
     const int q_begin = blockIdx.x * queries_per_block;
     const int q_end = (q_begin + queries_per_block) < G.nq ? (q_begin + queries_per_block) : G.nq;
@@ -862,6 +885,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         const int steps_total = (len2 + 31) & ~31;
         PSA_CHECK(steps_total <= chunk && 32 + (steps_total >> 5) <= nwords && qg.tile0 + tile < G.total_tiles);
         __syncwarp();                                               // previous query's row offsets are no longer read
+        // short queries, one warp: the plain loop beats batched predicated loads here (config 5: 2.07 vs 2.31 ms)
         for (int s = lane; s < steps_total; s += 32) {
             uint32_t row = kZeroRow;
             if (s < len2) {
@@ -886,16 +910,9 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         }
         VCounter<NUP> A, B, C;
         A.clear(); B.clear(); C.clear();
-        bool derive_on = DR;
-        for (int g = 0; g < groups; g++) {
-            const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8;
-            if (DR && derive_on) {
-                class_group_derive<NUP>(A, B, C, racc[0], dmask, pw, s_ro + g * 32);
-                if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) derive_on = false;
-            } else {
-                class_group<NUP>(A, B, C, pw, s_ro + g * 32);
-            }
-        }
+        for (int g = 0; g < groups; g++)
+            class_group<NUP>(A, B, C, reinterpret_cast<const char*>(s_cls) + size_t(lane + g) * 8, s_ro + g * 32);
+        if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
 
         Cand mine{ kKeyNone, 0x7FFFFFFF }, ub{ kKeyNone, 0x7FFFFFFF };
         typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
@@ -923,6 +940,220 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     }
     if (!staged) mbar_wait(&s_bar, 0);      // never leave with a bulk copy in flight
     pdl_launch_dependents();
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_scan_packed (packed mode: equal-length queries whose whole offset range fits one window, len2 <= 1023)
+//
+// A query with `noff` offsets needs L = ceil(noff / 32) lanes; k_scan gives it whole warps, so e.g. 2501 offsets
+// (L = 79) occupy 3 warps = 96 lanes and every sixth lane-instruction is idle.  Here a block owns Q whole queries and
+// lays their lanes end to end: thread t works on query t / L, offset word t % L, and the block is ceil(Q L / 32) warps
+// (config 3: Q = 2, 5 warps, 158 of 160 lanes busy).  All queries of a batch read the same Seq1 window, which is staged
+// once per block; only the per-step row offsets differ per query, and a warp that straddles two queries simply reads
+// two rows (the 64-bit loads are served per half-warp anyway).  Per-query results come from a segmented reduction:
+// each warp reduces (and, in exact mode, settles) one query segment at a time, a thread per query merges the warps.
+// -------------------------------------------------------------------------------------------------
+
+// what the fused finish of k_scan does, by one warp: sign counts, first position carrying the best rank,
+// replacement letter and score of the winning offset -> QueryRec
+__device__ __forceinline__ void finish_query_warp(const DeviceTable& T, const BatchPtrs& P, int q, int64_t qbeg, int len2, Cand r)
+{
+    const int lane = threadIdx.x & 31;
+    QueryRec out;
+    out.score = T.is_max ? -INFINITY : INFINITY;
+    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
+    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
+    if (r.key == kKeyNone) {
+        if (lane == 0) P.out[q] = out;
+        return;
+    }
+    const uint8_t* a = P.seq1 + r.off;
+    const uint8_t* b = P.seq2s + qbeg;
+    int cnt[4] = { 0, 0, 0, 0 };
+    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
+    walk_alignment<8>(a, b, P.code_table, len2, lane, 32, cnt, pos);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
+        pos = o > pos ? o : pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
+    }
+    if (lane == 0) {
+        const int rank = int(pos >> 32);
+        const int i = int(~uint32_t(pos));
+        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
+        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        out.offset = r.off;
+        out.char_offset = i;
+        out.ch = T.sub[c2][c1];
+        out.rank = rank;
+        double sc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            out.counts[c] = cnt[c];
+            sc = __dadd_rn(sc, __dmul_rn(double(cnt[c]), T.wcls[c]));          // exact (psa_table.cpp), same as k_finish
+        }
+        out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
+        if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
+        P.out[q] = out;
+    }
+}
+
+template <int NB, int K, bool BS, bool DR>
+__global__ void __launch_bounds__(256, NB <= 10 ? 3 : 2)
+k_scan_packed(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int nwords, const int steps,
+              const int Q, const int L, const int key_planes, const int64_t key_bias, const int fused_finish)
+{
+    constexpr int NUP = NB - 5;
+    constexpr bool kRankPass = K > 0 && !DR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_cls = smem;
+    unsigned char* s_rnk = smem + size_t(kPlaneRows) * nwords * 8;
+    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + (kRankPass ? size_t(kPlaneRows) * nwords * 4 * K : 0));
+    const int ro_stride = steps + 4;            // + 16 bytes: the row-offset vectors of different queries fall into different banks
+    __shared__ Cand s_part[kPackMaxWarps][kPackMaxQ];
+    __shared__ int64_t s_ptop[kPackMaxWarps][kPackMaxQ];
+    __shared__ Cand s_best[kPackMaxQ];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, warps = nthreads >> 5;
+    const int len2 = G.uniform_len2;
+    const int64_t noff = G.len1 - len2 + 1;
+    const int q0 = blockIdx.x * Q;
+    const int nqb = (G.nq - q0) < Q ? (G.nq - q0) : Q;              // queries of this block
+    const int j = tid / L, l = tid - j * L;                         // my query in the block, my offset word in the query
+    const bool lane_on = j < nqb;
+    const int jc = lane_on ? j : 0, lc = lane_on ? l : 0;           // idle lanes shadow lane 0 (addresses stay valid)
+    const int64_t ln0 = int64_t(lc) * 32;
+    const uint32_t vmask = lane_on ? valid_mask(ln0, 0, noff) : 0u;
+    PSA_CHECK(G.uniform_len2 > 0 && G.tiles_per_query == 1 && G.last < 0 && Q <= kPackMaxQ && warps <= kPackMaxWarps &&
+              Q * L <= nthreads && steps <= kScanChunkMax && L + (steps >> 5) + 1 <= nwords && nwords <= P.plane_words);
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(nwords) * uint32_t(8 + (kRankPass ? 4 * K : 0)));
+    }
+    __syncthreads();
+    pdl_wait();                                                     // the bit planes come from k_profile
+    if (warp == 0 && lane < kPlaneRows) {
+        tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words, uint32_t(nwords) * 8u, &s_bar);
+        if (kRankPass)
+            tma_load_1d(s_rnk + size_t(lane) * nwords * 4 * K, P.rank_planes + int64_t(lane) * P.plane_words * K,
+                        uint32_t(nwords) * 4u * K, &s_bar);
+    }
+    // per-step row offsets of the block's queries: their bytes are one contiguous run of nqb * len2 (equal lengths);
+    // eight loads per thread in flight, then the padding steps (the all-zero row)
+    {
+        const uint8_t* src = P.seq2s + int64_t(q0) * len2;
+        const int nbytes = nqb * len2;
+        bool bad = false;
+        for (int base = tid; base < nbytes; base += 8 * nthreads) {
+            uint8_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (base + u * nthreads) < nbytes ? src[base + u * nthreads] : uint8_t('A');
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = base + u * nthreads;
+                if (e < nbytes) {
+                    const int jj = e / len2, st = e - jj * len2;
+                    uint32_t row = symbol_of(v[u]);
+                    if (row == 0xFFu) { bad = true; row = 0; }
+                    s_ro_all[jj * ro_stride + st] = row * uint32_t(nwords) * 8u;
+                }
+            }
+        }
+        const int pad = steps - len2;
+        for (int e = tid; e < nqb * pad; e += nthreads) {
+            const int jj = e / pad, st = len2 + (e - jj * pad);
+            s_ro_all[jj * ro_stride + st] = uint32_t(kZeroRow) * uint32_t(nwords) * 8u;
+        }
+        if (bad) atomicOr(P.err_flag, 1);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+
+    const uint32_t* ro = s_ro_all + jc * ro_stride;
+    const int groups = steps >> 5;
+    uint32_t racc[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0;
+    racc[0] = ~vmask;
+    if (kRankPass) {
+        for (int g = 0; g < groups; g++) {
+            rank_group<K>(racc, reinterpret_cast<const char*>(s_rnk) + size_t(lc + g) * 4 * K, ro + g * 32);
+            if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+        }
+    }
+    VCounter<NUP> A, B, C;
+    A.clear(); B.clear(); C.clear();
+    for (int g = 0; g < groups; g++)
+        class_group<NUP>(A, B, C, reinterpret_cast<const char*>(s_cls) + size_t(lc + g) * 8, ro + g * 32);
+    if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
+    pdl_launch_dependents();
+
+    // ---- per-lane keys, then one query segment of the warp at a time ------------------------------------
+    const Cand none{ kKeyNone, 0x7FFFFFFF };
+    Cand mine = none, ub = none;
+    typename std::conditional<BS, SlicedKeys<NB, K>, OffsetKeys<NB, K, false>>::type keys;
+    keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
+    const uint32_t umask = keys.scan(vmask, ln0, mine, ub);
+    const int words_per_tile = G.tile >> 5;
+    if (!T.exact) {
+        // re-score mode: an upper estimate per 32-offset word for k_finish; words past the query's last one hold nothing
+        const int64_t top = mine.key > ub.key ? mine.key : ub.key;
+        if (lane_on) P.lane_keys[int64_t(q0 + j) * words_per_tile + l] = top;
+        for (int e = tid; e < nqb * (words_per_tile - L); e += nthreads) {
+            const int jj = e / (words_per_tile - L), w = e - jj * (words_per_tile - L);
+            P.lane_keys[int64_t(q0 + jj) * words_per_tile + L + w] = kKeyNone;
+        }
+    }
+    const int jlo = (warp * 32) / L;
+    const int jhi = ((warp * 32 + 31) / L) < (nqb - 1) ? ((warp * 32 + 31) / L) : (nqb - 1);
+    for (int jj = jlo; jj <= jhi; jj++) {                           // warp-uniform
+        const bool in = lane_on && j == jj;
+        Cand wb;
+        int64_t wtop = kKeyNone;
+        if (T.exact) {
+            wb = settle_unresolved(T, P, keys, in ? mine : none, in ? ub : none, in ? umask : 0u, ln0, int64_t(q0 + jj) * len2, len2);
+        } else {
+            wb = warp_best(in ? mine : none);
+            wtop = in ? (mine.key > ub.key ? mine.key : ub.key) : kKeyNone;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const int64_t o = __shfl_xor_sync(0xFFFFFFFFu, wtop, d);
+                wtop = o > wtop ? o : wtop;
+            }
+        }
+        if (lane == 0) { s_part[warp][jj - jlo] = wb; s_ptop[warp][jj - jlo] = wtop; }
+    }
+    __syncthreads();
+    if (tid < nqb) {
+        const int wlo = (tid * L) >> 5, whi = ((tid + 1) * L - 1) >> 5;
+        Cand r = none;
+        int64_t top = kKeyNone;
+        for (int w = wlo; w <= whi; w++) {
+            const int slot = tid - (w * 32) / L;
+            take(r, s_part[w][slot].key, s_part[w][slot].off);
+            top = s_ptop[w][slot] > top ? s_ptop[w][slot] : top;
+        }
+        s_best[tid] = r;
+        if (!fused_finish) {
+            TileRec rec;
+            rec.key = r.key; rec.offset = r.off;
+            rec.ub_key = top; rec.ub_offset = 0x7FFFFFFF;
+            rec.score = 0.0; rec.flags = 0; rec.pad = 0;
+            P.tiles[q0 + tid] = rec;                                // one tile per query: tile id == query id
+        }
+    }
+    if (!fused_finish) return;
+    __syncthreads();
+    for (int jj = warp; jj < nqb; jj += warps) finish_query_warp(T, P, q0 + jj, int64_t(q0 + jj) * len2, len2, s_best[jj]);
+}
+
+size_t packed_smem_bytes(int rank_bytes_per_word, int nwords, int steps, int Q)
+{
+    return size_t(kPlaneRows) * nwords * (8 + size_t(rank_bytes_per_word)) + size_t(Q) * (steps + 4) * 4;
 }
 
 // The bit-sliced epilogue applies when keys are small integers: exact mode, |multipliers| < 2^kSlicedMaxBits, rank
@@ -994,6 +1225,29 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
                          int64_t(0), SG.slice_len, 0);
         launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
         return;
+    }
+    if constexpr (NB <= 10) {
+        if (SG.pack_q > 0 && !batch) {
+            const int steps = int((G.uniform_len2 + 31) & ~31);
+            const int64_t noff = G.len1 - G.uniform_len2 + 1;
+            const int L = int((noff + 31) / 32);
+            const int nwords = round_up4(L + steps / 32 + 1);
+            const dim3 grid((G.nq + SG.pack_q - 1) / SG.pack_q), block(SG.pack_warps * 32);
+            if constexpr (K == 1) {
+                if (derive) {
+                    static bool done_dr[64];
+                    allow_big_smem(k_scan_packed<NB, K, BS, true>, done_dr);
+                    launch_dependent(k_scan_packed<NB, K, BS, true>, grid, block, packed_smem_bytes(0, nwords, steps, SG.pack_q), stream, T, G, P,
+                                     nwords, steps, SG.pack_q, L, key_planes, key_bias, SG.fused_finish ? 1 : 0);
+                    return;
+                }
+            }
+            static bool done[64];
+            allow_big_smem(k_scan_packed<NB, K, BS, false>, done);
+            launch_dependent(k_scan_packed<NB, K, BS, false>, grid, block, packed_smem_bytes(4 * K, nwords, steps, SG.pack_q), stream, T, G, P,
+                             nwords, steps, SG.pack_q, L, key_planes, key_bias, SG.fused_finish ? 1 : 0);
+            return;
+        }
     }
     if (batch) {
         const int warps = 4;
@@ -1082,6 +1336,17 @@ int64_t scan_plane_words(int64_t len1)
     // every window read stays inside the row: last tile start < len1 + 128, + tile + chunk + rounding
     const int64_t bits = len1 + 128 + kScanTile + kScanChunkMax + 256;
     return ((bits + 31) / 32 + 3) & ~int64_t(3);
+}
+
+bool scan_packed_fits(int64_t len1, int64_t len2)
+{
+    const int64_t noff = len1 - len2 + 1;
+    if (noff < 1 || len2 < 1 || len2 > 1023) return false;
+    const int64_t lanes = (noff + 31) / 32, steps = (len2 + 31) & ~int64_t(31);
+    const int64_t nwords = round_up4(int(lanes + steps / 32 + 1));
+    // worst case shared memory: 4 rank planes, 8 queries
+    const size_t smem = size_t(kPlaneRows) * nwords * (8 + 16) + size_t(kPackMaxQ) * (steps + 4) * 4;
+    return lanes <= 32 * kPackMaxWarps && nwords <= scan_plane_words(len1) && smem <= 160 * 1024;
 }
 
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,

@@ -360,6 +360,56 @@ def test_fused_finish_matches_separate_finish(ctx, port, synth):
         assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
 
 
+PACK_SHAPES = [(3000, 500, 96), (700, 300, 37), (2100, 1000, 11), (330, 64, 50), (1500, 1023, 9), (4200, 200, 7), (100, 90, 40),
+               (1055, 32, 5), (640, 129, 2), (2000, 1, 19)]
+
+
+@pytest.mark.parametrize("pack,planes,sliced", [(1, -1, 1), (2, -1, 1), (3, 0, 0), (8, 4, 1), (5, 1, 0), (2, 2, 1)])
+def test_packed_mode(ctx, port, pack, planes, sliced):
+    """Packed mode (k_scan_packed): equal-length queries that each fit one window share blocks lane by lane.  Every
+    forced packing factor, plane count and epilogue must give the oracle's answers, on random letters and on
+    low-entropy letters (many exact ties and offsets the tracked rank planes do not resolve)."""
+    rng = random.Random(1234 + pack)
+    used = 0
+    for len1, len2, nq in PACK_SHAPES:
+        for w, is_max in (([1, 3, 4, 2], True), ([1, 3, 4, 2], False), ([2, 1.5, 1.1, 1.3], True), ([1, 1, 1, 1], True), ([5, 1, 2, 3], False)):
+            alpha = rng.choice([ALPHA, ALPHA[:26], "ACDG", "AB", "A"])
+            s1 = "".join(rng.choice(alpha) for _ in range(len1))
+            qs = ["".join(rng.choice(alpha) for _ in range(len2)) for _ in range(nq)]
+            if len2 <= len1 // 2:
+                qs[nq // 2] = s1[len1 // 3: len1 // 3 + len2]            # one query that occurs verbatim
+            _set_engine(ctx, 2, planes=planes, batch=0, sliced=sliced)
+            ctx.set_option("pack_queries", pack)
+            try:
+                got = ctx.search_batch(w, is_max, s1, qs)
+                used += ctx.stat("packed_queries") > 0
+                if pack >= 2 and ((len1 - len2 + 1 + 31) // 32) * pack <= 256:
+                    assert ctx.stat("packed_queries") == pack, (len1, len2, nq)
+            finally:
+                ctx.set_option("pack_queries", 1)
+                _set_engine(ctx, 0)
+            exp = port.search_batch(w, is_max, s1, qs)
+            for k, (g, e) in enumerate(zip(got, exp)):
+                assert same_answer(g, e), (len1, len2, nq, w, is_max, alpha, k, g, e)
+                assert g.counts == e.counts
+    assert used > 0
+
+
+def test_packed_mode_is_chosen_for_config3_shape(ctx, port, synth):
+    """2501 offsets = 79 lanes per query: two queries per 5-warp block instead of 3 warps each; turning it off
+    changes nothing but the launch shape."""
+    wl = synth.workload("c3", nq=65)                                      # odd count: the last block holds one query
+    res = {}
+    for pack in (1, 0):
+        ctx.set_option("pack_queries", pack)
+        res[pack] = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+        assert (ctx.stat("packed_queries"), ctx.stat("packed_warps")) == ((2, 5) if pack else (0, 0))
+    ctx.set_option("pack_queries", 1)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    for a, b, e in zip(res[1], res[0], exp):
+        assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
+
+
 def test_reference_program_links_against_the_library(tmp_path, input_blocks):
     """The drop-in proof: the reference's OWN executable -- its unmodified main.c, cpu_funcs.c (file I/O,
     divide_execute_tasks, the call to gpu_run_program at cpu_funcs.c:180) and mpi_funcs.c, MPI stubbed to one rank --
