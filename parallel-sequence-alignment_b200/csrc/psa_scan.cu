@@ -31,6 +31,9 @@ namespace psa {
 namespace {
 
 constexpr int kProfileThreads = 64;      // few, fat threads: a 3000-letter Seq1 is only ~300 words
+// bytes between consecutive words' rows in a staged rank window: K = 1 keeps the class window's 8-byte pitch so the
+// per-step row offsets (row * nwords * 8) address both windows without a shift
+__host__ __device__ constexpr int rank_pitch(int K) { return K == 1 ? 8 : 4 * K; }
 constexpr int kScanChunkMax = 1024;     // alignment steps staged per shared-memory window
 
 // -------------------------------------------------------------------------------------------------
@@ -232,9 +235,9 @@ __device__ __forceinline__ void rank_group(uint32_t (&racc)[K > 0 ? K : 1], cons
             const int s = s4 + u;
             const uint32_t off = offs[u];                 // row * nwords * 8; rank entries are 4*K bytes wide
             if (K == 1) {
-                const uint32_t l = *reinterpret_cast<const uint32_t*>(pw + (off >> 1));
+                const uint32_t l = *reinterpret_cast<const uint32_t*>(pw + off);             // rows at the 8-byte pitch (rank_pitch)
                 uint32_t x = l;
-                if (s != 0) x = __funnelshift_r(l, *reinterpret_cast<const uint32_t*>(pw + (off >> 1) + 4), s);
+                if (s != 0) x = __funnelshift_r(l, *reinterpret_cast<const uint32_t*>(pw + off + 4), s);
                 racc[0] |= x;
             } else if (K == 2) {
                 const uint2 l = *reinterpret_cast<const uint2*>(pw + off);
@@ -567,7 +570,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
                 if (lane == 0) mbar_arrive_expect_tx(&s_bar, uint32_t(kPlaneRows) * uint32_t(need) * uint32_t(4 * K));
                 __syncwarp();
                 if (lane < kPlaneRows)
-                    tma_load_1d(smem + size_t(lane) * nwords * 4 * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
+                    tma_load_1d(smem + size_t(lane) * nwords * rank_pitch(K), P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
                                 uint32_t(need) * 4u * K, &s_bar);
             }
             fill_row_offsets(c0, cl);
@@ -848,7 +851,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_cls = smem;
     unsigned char* s_rnk = smem + size_t(kPlaneRows) * nwords * 8;
-    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + size_t(kPlaneRows) * nwords * 4 * K);
+    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + size_t(kPlaneRows) * nwords * rank_pitch(K));
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
@@ -868,18 +871,32 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         const int64_t g0 = tb >> 5;
         tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words + g0, uint32_t(nwords) * 8u, &s_bar);
         if (K > 0 && !DR)
-            tma_load_1d(s_rnk + size_t(lane) * nwords * 4 * K, P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
+            tma_load_1d(s_rnk + size_t(lane) * nwords * rank_pitch(K), P.rank_planes + (int64_t(lane) * P.plane_words + g0) * K,
                         uint32_t(nwords) * 4u * K, &s_bar);
     }
     bool staged = false;
 
     const int q_begin = blockIdx.x * queries_per_block;
     const int q_end = (q_begin + queries_per_block) < G.nq ? (q_begin + queries_per_block) : G.nq;
+    // The first 64 bytes of a warp's NEXT query are fetched while it works on the current one, so the global round
+    // trip of the row-offset set-up is off the critical path (most of a short query fits those two loads).
+    auto fetch_head = [&](int qq, uint8_t& h0, uint8_t& h1) {
+        h0 = h1 = uint8_t('A');
+        if (qq < q_end) {
+            const QueryGeom g = query_geom(G, P.qoff, P.tile_start, qq);
+            if (lane < g.len2) h0 = P.seq2s[g.qbeg + lane];
+            if (lane + 32 < g.len2) h1 = P.seq2s[g.qbeg + lane + 32];
+        }
+    };
+    uint8_t head0, head1;
+    fetch_head(q_begin + warp, head0, head1);
     for (int q = q_begin + warp; q < q_end; q += warps) {
         const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
         const int64_t qbeg = qg.qbeg;
         const int len2 = qg.len2;
         const int64_t last = G.len1 - len2 + 1;
+        const uint8_t cur0 = head0, cur1 = head1;
+        fetch_head(q + warps, head0, head1);
         if (tb >= last) continue;                                   // this query does not reach the tile
         const uint32_t vmask = valid_mask(ln0, 0, last);
         const int steps_total = (len2 + 31) & ~31;
@@ -889,7 +906,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
         for (int s = lane; s < steps_total; s += 32) {
             uint32_t row = kZeroRow;
             if (s < len2) {
-                row = symbol_of(P.seq2s[qbeg + s]);
+                row = symbol_of(s < 32 ? cur0 : s < 64 ? cur1 : P.seq2s[qbeg + s]);
                 if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
             }
             s_ro[s] = row * uint32_t(nwords) * 8u;
@@ -1010,7 +1027,7 @@ k_scan_packed(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_cls = smem;
     unsigned char* s_rnk = smem + size_t(kPlaneRows) * nwords * 8;
-    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + (kRankPass ? size_t(kPlaneRows) * nwords * 4 * K : 0));
+    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_rnk + (kRankPass ? size_t(kPlaneRows) * nwords * rank_pitch(K) : 0));
     const int ro_stride = steps + 4;            // + 16 bytes: the row-offset vectors of different queries fall into different banks
     __shared__ Cand s_part[kPackMaxWarps][kPackMaxQ];
     __shared__ int64_t s_ptop[kPackMaxWarps][kPackMaxQ];
@@ -1039,7 +1056,7 @@ k_scan_packed(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
     if (warp == 0 && lane < kPlaneRows) {
         tma_load_1d(s_cls + size_t(lane) * nwords * 8, P.cls_planes + int64_t(lane) * P.plane_words, uint32_t(nwords) * 8u, &s_bar);
         if (kRankPass)
-            tma_load_1d(s_rnk + size_t(lane) * nwords * 4 * K, P.rank_planes + int64_t(lane) * P.plane_words * K,
+            tma_load_1d(s_rnk + size_t(lane) * nwords * rank_pitch(K), P.rank_planes + int64_t(lane) * P.plane_words * K,
                         uint32_t(nwords) * 4u * K, &s_bar);
     }
     // per-step row offsets of the block's queries: their bytes are one contiguous run of nqb * len2 (equal lengths);
@@ -1178,7 +1195,7 @@ int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int nb, int64_t* b
 size_t batch_smem_bytes(int rank_planes, int chunk, int warps)
 {
     const size_t nwords = size_t(round_up4(32 + chunk / 32));
-    return size_t(kPlaneRows) * nwords * (8 + 4 * size_t(rank_planes)) + size_t(warps) * chunk * 4;
+    return size_t(kPlaneRows) * nwords * (8 + size_t(rank_pitch(rank_planes))) + size_t(warps) * chunk * 4;
 }
 
 // function attributes are per device and sticky: set them once per (kernel, device) instead of per launch
@@ -1244,7 +1261,7 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
             }
             static bool done[64];
             allow_big_smem(k_scan_packed<NB, K, BS, false>, done);
-            launch_dependent(k_scan_packed<NB, K, BS, false>, grid, block, packed_smem_bytes(4 * K, nwords, steps, SG.pack_q), stream, T, G, P,
+            launch_dependent(k_scan_packed<NB, K, BS, false>, grid, block, packed_smem_bytes(rank_pitch(K), nwords, steps, SG.pack_q), stream, T, G, P,
                              nwords, steps, SG.pack_q, L, key_planes, key_bias, SG.fused_finish ? 1 : 0);
             return;
         }
