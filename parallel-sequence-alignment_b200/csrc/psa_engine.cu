@@ -58,7 +58,9 @@ struct DeviceState {
     BatchGeom G{};
     BatchPtrs P{};
     bool active = false;
-    long long st_launches = 0, st_cand = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
+    long long st_launches = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
+    int32_t* h_err = nullptr;  // mapped page-locked word the kernels write the run's tag into on a bad symbol (no copy, no memset)
+    int32_t run_tag = 0;
     float run_ms = 0.f;
 };
 
@@ -167,6 +169,7 @@ void release(DeviceState& d)
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
+    if (d.h_err) cudaFreeHost(d.h_err);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.evk0) cudaEventDestroy(d.evk0);
@@ -238,7 +241,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     const bool scan = ctx->engine == 2;
     const int tile = scan ? ctx->scan_tile : kExactTile;
     int rc;
-    if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq + 16))) return rc;     // + the 4 flag words, one copy back
+    if ((rc = ensure_pin(ctx, d.h_out, sizeof(QueryRec) * nq + 16))) return rc;
     const int64_t byte0 = q_off[q_begin];
     const int64_t seq2_bytes = q_off[q_end] - byte0;
     const bool uniform_len = ctx->uniform_len2 > 0;       // every query of the batch has the same length
@@ -367,21 +370,30 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.code_table = (uint8_t*)d.code_table.p;
     d.P.partial = (uint2*)d.partial.p;
     d.P.partial_stride = int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
-    d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // flags sit behind the records
-    d.P.err_flag = d.P.cand_count + 1;
+    d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // the counter sits behind the records
+    d.P.err_flag = d.h_err;                                                  // unified addressing: the host pointer is the device pointer
     d.P.cls_planes = (uint2*)d.cls_planes.p;
     d.P.rank_planes = (uint32_t*)d.rank_planes.p;
     d.P.plane_words = plane_words;
     return PSA_OK;
 }
 
+// A fresh tag per run: a kernel that meets a bad symbol stores the tag in the mapped word, the host compares after the
+// stream has drained.  Nothing to clear between runs, nothing to copy back.
+static int32_t next_run_tag(DeviceState& d)
+{
+    if (d.run_tag >= 0x7FFFFFF0) { d.run_tag = 0; *(volatile int32_t*)d.h_err = 0; }      // no run is in flight here
+    return ++d.run_tag;
+}
+static bool bad_symbol_seen(const DeviceState& d) { return *(volatile const int32_t*)d.h_err == d.run_tag; }
+
 int run_device(psa_context* ctx, DeviceState& d, bool timed)
 {
-    d.st_launches = d.st_cand = d.st_tiles = d.st_main_ns = 0;
+    d.st_launches = d.st_tiles = d.st_main_ns = 0;
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
-    PSA_CUDA(ctx, cudaMemsetAsync(d.P.cand_count, 0, sizeof(int32_t) * 4, d.stream));
+    d.P.run_tag = next_run_tag(d);
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
@@ -471,13 +483,15 @@ int psa_create(psa_context** out, const int* devices, int ndevices)
             cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.dev) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
-            cudaEventCreate(&d.evk0) != cudaSuccess || cudaEventCreate(&d.evk1) != cudaSuccess) {
+            cudaEventCreate(&d.evk0) != cudaSuccess || cudaEventCreate(&d.evk1) != cudaSuccess ||
+            cudaHostAlloc((void**)&d.h_err, 64, cudaHostAllocMapped) != cudaSuccess) {
             cudaGetLastError();
             for (DeviceState& x : ctx->devs) release(x);
             delete ctx;
             return PSA_ERR_CUDA;     // the kernels are sm_100a only: no other device can run them
         }
     }
+    for (DeviceState& d : ctx->devs) std::memset(d.h_err, 0, 64);
     for (int i = 1; i < ndevices; i++) {
         ctx->workers.emplace_back(new Worker());
         Worker* w = ctx->workers.back().get();
@@ -524,13 +538,24 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
 long long psa_get_stat(const psa_context* ctx, const char* name)
 {
     if (!ctx || !name) return -1;
-    long long launches = 0, cand = 0, tiles = 0, main_ns = 0;
+    long long launches = 0, tiles = 0, main_ns = 0;
     for (const DeviceState& d : ctx->devs) {
-        launches += d.st_launches; cand += d.st_cand; tiles += d.st_tiles;
+        launches += d.st_launches; tiles += d.st_tiles;
         main_ns = std::max(main_ns, d.st_main_ns);
     }
     if (!std::strcmp(name, "kernel_launches")) return launches;
-    if (!std::strcmp(name, "candidate_tiles")) return cand;
+    if (!std::strcmp(name, "candidate_tiles")) {
+        // a statistic nobody waits for: the counter stays on the device and is read only when asked
+        long long cand = 0;
+        for (const DeviceState& d : ctx->devs) {
+            if (!d.active || !ctx->ran || !d.P.cand_count) continue;
+            int32_t v = 0;
+            if (cudaSetDevice(d.dev) != cudaSuccess || cudaStreamSynchronize(d.stream) != cudaSuccess ||
+                cudaMemcpy(&v, d.P.cand_count, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+            cand += v;
+        }
+        return cand;
+    }
     if (!std::strcmp(name, "tiles")) return tiles;
     if (!std::strcmp(name, "main_kernel_ns")) return main_ns;           // dominant kernel of the last psa_batch_run
     if (!std::strcmp(name, "engine")) return ctx->engine;
@@ -710,14 +735,8 @@ static int fetch_shard(psa_context* ctx, DeviceState& d, psa_result* out, bool d
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     const size_t bytes = sizeof(QueryRec) * d.G.nq;
-    if (direct) {
-        PSA_CUDA(ctx, cudaMemcpyAsync(out + d.q_begin, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
-        PSA_CUDA(ctx, cudaMemcpyAsync((char*)d.h_out.p + bytes, (const char*)d.out.p + bytes, 16, cudaMemcpyDeviceToHost, d.stream));
-    } else {
-        PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, bytes + 16, cudaMemcpyDeviceToHost, d.stream));
-    }
+    PSA_CUDA(ctx, cudaMemcpyAsync(direct ? (void*)(out + d.q_begin) : d.h_out.p, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
     PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    d.st_cand = ((const int32_t*)((const char*)d.h_out.p + bytes))[0];
     if (!direct && ctx->nq > 1) std::memcpy(out + d.q_begin, d.h_out.p, bytes);
     return PSA_OK;
 }
@@ -726,8 +745,7 @@ static int fetch_shard(psa_context* ctx, DeviceState& d, psa_result* out, bool d
 static int finish_fetch(psa_context* ctx, psa_result* out)
 {
     for (DeviceState& d : ctx->devs)
-        if (d.active && ((const int32_t*)((const char*)d.h_out.p + sizeof(QueryRec) * d.G.nq))[1])
-            return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
+        if (d.active && bad_symbol_seen(d)) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
     if (ctx->nq == 1) {
         // per-GPU candidates of the single query in ascending offset order
         std::vector<psa_result> parts;
@@ -873,18 +891,16 @@ int psa_offset_scores(psa_context* ctx, const double weights[4], int is_max, con
     G.len1 = len1; G.first = first; G.last = last; G.nq = 1; G.uniform_len2 = (int32_t)len2;
     BatchPtrs P{};
     P.seq1 = (const uint8_t*)d.seq1.p; P.seq2s = (const uint8_t*)d.seq2s.p;
-    P.cand_count = (int32_t*)d.out.p; P.err_flag = P.cand_count + 1;
+    P.cand_count = (int32_t*)d.out.p; P.err_flag = d.h_err; P.run_tag = next_run_tag(d);
     PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
     PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2, (size_t)len2, cudaMemcpyHostToDevice, d.stream));
-    PSA_CUDA(ctx, cudaMemsetAsync(d.out.p, 0, 16, d.stream));
     launch_offset_profile(T, G, P, d_scores, d_coff, d_let, d.stream);
     PSA_CUDA(ctx, cudaGetLastError());
     PSA_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
     if (char_offsets) PSA_CUDA(ctx, cudaMemcpyAsync(char_offsets, d_coff, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
     if (letters) PSA_CUDA(ctx, cudaMemcpyAsync(letters, d_let, (size_t)n, cudaMemcpyDeviceToHost, d.stream));
-    PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d.out.p, 16, cudaMemcpyDeviceToHost, d.stream));
     PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    if (((const int32_t*)d.h_out.p)[1]) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
+    if (bad_symbol_seen(d)) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
     return PSA_OK;
 }
 

@@ -48,8 +48,10 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
         s_tab[k] = e;
     }
     if (tid < 4) s_w[tid] = T.wcls[tid];
-    if (blockIdx.x == 0)            // the finish kernel reads the pair table from global memory
+    if (blockIdx.x == 0) {          // the finish kernel reads the pair table from global memory
         for (int k = tid; k < kSymbols * kRowPad; k += kExactThreads) P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
+        if (tid == 0) *P.cand_count = 0;                            // first kernel of the chain: only k_finish adds to it
+    }
     __syncthreads();
 
     for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {
@@ -76,7 +78,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
                 __syncthreads();
                 for (int k = tid; k < cl; k += kExactThreads) {
                     uint32_t s = symbol_of(P.seq2s[qbeg + c0 + k]);
-                    if (s == 0xFFu) { atomicOr(P.err_flag, 1); s = 0; }
+                    if (s == 0xFFu) { report_bad_symbol(P); s = 0; }
                     s_q[k] = uint8_t(s);
                 }
                 for (int k = tid; k < kExactThreads + cl - 1; k += kExactThreads) {
@@ -84,7 +86,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
                     uint32_t s = 0;
                     if (p < G.len1) {
                         s = symbol_of(P.seq1[p]);
-                        if (s == 0xFFu) { atomicOr(P.err_flag, 1); s = 0; }
+                        if (s == 0xFFu) { report_bad_symbol(P); s = 0; }
                     }
                     s_win[k] = uint8_t(s);
                 }
@@ -169,7 +171,7 @@ k_offset_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const
         __syncthreads();
         for (int k = tid; k < cl; k += kExactThreads) {
             uint32_t c = symbol_of(P.seq2s[c0 + k]);
-            if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
+            if (c == 0xFFu) { report_bad_symbol(P); c = 0; }
             s_q[k] = uint8_t(c);
         }
         for (int k = tid; k < kExactThreads + cl - 1; k += kExactThreads) {
@@ -177,7 +179,7 @@ k_offset_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const
             uint32_t c = 0;
             if (p < G.len1) {
                 c = symbol_of(P.seq1[p]);
-                if (c == 0xFFu) { atomicOr(P.err_flag, 1); c = 0; }
+                if (c == 0xFFu) { report_bad_symbol(P); c = 0; }
             }
             s_win[k] = uint8_t(c);
         }

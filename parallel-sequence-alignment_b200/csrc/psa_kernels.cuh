@@ -17,14 +17,22 @@ struct BatchPtrs {
     uint8_t*       code_table;  // [27][32] copy of DeviceTable::code in global memory (written by k_profile / k_exact_tiles)
     uint2*         partial;     // slice mode: [slice][offset] partial counts {N(b0) | N(b1) << 16, N(b0&b1) | rank bits << 16}
     int64_t        partial_stride;   // offsets per slice row of `partial`
-    int32_t*       cand_count;  // [0] = number of 32-offset words re-scored in reference order (statistic)
-    int32_t*       err_flag;    // bit0: symbol outside [A-Z-]
+    int32_t*       cand_count;  // [0] = number of 32-offset words re-scored in reference order (statistic; zeroed by the first kernel)
+    int32_t*       err_flag;    // mapped host word: set to run_tag by any thread that meets a symbol outside [A-Z-]
+    int32_t        run_tag;     //   (a fresh tag per run: the word never needs clearing and is read without a copy)
     // bit-plane profile of Seq1 (scan engine): [row][word] of 64-bit (class planes) and
     // [row][word][rank_planes] of 32-bit words; rows = 28 (27 symbols + zero row)
     uint2*         cls_planes;
     uint32_t*      rank_planes;
     int64_t        plane_words; // words per row
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void report_bad_symbol(const BatchPtrs& P)
+{
+    *reinterpret_cast<volatile int32_t*>(P.err_flag) = P.run_tag;
+}
+#endif
 
 // Offsets of a query are tiled from `base` = first rounded down to a multiple of 128 so that bit-plane
 // rows line up on 16 bytes (TMA bulk copies); a tile covers [base + t*tile, base + (t+1)*tile) intersected

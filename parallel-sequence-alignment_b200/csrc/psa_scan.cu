@@ -48,9 +48,11 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 {
     __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
     pdl_launch_dependents();                                        // the scan may set itself up while we run
-    if (blockIdx.x == 0)            // the pair table for the kernels after us: divergent reads of a kernel parameter are
+    if (blockIdx.x == 0) {          // the pair table for the kernels after us: divergent reads of a kernel parameter are
         for (int k = threadIdx.x; k < kSymbols * kRowPad; k += kProfileThreads)       // slow, a global copy is not
             P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
+        if (threadIdx.x == 0) *P.cand_count = 0;                    // first kernel of the chain: only k_finish adds to it
+    }
     if (threadIdx.x < 32) {
         const int c = threadIdx.x;
         uint32_t b0 = 0, b1 = 0, rk[K > 0 ? K : 1] = {};
@@ -84,7 +86,7 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 #pragma unroll
             for (int t = 0; t < 32; t++) {
                 uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
-                if (t < n && c == 0xFFu) atomicOr(P.err_flag, 1);
+                if (t < n && c == 0xFFu) report_bad_symbol(P);
                 sym[t] = uint8_t(c == 0xFFu ? 0u : c);
             }
         }
@@ -554,7 +556,7 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 
     // Seq2 slice -> per-step row offsets (row * nwords * 8 bytes); padding steps use the all-zero row
     auto fill_row_offsets = [&](int c0, int cl) {
-        if (fill_rows<8>(s_ro, P.seq2s + qbeg, c0, cl, len2, uint32_t(nwords) * 8u, tid, nthreads)) atomicOr(P.err_flag, 1);
+        if (fill_rows<8>(s_ro, P.seq2s + qbeg, c0, cl, len2, uint32_t(nwords) * 8u, tid, nthreads)) report_bad_symbol(P);
     };
 
     // ---- pass R: best rank per offset -----------------------------------------------------------------
@@ -907,7 +909,7 @@ k_scan_batch(const __grid_constant__ DeviceTable T, const BatchGeom G, const Bat
             uint32_t row = kZeroRow;
             if (s < len2) {
                 row = symbol_of(s < 32 ? cur0 : s < 64 ? cur1 : P.seq2s[qbeg + s]);
-                if (row == 0xFFu) { atomicOr(P.err_flag, 1); row = 0; }
+                if (row == 0xFFu) { report_bad_symbol(P); row = 0; }
             }
             s_ro[s] = row * uint32_t(nwords) * 8u;
         }
@@ -1085,7 +1087,7 @@ k_scan_packed(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
             const int jj = e / pad, st = len2 + (e - jj * pad);
             s_ro_all[jj * ro_stride + st] = uint32_t(kZeroRow) * uint32_t(nwords) * 8u;
         }
-        if (bad) atomicOr(P.err_flag, 1);
+        if (bad) report_bad_symbol(P);
     }
     __syncthreads();
     mbar_wait(&s_bar, 0);
