@@ -99,6 +99,8 @@ const char* psa_last_error(const psa_context* ctx);
      "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
      "pack_queries"  1 auto: equal-length queries that fit one window share blocks lane by lane when whole warps per
                      query would idle | 0 never | 2..8 force that many queries per block
+     "zero_copy_results" 1 result sets up to 128 KB are stored by the kernels straight into page-locked host memory (the
+                     caller's array if it is page-locked, else the context's staging buffer) | 0 always copy back
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference

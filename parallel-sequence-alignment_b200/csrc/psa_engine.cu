@@ -61,6 +61,8 @@ struct DeviceState {
     long long st_launches = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
     int32_t* h_err = nullptr;  // mapped page-locked word the kernels write the run's tag into on a bad symbol (no copy, no memset)
     int32_t run_tag = 0;
+    bool zc_out = false;       // this run's records are written over the bus by the kernels themselves (no device-to-host copy)
+    bool zc_direct = false;    //   ... into the caller's page-locked array (else into h_out)
     float run_ms = 0.f;
 };
 
@@ -90,6 +92,8 @@ struct psa_context {
     int opt_fused_finish = 1;  // 0: always run k_finish as its own kernel
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_pack_queries = 1;  // 0 never pack | 1 auto | 2..8 force that many queries per block (tests)
+    int opt_zero_copy = 1;     // 1: small result sets are written by the kernels straight into page-locked host memory
+    bool one_shot = false;     // the batch being prepared belongs to a prepare + run + fetch call (psa_search_batch / _range)
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
@@ -365,7 +369,13 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.qoff = (const int64_t*)d.qoff.p;
     d.P.tile_start = (const int32_t*)d.tile_start.p;
     d.P.tiles = (TileRec*)d.tiles.p;
-    d.P.out = (QueryRec*)d.out.p;
+    // Small result sets: the finishing threads store their 56-byte records straight into page-locked host memory, which
+    // takes the device-to-host copy (an extra stream operation, ~4 us) off the end of the chain.  Large ones (config 5:
+    // 3.7 MB) stay on the copy engine -- one DMA beats half a million 8-byte posted writes.
+    // Only the one-shot calls do this: the split-phase form keeps its results resident until psa_batch_fetch.
+    d.zc_out = ctx->one_shot && ctx->opt_zero_copy != 0 && sizeof(QueryRec) * (size_t)nq <= kZeroCopyMaxBytes;
+    d.zc_direct = false;
+    d.P.out = d.zc_out ? (QueryRec*)d.h_out.p : (QueryRec*)d.out.p;
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
     d.P.code_table = (uint8_t*)d.code_table.p;
     d.P.partial = (uint2*)d.partial.p;
@@ -527,6 +537,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "fused_finish") && value >= 0 && value <= 1) { ctx->opt_fused_finish = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "derive_rank") && value >= 0 && value <= 1) { ctx->opt_derive_rank = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "pack_queries") && value >= 0 && value <= kPackMaxQ) { ctx->opt_pack_queries = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "zero_copy_results") && value >= 0 && value <= 1) { ctx->opt_zero_copy = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
@@ -735,6 +746,11 @@ static int fetch_shard(psa_context* ctx, DeviceState& d, psa_result* out, bool d
     if (!d.active) return PSA_OK;
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     const size_t bytes = sizeof(QueryRec) * d.G.nq;
+    if (d.zc_out) {
+        PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        if (!d.zc_direct && ctx->nq > 1) std::memcpy(out + d.q_begin, d.h_out.p, bytes);
+        return PSA_OK;
+    }
     PSA_CUDA(ctx, cudaMemcpyAsync(direct ? (void*)(out + d.q_begin) : d.h_out.p, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
     PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
     if (!direct && ctx->nq > 1) std::memcpy(out + d.q_begin, d.h_out.p, bytes);
@@ -771,6 +787,15 @@ static bool result_array_is_pinned(const psa_context* ctx, const psa_result* out
     return false;
 }
 
+// the address kernels can use to write a page-locked host array in place, or null
+static void* device_view_of(const void* host)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost) return attr.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
+
 int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
                       const char* seq2s, const int64_t* q_off, int32_t nq)
 {
@@ -778,6 +803,7 @@ int psa_batch_prepare(psa_context* ctx, const double weights[4], int is_max, con
     if (rc) return rc;
     if (nq == 0) return PSA_OK;
     // the split-phase form promises a resident batch: wait for the copies here
+    ctx->one_shot = false;
     return for_each_device(ctx, [ctx](DeviceState& d) {
         int r = prepare_shard(ctx, d);
         if (r || !d.active) return r;
@@ -826,10 +852,21 @@ static int search_prepared(psa_context* ctx, psa_result* out)
     if (ctx->nq == 0) return PSA_OK;
     if (!out) return fail(ctx, PSA_ERR_ARG, "null result buffer");
     const bool direct = result_array_is_pinned(ctx, out);
+    ctx->one_shot = true;
     int rc = for_each_device(ctx, [ctx, out, direct](DeviceState& d) {
         int r = prepare_shard(ctx, d);
+        if (!r && d.active && d.zc_out && direct) {                 // the caller's array is page-locked: write it in place
+            if (void* dv = device_view_of(out + d.q_begin)) {
+                d.P.out = static_cast<QueryRec*>(dv);
+                d.zc_direct = true;
+            }
+        }
         if (!r) r = run_device(ctx, d, false);
         if (!r) r = fetch_shard(ctx, d, out, direct);
+        if (d.zc_direct) {                                          // the caller's array is theirs again: a later
+            d.P.out = (QueryRec*)d.h_out.p;                         // psa_batch_run on this batch writes the staging buffer
+            d.zc_direct = false;
+        }
         return r;
     });
     ctx->ran = rc == PSA_OK;

@@ -52,6 +52,7 @@ struct SliceGeom {
     int pack_warps = 0;         //   and warps per block = ceil(pack_q * lanes per query / 32)
 };
 constexpr int kCombineTile = 256;   // offsets per tile record in slice mode
+constexpr size_t kZeroCopyMaxBytes = 128 * 1024;   // result sets up to this size are written straight into host memory
 constexpr int kPackMaxQ = 8;        // packed mode: queries per block
 constexpr int kPackMaxWarps = 8;    //   and warps per block
 // packed mode: does one window hold every offset of a (len1, len2) query, inside the plane buffer?

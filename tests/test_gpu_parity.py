@@ -410,6 +410,30 @@ def test_packed_mode_is_chosen_for_config3_shape(ctx, port, synth):
         assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
 
 
+def test_zero_copy_results_match_copied_results(psa, ctx, port, synth):
+    """Small result sets are written by the kernels straight into page-locked host memory (the caller's array when it
+    is page-locked, the context's staging buffer otherwise); the copy-engine path must give the same records."""
+    import ctypes as C
+    wl = synth.workload("c3", nq=200)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    batch = psa.Batch(wl.seq1, wl.queries, pinned=True)
+    w = (C.c_double * 4)(*wl.weights)
+    for zc in (1, 0):
+        ctx.set_option("zero_copy_results", zc)
+        for pinned in (True, False):
+            out = ctx.new_result_array(batch.nq, pinned=pinned)
+            ctx.search_batch_raw(w, wl.is_max, batch, out)
+            for k, e in enumerate(exp):
+                assert same_answer(ctx.result_from_array(out, k), e), (zc, pinned, k)
+        # single query (staged for the merge) and a bad symbol (flag path) on both settings
+        r = ctx.search(wl.weights, wl.is_max, wl.seq1, wl.queries[3])
+        assert same_answer(r, exp[3])
+        with pytest.raises(psa.PsaError):
+            ctx.search_batch(wl.weights, wl.is_max, wl.seq1, [wl.queries[0], b"AB?D"])
+        assert same_answer(ctx.search(wl.weights, wl.is_max, wl.seq1, wl.queries[5]), exp[5])      # and it recovers
+    ctx.set_option("zero_copy_results", 1)
+
+
 def test_reference_program_links_against_the_library(tmp_path, input_blocks):
     """The drop-in proof: the reference's OWN executable -- its unmodified main.c, cpu_funcs.c (file I/O,
     divide_execute_tasks, the call to gpu_run_program at cpu_funcs.c:180) and mpi_funcs.c, MPI stubbed to one rank --
