@@ -11,6 +11,7 @@ constexpr int kZeroRow   = 27;   // bit-plane row of zeros used to pad Seq2 to a
 constexpr int kPlaneRows = 28;
 constexpr int kMaxRanks  = 15;   // rank field is 4 bits; 0 = "no substitute"
 constexpr uint8_t kBadSymbol = 0xFF;
+constexpr int kPlaneKinds = 6;   // bit-plane kinds k_profile can build: class bit 0, class bit 1, up to 4 rank planes
 
 // Packed per-pair payload, code[c2][c1]:
 //   bits 0-1  sign class   0 '*'  1 ':'  2 '.'  3 '_'
@@ -30,6 +31,7 @@ struct DeviceTable {
     int32_t is_max;
     int32_t exact;
     int32_t has_none;                 // some pair has no substitute (never observed; handled anyway)
+    uint32_t col[kPlaneKinds][kRowPad];   // k_profile's columns: [plane kind][Seq1 symbol], bit r = row symbol r
     int32_t top_rank_lut;             // >= 0: "pair carries the best rank" is a function of its sign class alone (bit c = class c);
                                       // -1: it is not (then the scan reads it from a rank bit plane)
 };

@@ -61,6 +61,7 @@ struct DeviceState {
     long long st_launches = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
     int32_t* h_err = nullptr;  // mapped page-locked word the kernels write the run's tag into on a bad symbol (no copy, no memset)
     int32_t run_tag = 0;
+    long long table_epoch = -1;   // ctx->table_epoch whose pair table is in code_table
     bool zc_out = false;       // this run's records are written over the bus by the kernels themselves (no device-to-host copy)
     bool zc_direct = false;    //   ... into the caller's page-locked array (else into h_out)
     float run_ms = 0.f;
@@ -93,6 +94,7 @@ struct psa_context {
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_pack_queries = 1;  // 0 never pack | 1 auto | 2..8 force that many queries per block (tests)
     int opt_zero_copy = 1;     // 1: small result sets are written by the kernels straight into page-locked host memory
+    long long table_epoch = 0; // bumped whenever `table` is rebuilt
     bool one_shot = false;     // the batch being prepared belongs to a prepare + run + fetch call (psa_search_batch / _range)
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
@@ -332,6 +334,12 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
+    if (d.table_epoch != ctx->table_epoch) {
+        // the pair table in global memory for the kernels that index it per thread (divergent reads of a kernel
+        // parameter are slow); uploaded when the table changes, not per batch
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.code_table.p, ctx->table.code, kSymbols * kRowPad, cudaMemcpyHostToDevice, d.stream));
+        d.table_epoch = ctx->table_epoch;
+    }
     if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
     if ((rc = ensure_dev(ctx, d.seq2s, (size_t)seq2_bytes + 64))) return rc;
     if (!uniform_len) {
@@ -679,6 +687,7 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
         rc = build_tables(weights, is_max, std::max<int64_t>(max_len2, 1), nullptr, &ctx->table);
         if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
         std::memcpy(ctx->weights, weights, sizeof(ctx->weights));
+        ctx->table_epoch++;
         ctx->is_max = is_max ? 1 : 0;
         ctx->table_len2 = max_len2;
         ctx->table_valid = true;

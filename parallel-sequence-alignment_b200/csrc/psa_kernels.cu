@@ -48,10 +48,7 @@ k_exact_tiles(const __grid_constant__ DeviceTable T, const BatchGeom G, const Ba
         s_tab[k] = e;
     }
     if (tid < 4) s_w[tid] = T.wcls[tid];
-    if (blockIdx.x == 0) {          // the finish kernel reads the pair table from global memory
-        for (int k = tid; k < kSymbols * kRowPad; k += kExactThreads) P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
-        if (tid == 0) *P.cand_count = 0;                            // first kernel of the chain: only k_finish adds to it
-    }
+    if (blockIdx.x == 0 && tid == 0) *P.cand_count = 0;             // first kernel of the chain: only k_finish adds to it
     __syncthreads();
 
     for (int tile_id = blockIdx.x; tile_id < G.total_tiles; tile_id += gridDim.x) {

@@ -14,7 +14,7 @@ struct BatchPtrs {
     TileRec*       tiles;       // total_tiles records
     QueryRec*      out;         // nq records
     int64_t*       lane_keys;   // scan engine, re-score mode: per (tile, 32-offset word) upper estimate of its keys
-    uint8_t*       code_table;  // [27][32] copy of DeviceTable::code in global memory (written by k_profile / k_exact_tiles)
+    uint8_t*       code_table;  // [27][32] copy of DeviceTable::code in global memory (uploaded when the table changes)
     uint2*         partial;     // slice mode: [slice][offset] partial counts {N(b0) | N(b1) << 16, N(b0&b1) | rank bits << 16}
     int64_t        partial_stride;   // offsets per slice row of `partial`
     int32_t*       cand_count;  // [0] = number of 32-offset words re-scored in reference order (statistic; zeroed by the first kernel)

@@ -48,29 +48,9 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 {
     __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
     pdl_launch_dependents();                                        // the scan may set itself up while we run
-    if (blockIdx.x == 0) {          // the pair table for the kernels after us: divergent reads of a kernel parameter are
-        for (int k = threadIdx.x; k < kSymbols * kRowPad; k += kProfileThreads)       // slow, a global copy is not
-            P.code_table[k] = T.code[k / kRowPad][k % kRowPad];
-        if (threadIdx.x == 0) *P.cand_count = 0;                    // first kernel of the chain: only k_finish adds to it
-    }
-    if (threadIdx.x < 32) {
-        const int c = threadIdx.x;
-        uint32_t b0 = 0, b1 = 0, rk[K > 0 ? K : 1] = {};
-        if (c < kSymbols) {
-            for (int r = 0; r < kSymbols; r++) {
-                const uint32_t code = T.code[r][c];
-                b0 |= (code & 1u) << r;
-                b1 |= ((code >> 1) & 1u) << r;
-                const int rank = int(code >> 2);
-#pragma unroll
-                for (int k = 0; k < K; k++) rk[k] |= uint32_t(rank != 0 && rank == T.nranks - k) << r;
-            }
-        }
-        s_col[0][c] = b0;
-        s_col[1][c] = b1;
-#pragma unroll
-        for (int k = 0; k < K; k++) s_col[2 + k][c] = rk[k];
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *P.cand_count = 0;     // first kernel of the chain: only k_finish adds to it
+    for (int k = threadIdx.x; k < (2 + K) * 32; k += kProfileThreads)       // columns resolved on the host (psa_table.cpp)
+        s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
     __syncthreads();
     for (int64_t w = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; w < P.plane_words;
          w += int64_t(gridDim.x) * kProfileThreads) {

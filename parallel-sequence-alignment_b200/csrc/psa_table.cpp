@@ -233,6 +233,19 @@ int build_tables(const double* w, int is_max, long long max_len2, psa_pair_table
                 }
             dev->top_rank_lut = (yes & no) == 0 ? yes : -1;
         }
+        // Bit-plane columns for k_profile: per plane kind and Seq1 symbol, bit r = what row symbol r gets at a position
+        // holding that Seq1 symbol (class bit 0, class bit 1, "rank == nranks - k").
+        for (int c1 = 0; c1 < kRowPad; c1++)
+            for (int kind = 0; kind < kPlaneKinds; kind++) dev->col[kind][c1] = 0;
+        for (int c1 = 0; c1 < kSymbols; c1++)
+            for (int r = 0; r < kSymbols; r++) {
+                const uint32_t code = dev->code[r][c1];
+                dev->col[0][c1] |= (code & 1u) << r;
+                dev->col[1][c1] |= ((code >> 1) & 1u) << r;
+                const int rank = int(code >> 2);
+                for (int k = 0; k < kPlaneKinds - 2; k++)
+                    dev->col[2 + k][c1] |= uint32_t(rank != 0 && rank == t.nranks - k) << r;
+            }
     }
     return PSA_OK;
 }
