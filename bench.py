@@ -61,7 +61,7 @@ def profiled_traffic(workload: str, kernel: str):
         return None, None
     rec = json.load(open(p)).get(workload, {})
     for name, v in rec.items():
-        if name.startswith(kernel):
+        if name == kernel or name.startswith(kernel + "<"):
             return v.get("dram_bytes_per_launch"), v
     return None, None
 
@@ -389,7 +389,7 @@ def run_ours(args, synth, rank, local_rank, world):
         peak = SM_COUNT * 128 * clk / LANE_OPS_PER_PAIR_EVAL
         alg_bytes = batch.len1 + sum(batch.lens) + batch.nq * HBM_BYTES_PER_QUERY_FIXED
         engine = ctx.stat("engine")
-        kname = ("k_scan_batch" if ctx.stat("batch_mode") else "k_scan") if engine == 2 else "k_exact_tiles"
+        kname = ("k_scan_batch" if ctx.stat("batch_mode") else "k_scan_packed" if ctx.stat("packed_queries") > 0 else "k_scan") if engine == 2 else "k_exact_tiles"
         traffic, prof = profiled_traffic(args.workload, kname)
         # the scan kernel's own bound: its inner loop issues ALU_OPS_PER_WARP_STEP integer-ALU instructions (LOP3/SHF,
         # 64 lanes/clk/SM) per warp per alignment step, and a warp step covers 1024 pair-evals (profiles/)
@@ -403,7 +403,9 @@ def run_ours(args, synth, rank, local_rank, world):
                        "exact_integer_keys": bool(ctx.stat("exact")), "rank_planes": ctx.stat("rank_planes"),
                        "scan_warps": ctx.stat("scan_warps"), "packed_queries_per_block": ctx.stat("packed_queries"), "rescored_words": ctx.stat("candidate_tiles"), "sharding": "one full batch per rank, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes,
-                    "d2h_bytes_per_step": 56 * batch.nq + 16, "ms_per_step": 1e3 * e2e_s_max / args.steps},
+                    "d2h_bytes_per_step": 56 * batch.nq, "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "d2h_path": "result records stored by the finishing threads straight into the caller's page-locked array" if 56 * batch.nq <= 128 * 1024
+                                else "one device-to-host copy into the caller's page-locked array"},
             "gpu_launches": launches,
             "roofline": {"bound": "int-alu-issue", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
                          "traffic": traffic,
