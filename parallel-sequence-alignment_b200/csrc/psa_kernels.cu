@@ -226,8 +226,9 @@ constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kFinishChunk = 1024;
 constexpr int kFinishList = 32;       // candidate tiles remembered per query before falling back to a full walk
 
+// (block per query: min blocks = 1, so ptxas may spend registers on keeping the re-score loop's loads well ahead of its add chain)
 template <int WPQ>
-__global__ void __launch_bounds__(kFinishThreads)
+__global__ void __launch_bounds__(kFinishThreads, WPQ == 1 ? 4 : 1)
 k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int scan_records)
 {
     constexpr int kGroup = WPQ * 32;                                    // threads working on one query
@@ -240,6 +241,7 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     __shared__ int s_nlist[kFinishWarps];
     __shared__ uint16_t s_q[kFinishWarps][kFinishChunk];               // Seq2 symbol * kRowPad
     __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
+    __shared__ double s_wtab[kSymbols * kRowPad];                       // pair weight by (Seq2 symbol * kRowPad + Seq1 symbol)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 4) s_w[tid] = T.wcls[tid];
     if (tid == 0) s_pos = 0ull;
@@ -247,6 +249,8 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     pdl_wait();                                                         // tile records and the pair table come from the kernels before us
     for (int k = tid; k < kSymbols * kRowPad / 4; k += kFinishThreads)
         reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(P.code_table)[k];
+    if (!T.exact)
+        for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_wtab[k] = T.wcls[P.code_table[k] & 3u];
     __syncthreads();
     const int q = WPQ == 1 ? blockIdx.x * kFinishWarps + warp : blockIdx.x;
     if (q >= G.nq) return;
@@ -331,11 +335,33 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
                         }
                         __syncwarp();
                         const uint8_t* wv = &s_win[warp][lane];
-#pragma unroll 8
-                        for (int i = 0; i < cl; i++) {
-                            const uint32_t code = s_code[uint32_t(s_q[warp][i]) + wv[i]];
-                            total += s_w[code & 3u];
-                            best_rank = max(best_rank, code >> 2);
+                        // The sum must be the reference's: one rounding per step, in step order -- a chain of dependent
+                        // double adds run by one warp, with nothing to hide latency behind.  Measured on B200
+                        // (tools/probes/dadd_probe.cu): 8 cycles per step when each addend is a plain shared-memory load
+                        // issued well ahead, 36-45 when a select or a constant-bank operand sits on the chain.  So 32 steps
+                        // at a time: all symbol loads, then all weight loads (one table indexed by the symbol pair), then
+                        // the 32 adds.  (A hand-pipelined version with the next block's loads between the adds was slower:
+                        // ptxas places the address adds right behind their loads and a lone warp stalls on each.)
+                        for (int i0 = 0; i0 < cl; i0 += 32) {
+                            if (i0 + 32 <= cl) {
+                                uint32_t idx[32];
+                                double w32[32];
+#pragma unroll
+                                for (int u = 0; u < 32; u++) idx[u] = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+#pragma unroll
+                                for (int u = 0; u < 32; u++) {
+                                    w32[u] = s_wtab[idx[u]];
+                                    best_rank = max(best_rank, uint32_t(s_code[idx[u]]) >> 2);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 32; u++) total += w32[u];
+                            } else {
+                                for (int i = i0; i < cl; i++) {
+                                    const uint32_t code = s_code[uint32_t(s_q[warp][i]) + wv[i]];
+                                    total += s_w[code & 3u];
+                                    best_rank = max(best_rank, code >> 2);
+                                }
+                            }
                         }
                     }
                     if (best_rank && n >= first && n < last) {
