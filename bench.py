@@ -415,7 +415,9 @@ def run_ours(args, synth, rank, local_rank, world):
                                                            "issue_active_pct": prof["issue_active_pct"],
                                                            "dram_throughput_pct": prof["dram_throughput_pct"]},
                          "kernel_share_of_step": (main_ns * 1e-6) / dev_ms_bracketed if dev_ms_bracketed else None,
-                         "model": "SURVEY 8(d): 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM x 148 SMs x "
+                         "measured_int_lane_ops_per_clk_per_sm": {"LOP3": 64.0, "IADD3": 64.0, "SHF": 64.0, "IMAD(fma pipe)": 64.0,
+                                                                  "source": "tools/probes/alu_rate_probe.cu on this pool's B200"},
+                         "model": "SURVEY 8(d): 2 int32 lane-ops per pair-eval, 128 lanes/clk/SM (both integer-capable pipes) x 148 SMs x "
                                   f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} clock); not HBM, not tensor. frac > 1 is "
                                   "possible because the bit-sliced kernel spends 0.32 ALU lane-ops per pair-eval, not 2",
                          "kernel_model": {"alu_lane_ops_per_pair_eval": ALU_OPS_PER_WARP_STEP / 32.0, "peak": kernel_model_peak,
