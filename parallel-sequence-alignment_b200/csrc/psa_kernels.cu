@@ -266,11 +266,21 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
     const uint8_t* b = P.seq2s + qbeg;
 
+    // A query can have thousands of tile records and this is a latency-bound walk: 8 records per thread are fetched
+    // together (one round trip), then compared.
     Cand mine{ kKeyNone, 0x7FFFFFFF };
-#pragma unroll 4
-    for (int t = t0 + gtid; t < t1; t += kGroup) {
-        const TileRec r = P.tiles[t];
-        if (better(r.key, r.offset, mine.key, mine.off)) { mine.key = r.key; mine.off = r.offset; }
+    for (int tbase = t0 + gtid; tbase < t1; tbase += 8 * kGroup) {
+        int64_t k8[8];
+        int32_t o8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int t = tbase + u * kGroup;
+            k8[u] = t < t1 ? P.tiles[t].key : kKeyNone;
+            o8[u] = t < t1 ? P.tiles[t].offset : 0x7FFFFFFF;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (better(k8[u], o8[u], mine.key, mine.off)) { mine.key = k8[u]; mine.off = o8[u]; }
     }
     Cand win = WPQ == 1 ? warp_best(mine) : block_best<kFinishThreads>(mine, s_part);
 
@@ -284,12 +294,20 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
         int* my_count = &s_nlist[WPQ == 1 ? warp : 0];
         if (gtid == 0) *my_count = 0;
         if (WPQ == 1) __syncwarp(); else __syncthreads();
-        for (int t = t0 + gtid; t < t1; t += kGroup) {
-            const TileRec r = P.tiles[t];
-            const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
-            if (top == kKeyNone || top < threshold) continue;
-            const int slot = atomicAdd(my_count, 1);
-            if (slot < kFinishList) my_list[slot] = t;
+        for (int tbase = t0 + gtid; tbase < t1; tbase += 8 * kGroup) {
+            int64_t top8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int t = tbase + u * kGroup;
+                const int64_t k = t < t1 ? P.tiles[t].key : kKeyNone, ub = t < t1 ? P.tiles[t].ub_key : kKeyNone;
+                top8[u] = k > ub ? k : ub;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (top8[u] == kKeyNone || top8[u] < threshold) continue;
+                const int slot = atomicAdd(my_count, 1);
+                if (slot < kFinishList) my_list[slot] = tbase + u * kGroup;
+            }
         }
         if (WPQ == 1) __syncwarp(); else __syncthreads();
         const int nlist = *my_count;
