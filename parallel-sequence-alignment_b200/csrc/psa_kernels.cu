@@ -338,18 +338,39 @@ k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
                     for (int c0 = 0; c0 < len2; c0 += kFinishChunk) {
                         const int cl = (len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk;
                         __syncwarp();
+                        // symbols of this chunk, 16 bytes per lane per load (both device buffers carry 64 bytes of padding;
+                        // the Seq1 window starts on a multiple of 32, the query start may be anywhere)
+                        const uint8_t* qsrc = b + c0;
+                        if ((reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
+                            for (int i = lane * 16; i < cl; i += 512) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(qsrc + i);
+                                const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                                for (int t = 0; t < 16; t++) {
+                                    uint32_t c2 = symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3))));
+                                    if (c2 == 0xFFu) c2 = 0;           // flagged by the kernels before us
+                                    if (i + t < cl) s_q[warp][i + t] = uint16_t(c2 * kRowPad);
+                                }
+                            }
+                        } else {
 #pragma unroll 8
-                        for (int i = lane; i < cl; i += 32) {
-                            uint32_t c2 = symbol_of(b[c0 + i]);
-                            if (c2 == 0xFFu) c2 = 0;                   // flagged by the kernels before us
-                            s_q[warp][i] = uint16_t(c2 * kRowPad);
+                            for (int i = lane; i < cl; i += 32) {
+                                uint32_t c2 = symbol_of(qsrc[i]);
+                                if (c2 == 0xFFu) c2 = 0;
+                                s_q[warp][i] = uint16_t(c2 * kRowPad);
+                            }
                         }
-#pragma unroll 8
-                        for (int i = lane; i < cl + 31; i += 32) {
-                            const int64_t p = n0 + c0 + i;
-                            uint32_t c1 = p < G.len1 ? symbol_of(P.seq1[p]) : 0u;
-                            if (c1 == 0xFFu) c1 = 0;
-                            s_win[warp][i] = uint8_t(c1);
+                        const int64_t p0 = n0 + c0;                    // multiple of 32
+                        for (int i = lane * 16; i < cl + 31; i += 512) {
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (p0 + i < G.len1) v = *reinterpret_cast<const uint4*>(P.seq1 + p0 + i);
+                            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                            for (int t = 0; t < 16; t++) {
+                                uint32_t c1 = (p0 + i + t) < G.len1 ? symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3)))) : 0u;
+                                if (c1 == 0xFFu) c1 = 0;
+                                if (i + t < cl + 31) s_win[warp][i + t] = uint8_t(c1);
+                            }
                         }
                         __syncwarp();
                         const uint8_t* wv = &s_win[warp][lane];
