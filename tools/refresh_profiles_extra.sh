@@ -3,7 +3,7 @@
 # (packed mode switched off) for comparison with k_scan_packed.
 set -u
 out=gpurun_out/profiles; mkdir -p $out
-[ -f profiles/r01_summary.json ] && cp profiles/r01_summary.json $out/
+[ -f $out/r01_summary.json ] || { [ -f profiles/r01_summary.json ] && cp profiles/r01_summary.json $out/; }   # keep what refresh_profiles.sh just wrote
 cap() {   # workload, extra bench args, kernel regex, file stem
   B="python bench.py --workload $1 --steps 3 --warmup 3 --no-cpu-baseline --no-others $2"
   $B > /dev/null 2>&1 || { echo "plain run of $1 failed"; return; }
