@@ -130,6 +130,13 @@ typedef struct psa_shard {
 int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards, int64_t granule,
                     int64_t first, int64_t last, psa_shard* out);
 
+/* The launch shape of packed mode (equal-length queries that each fit one window share thread blocks lane by lane,
+   DESIGN.md section 4): for `nq` queries of `len2` symbols against `len1`, how many queries one block takes
+   (*queries_per_block, 0 = packed mode does not apply or would not pay) and how many warps it has (*warps).
+   `force` = 0 picks the shape with the fewest idle lanes and requires >= 5 % over whole warps per query;
+   2..8 forces that many queries per block when it fits.  Pure host arithmetic. */
+int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* queries_per_block, int* warps);
+
 /* Merge per-shard answers of ONE query given in ascending offset-range order, under the reference
    order: strictly better score wins, ties keep the earlier shard = lower offsets
    (MPI_MAXLOC/MINLOC on (score, rank), cpu_funcs.c:73-76; is_swapable cuda_funcs.cu:290-307). */

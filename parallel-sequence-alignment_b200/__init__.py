@@ -124,6 +124,7 @@ def _sig():
     _lib.psa_plan_shards.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(_CShard)]
     _lib.psa_merge_results.argtypes = [C.c_int, C.POINTER(_CResult), C.c_int, C.POINTER(_CResult)]
+    _lib.psa_plan_packing.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     batch = [C.c_void_p, dp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     _lib.psa_search_batch.argtypes = batch + [C.POINTER(_CResult)]
     _lib.psa_batch_prepare.argtypes = batch
@@ -202,6 +203,16 @@ def plan_shards(len1: int, query_lens: Sequence[int], nshards: int, granule: int
     if rc:
         raise PsaError(rc, "psa_plan_shards")
     return [Shard(o.q_begin, o.q_end, o.first, o.last) for o in out]
+
+
+def plan_packing(len1: int, len2: int, nq: int, force: int = 0):
+    """(queries per block, warps per block) of packed mode for nq equal-length queries, (0, 0) if it does not apply
+    (host only, no GPU needed)."""
+    q, w = C.c_int(0), C.c_int(0)
+    rc = _lib.psa_plan_packing(len1, len2, nq, force, C.byref(q), C.byref(w))
+    if rc:
+        raise PsaError(rc, "psa_plan_packing")
+    return q.value, w.value
 
 
 def merge_results(is_max: bool, parts: Sequence[Result]) -> Result:

@@ -310,27 +310,9 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     // Packed mode: equal-length queries that each fit one window share blocks lane by lane (k_scan_packed) when that
     // leaves fewer idle lanes than whole warps per query do.
-    if (scan && !ctx->batch_mode && d.SG.slices <= 1 && uniform_len && uniform == 1 && last < 0 && nq >= 2 &&
-        ctx->max_len2 <= 1023 && ctx->opt_pack_queries != 0) {
-        const int64_t lanes = (offsets_of(len1, ctx->uniform_len2) + 31) / 32;      // per query
-        const double plain = double(lanes) / double(32 * ((lanes + 31) / 32));
-        int best_q = 0, best_w = 0;
-        double best_u = 0.0;
-        if (ctx->opt_pack_queries >= 2) {                                            // forced (tests)
-            const int64_t w = (ctx->opt_pack_queries * lanes + 31) / 32;
-            if (w <= kPackMaxWarps && ctx->opt_pack_queries <= kPackMaxQ) { best_q = ctx->opt_pack_queries; best_w = (int)w; }
-        } else if (lanes >= 1) {
-            for (int w = 1; w <= kPackMaxWarps; w++) {
-                const int q = (int)std::min<int64_t>(std::min<int64_t>(kPackMaxQ, nq), (32 * w) / lanes);
-                if (q < 2) continue;
-                const int ww = (int)((q * lanes + 31) / 32);                         // warps those q queries really need
-                const double u = double(q * lanes) / double(32 * ww);
-                if (u > best_u + 1e-9) { best_u = u; best_q = q; best_w = ww; }
-            }
-            if (best_u < plain * 1.05) best_q = 0;                                   // not worth leaving the plain kernel
-        }
-        if (best_q >= 2 && scan_packed_fits(len1, ctx->uniform_len2)) { d.SG.pack_q = best_q; d.SG.pack_warps = best_w; }
-    }
+    if (scan && !ctx->batch_mode && d.SG.slices <= 1 && uniform_len && uniform == 1 && last < 0 && ctx->opt_pack_queries != 0)
+        psa_plan_packing(len1, ctx->uniform_len2, nq, ctx->opt_pack_queries >= 2 ? ctx->opt_pack_queries : 0, &d.SG.pack_q,
+                         &d.SG.pack_warps);
 
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
@@ -586,6 +568,34 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "packed_warps")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_warps; return 0; }
     if (!std::strcmp(name, "exact")) return ctx->table.exact;
     return -1;
+}
+
+int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* queries_per_block, int* warps)
+{
+    if (!queries_per_block || !warps) return PSA_ERR_ARG;
+    *queries_per_block = *warps = 0;
+    if (len1 < 1 || len2 < 1 || len2 > len1 || nq < 0 || force < 0 || force == 1 || force > kPackMaxQ) return PSA_ERR_ARG;
+    if (nq < 2 || !scan_packed_fits(len1, len2)) return PSA_OK;
+    const int64_t lanes = (offsets_of(len1, len2) + 31) / 32;                        // per query
+    int best_q = 0, best_w = 0;
+    if (force >= 2) {
+        const int64_t w = (force * lanes + 31) / 32;
+        if (w <= kPackMaxWarps) { best_q = force; best_w = (int)w; }
+    } else {
+        const double plain = double(lanes) / double(32 * ((lanes + 31) / 32));
+        double best_u = 0.0;
+        for (int w = 1; w <= kPackMaxWarps; w++) {
+            const int q = (int)std::min<int64_t>(std::min<int64_t>(kPackMaxQ, nq), (32 * w) / lanes);
+            if (q < 2) continue;
+            const int ww = (int)((q * lanes + 31) / 32);                             // warps those q queries really need
+            const double u = double(q * lanes) / double(32 * ww);
+            if (u > best_u + 1e-9) { best_u = u; best_q = q; best_w = ww; }
+        }
+        if (best_u < plain * 1.05) best_q = best_w = 0;                              // not worth leaving the plain kernel
+    }
+    *queries_per_block = best_q;
+    *warps = best_q ? best_w : 0;
+    return PSA_OK;
 }
 
 int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards, int64_t granule,

@@ -124,3 +124,30 @@ def test_two_ranks_gloo(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")]
     assert line and line[0].split()[1:3] == ["True", "True"], p.stdout[-2000:]
+
+
+def test_packing_plan(psa):
+    """Packed mode's launch shape (psa_plan_packing, host arithmetic): a block takes Q whole queries laid lane by lane,
+    L = ceil(offsets / 32) lanes each, in ceil(Q L / 32) warps; chosen for the fewest idle lanes, only when that beats whole
+    warps per query by 5 %."""
+    # config 3: 2501 offsets = 79 lanes -> 3 warps plain (82 %), two queries in 5 warps packed (99 %)
+    assert psa.plan_packing(3000, 500, 1024) == (2, 5)
+    assert psa.plan_packing(3000, 500, 1) == (0, 0)                     # a single query has nobody to share with
+    # 1024 offsets fill one warp exactly: nothing to gain
+    assert psa.plan_packing(1523, 500, 100) == (0, 0)
+    # 11 offsets = 1 lane: eight queries (the cap) share one warp
+    assert psa.plan_packing(100, 90, 40) == (8, 1)
+    # config 5 is 311 lanes per query: beyond one block, and batch mode's job anyway
+    assert psa.plan_packing(10000, 64, 65536) == (0, 0)
+    assert psa.plan_packing(3000, 1024, 50) == (0, 0)                   # len2 > 1023: more than one staged window
+    # forcing: honoured when the block stays within 8 warps
+    assert psa.plan_packing(3000, 500, 1024, force=3) == (3, 8)
+    assert psa.plan_packing(3000, 500, 1024, force=4) == (0, 0)
+    for len1, len2, nq in ((700, 300, 37), (2100, 1000, 11), (330, 64, 50), (4200, 200, 7), (1055, 32, 5)):
+        q, w = psa.plan_packing(len1, len2, nq)
+        lanes = (len1 - len2 + 1 + 31) // 32
+        if q:
+            assert 2 <= q <= min(8, nq) and w == (q * lanes + 31) // 32 <= 8
+            assert q * lanes / (32 * w) >= 1.05 * lanes / (32 * ((lanes + 31) // 32))
+    with pytest.raises(psa.PsaError):
+        psa.plan_packing(10, 20, 5)
