@@ -37,10 +37,10 @@ __host__ __device__ constexpr int rank_pitch(int K) { return K == 1 ? 8 : 4 * K;
 constexpr int kScanChunkMax = 1024;     // alignment steps staged per shared-memory window
 
 // -------------------------------------------------------------------------------------------------
-// k_profile: bit planes of Seq1 against every Seq2 symbol.  One thread per (32-position word, plane kind): each
-// position contributes a 28-bit column (one bit per row symbol) looked up by its Seq1 symbol; a 32x32 bit
-// transpose then turns 32 columns into the 28 row words.  One transpose per plane kind instead of 28 x 32 table
-// lookups.
+// k_profile: bit planes of Seq1 against every Seq2 symbol.  One thread per 32-position word: each position
+// contributes, per plane kind, a 28-bit column (one bit per row symbol) looked up by its Seq1 symbol; a
+// 32x32 bit transpose then turns 32 columns into the 28 row words.  (2+K) transposes per word instead of
+// 28 x 32 table lookups.
 // -------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kProfileThreads)
@@ -52,39 +52,40 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
     for (int k = threadIdx.x; k < (2 + K) * 32; k += kProfileThreads)       // columns resolved on the host (psa_table.cpp)
         s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
     __syncthreads();
-    // one thread per (word, plane kind): the 2 + K transposes of a word run side by side (a short Seq1 is a few hundred
-    // words, so the kernel is all latency)
-    constexpr int NK = 2 + K;
-    const int64_t items = P.plane_words * NK;
-    for (int64_t it = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; it < items; it += int64_t(gridDim.x) * kProfileThreads) {
-        const int64_t w = it / NK;
-        const int kind = int(it - w * NK);
+    for (int64_t w = int64_t(blockIdx.x) * kProfileThreads + threadIdx.x; w < P.plane_words;
+         w += int64_t(gridDim.x) * kProfileThreads) {
         const int64_t base = w * 32;
-        uint32_t m[32];
-#pragma unroll
-        for (int t = 0; t < 32; t++) m[t] = 0u;
+        uint8_t sym[32];
+        int n = 0;
         if (base < G.len1) {
             // 32 bytes of Seq1; the buffer is padded so the vector loads stay inside the allocation
             const uint4 v0 = *reinterpret_cast<const uint4*>(P.seq1 + base);
             const uint4 v1 = *reinterpret_cast<const uint4*>(P.seq1 + base + 16);
             const uint32_t words[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-            const int n = (G.len1 - base) < 32 ? int(G.len1 - base) : 32;
-            const uint32_t* col = s_col[kind];
+            n = (G.len1 - base) < 32 ? int(G.len1 - base) : 32;
 #pragma unroll
             for (int t = 0; t < 32; t++) {
-                const uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
-                if (t < n && c == 0xFFu && kind == 0) report_bad_symbol(P);
-                m[t] = t < n ? col[c == 0xFFu ? 0u : c] : 0u;
+                uint32_t c = symbol_of(uint8_t(words[t >> 2] >> (8 * (t & 3))));
+                if (t < n && c == 0xFFu) report_bad_symbol(P);
+                sym[t] = uint8_t(c == 0xFFu ? 0u : c);
             }
-            transpose32(m);
         }
-        if (kind < 2) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(P.cls_planes) + kind;          // {b0, b1} pairs
+        uint32_t m[32], b0rows[kPlaneRows];
 #pragma unroll
-            for (int r = 0; r < kPlaneRows; r++) dst[(int64_t(r) * P.plane_words + w) * 2] = m[r];
-        } else {
+        for (int kind = 0; kind < 2 + K; kind++) {
 #pragma unroll
-            for (int r = 0; r < kPlaneRows; r++) P.rank_planes[(int64_t(r) * P.plane_words + w) * K + (kind - 2)] = m[r];
+            for (int t = 0; t < 32; t++) m[t] = t < n ? s_col[kind][sym[t]] : 0u;
+            transpose32(m);
+            if (kind == 0) {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) b0rows[r] = m[r];
+            } else if (kind == 1) {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) P.cls_planes[int64_t(r) * P.plane_words + w] = make_uint2(b0rows[r], m[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) P.rank_planes[(int64_t(r) * P.plane_words + w) * K + (kind - 2)] = m[r];
+            }
         }
     }
 }
@@ -1350,8 +1351,7 @@ bool scan_packed_fits(int64_t len1, int64_t len2)
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
                     cudaStream_t stream)
 {
-    const int kinds = 2 + (rank_planes > 2 ? 4 : rank_planes);
-    int64_t blocks = (P.plane_words * kinds + kProfileThreads - 1) / kProfileThreads;      // a thread per (word, plane kind)
+    int64_t blocks = (P.plane_words + kProfileThreads - 1) / kProfileThreads;
     const int64_t cap = int64_t(sm_count) * 16;
     if (blocks > cap) blocks = cap;
     switch (rank_planes) {
