@@ -434,6 +434,38 @@ def test_zero_copy_results_match_copied_results(psa, ctx, port, synth):
     ctx.set_option("zero_copy_results", 1)
 
 
+def test_random_batches(ctx, port):
+    """Random batches through the default dispatch (long / packed / batch mode, fused or separate finish, exact or
+    re-scored order, zero-copy or copied results): equal-length and ragged, tiny and multi-tile, five alphabets."""
+    rng = random.Random(20261018)
+    wsets = [[1, 3, 4, 2], [1, 1, 1, 1], [2, 1.5, 1.1, 1.3], [5, 1, 2, 3], [0.1, 0.7, 0.3, 0.9], [10, 2, 3, 4], [1.5, 2.6, 0.1, 0.2]]
+    modes = set()
+    for trial in range(60):
+        w = rng.choice(wsets)
+        is_max = bool(rng.getrandbits(1))
+        len1 = rng.choice([rng.randint(1, 400), rng.randint(400, 3000), rng.randint(3000, 9000)])
+        nq = rng.choice([1, 2, 3, rng.randint(4, 40), rng.randint(40, 300)])
+        alpha = rng.choice([ALPHA, ALPHA[:26], "ACDG", "AB", "A-"])
+        s1 = "".join(rng.choice(alpha) for _ in range(len1))
+        if rng.getrandbits(1):                                            # equal lengths
+            n2 = rng.choice([1, len1, rng.randint(1, len1), rng.randint(1, min(len1, 200))])
+            lens = [n2] * nq
+        else:
+            lens = [rng.choice([1, len1, rng.randint(1, len1), rng.randint(1, min(len1, 64))]) for _ in range(nq)]
+        if sum((len1 - n + 1) * n for n in lens) > 60_000_000:            # keep the oracle's share of the test short
+            lens = [min(n, 300) for n in lens]
+        qs = ["".join(rng.choice(alpha) for _ in range(n)) for n in lens]
+        if lens[0] < len1:
+            qs[0] = s1[(len1 - lens[0]) // 2: (len1 - lens[0]) // 2 + lens[0]]     # an exact occurrence
+        got = ctx.search_batch(w, is_max, s1, qs)
+        modes.add((ctx.stat("batch_mode"), ctx.stat("packed_queries") > 0, ctx.stat("slices") > 1, ctx.stat("exact")))
+        exp = port.search_batch(w, is_max, s1, qs)
+        for k, (g, e) in enumerate(zip(got, exp)):
+            assert same_answer(g, e), (trial, w, is_max, len1, lens[k], nq, alpha, k, g, e)
+            assert g.counts == e.counts
+    assert len(modes) >= 4, modes
+
+
 def test_reference_program_links_against_the_library(tmp_path, input_blocks):
     """The drop-in proof: the reference's OWN executable -- its unmodified main.c, cpu_funcs.c (file I/O,
     divide_execute_tasks, the call to gpu_run_program at cpu_funcs.c:180) and mpi_funcs.c, MPI stubbed to one rank --
