@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Longer randomized parity run than tests/test_gpu_parity.py::test_random_batches (same generator, any seed, any count,
-random tuning knobs): python tools/fuzz_batches.py [trials] [seed].  Needs a B200; checks against the C oracle."""
+random tuning knobs): python tools/fuzz_batches.py [trials] [seed]   (PSA_FUZZ_GPUS=n for a multi-GPU context).
+Needs a B200; checks against the C oracle."""
 import importlib
 import os
 import random
@@ -28,7 +29,7 @@ def main():
     wsets = [[1, 3, 4, 2], [1, 1, 1, 1], [2, 1.5, 1.1, 1.3], [5, 1, 2, 3], [0.1, 0.7, 0.3, 0.9], [10, 2, 3, 4], [1.5, 2.6, 0.1, 0.2],
              [0, 0, 0, 0], [7, 0, 2, 0.5], [3, 3, 3, 3], [1e6, 1, 1e-3, 5]]
     bad = 0
-    with psa.Context(ngpus=1) as ctx:
+    with psa.Context(ngpus=int(os.environ.get("PSA_FUZZ_GPUS", "1"))) as ctx:
         for trial in range(trials):
             w = rng.choice(wsets)
             is_max = bool(rng.getrandbits(1))
