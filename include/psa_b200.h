@@ -95,7 +95,9 @@ const char* psa_last_error(const psa_context* ctx);
      "batch_mode"    -1 auto | 0 never | 1 whenever every query fits one window (len2 <= 1023)
      "slices"        0 auto | 1 never | n>=2 cut a single query into n ranges of alignment steps
      "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
-     "fused_finish"  1 the scan block also finishes its query when the query is a single tile (exact order) | 0 never
+     "fused_finish"  1 the finish step runs inside the kernel before it where that saves a launch: in the scan block when
+                     a query is a single tile (exact order), in k_combine's last block for a sliced query with few
+                     combine blocks | 0 always its own kernel
      "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
      "pack_queries"  1 auto: equal-length queries that fit one window share blocks lane by lane when whole warps per
                      query would idle | 0 never | 2..8 force that many queries per block

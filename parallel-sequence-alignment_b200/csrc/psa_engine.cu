@@ -307,6 +307,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     d.SG.fused_finish = scan && !ctx->batch_mode && d.SG.slices <= 1 && ctx->table.exact && uniform == 1 &&
                         ctx->opt_fused_finish != 0;
+    // slice mode with few combine blocks: the last of them finishes the query
+    d.SG.fused_combine = scan && d.SG.slices > 1 && tiles <= 2 * (int64_t)d.sm_count && ctx->opt_fused_finish != 0;
 
     // Packed mode: equal-length queries that each fit one window share blocks lane by lane (k_scan_packed) when that
     // leaves fewer idle lanes than whole warps per query do.
@@ -407,7 +409,7 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
         d.st_launches += 1;
     }
-    if (!d.SG.fused_finish) {
+    if (!d.SG.fused_finish && !d.SG.fused_combine) {
         launch_finish(ctx->table, d.G, d.P, ctx->engine == 2, d.stream);
         d.st_launches += 1;
     }

@@ -14,6 +14,7 @@
 //     reference's winner.
 #include "psa_kernels.cuh"
 #include "psa_device.cuh"
+#include "psa_finish.cuh"
 
 namespace psa {
 
@@ -208,277 +209,12 @@ k_offset_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-// Finish: one warp per query, 8 queries per block (WPQ = 1), or -- for small batches, where a single warp
-// would crawl through dependent global loads -- the whole block on one query (WPQ = 8).
-//  (1) winner over the query's tile records under (key desc, offset asc);
-//  (2) only when the weights are not exactly summable and the records come from the bit-sliced scan:
-//      the integer keys order offsets like the reference only up to key_slack, so every 32-offset word
-//      whose key estimate is within key_slack of the best key is re-scored here -- one lane per offset,
-//      a double accumulated over i = 0..len2-1 in the reference's order (cpu_funcs.c:271-299), symbols
-//      staged through shared memory 256 steps at a time -- and the winner is chosen among those doubles
-//      under is_swapable's order (cuda_funcs.cu:290-307);
-//  (3) one pass over the winning alignment for the sign counts, the first position carrying the best
-//      rank (cpu_funcs.c:287-294: strict compare, so the lowest i wins ties) and its replacement letter.
-// -------------------------------------------------------------------------------------------------
-constexpr int kFinishWarps = 8;
-constexpr int kFinishThreads = kFinishWarps * 32;
-constexpr int kFinishChunk = 1024;
-constexpr int kFinishList = 32;       // candidate tiles remembered per query before falling back to a full walk
-
 // (block per query: min blocks = 1, so ptxas may spend registers on keeping the re-score loop's loads well ahead of its add chain)
 template <int WPQ>
 __global__ void __launch_bounds__(kFinishThreads, WPQ == 1 ? 4 : 1)
 k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int scan_records)
 {
-    constexpr int kGroup = WPQ * 32;                                    // threads working on one query
-    __shared__ Cand s_part[kFinishWarps];
-    __shared__ unsigned long long s_pos;
-    __shared__ int s_cnt[4];
-    __shared__ __align__(16) uint8_t s_code[kSymbols * kRowPad];
-    __shared__ double s_w[4];
-    __shared__ int s_list[kFinishWarps][kFinishList];
-    __shared__ int s_nlist[kFinishWarps];
-    __shared__ uint16_t s_q[kFinishWarps][kFinishChunk];               // Seq2 symbol * kRowPad
-    __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
-    __shared__ double s_wtab[kSymbols * kRowPad];                       // pair weight by (Seq2 symbol * kRowPad + Seq1 symbol)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 4) s_w[tid] = T.wcls[tid];
-    if (tid == 0) s_pos = 0ull;
-    if (tid < 4) s_cnt[tid] = 0;
-    pdl_wait();                                                         // tile records and the pair table come from the kernels before us
-    for (int k = tid; k < kSymbols * kRowPad / 4; k += kFinishThreads)
-        reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(P.code_table)[k];
-    if (!T.exact)
-        for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_wtab[k] = T.wcls[P.code_table[k] & 3u];
-    __syncthreads();
-    const int q = WPQ == 1 ? blockIdx.x * kFinishWarps + warp : blockIdx.x;
-    if (q >= G.nq) return;
-    const int gtid = WPQ == 1 ? lane : tid;                             // index within the query's thread group
-    const int gwarp = WPQ == 1 ? 0 : warp;
-
-    const QueryGeom qg = query_geom(G, P.qoff, P.tile_start, q);
-    const int t0 = qg.tile0, t1 = q + 1 < G.nq ? first_tile_of(G, P.tile_start, q + 1) : G.total_tiles;
-    PSA_CHECK(t0 >= 0 && t0 <= t1 && t1 <= G.total_tiles);
-    const int64_t qbeg = qg.qbeg;
-    const int len2 = qg.len2;
-    const int64_t first = G.last >= 0 ? G.first : 0;
-    const int64_t last = G.last >= 0 ? G.last : G.len1 - len2 + 1;
-    const uint8_t* b = P.seq2s + qbeg;
-
-    // A query can have thousands of tile records and this is a latency-bound walk: 8 records per thread are fetched
-    // together (one round trip), then compared.
-    Cand mine{ kKeyNone, 0x7FFFFFFF };
-    for (int tbase = t0 + gtid; tbase < t1; tbase += 8 * kGroup) {
-        int64_t k8[8];
-        int32_t o8[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int t = tbase + u * kGroup;
-            k8[u] = t < t1 ? P.tiles[t].key : kKeyNone;
-            o8[u] = t < t1 ? P.tiles[t].offset : 0x7FFFFFFF;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-            if (better(k8[u], o8[u], mine.key, mine.off)) { mine.key = k8[u]; mine.off = o8[u]; }
-    }
-    Cand win = WPQ == 1 ? warp_best(mine) : block_best<kFinishThreads>(mine, s_part);
-
-    if (!T.exact && scan_records) {
-        const int64_t threshold = win.key == kKeyNone ? kKeyNone : win.key - T.key_slack;   // |key| < 2^61: no wrap
-        const int tile_words = G.tile >> 5;
-        Cand mine2{ kKeyNone, 0x7FFFFFFF };
-        int words = 0;
-        // candidate tiles, found in parallel (a query can have thousands of tiles and one or two candidates)
-        int* my_list = s_list[WPQ == 1 ? warp : 0];
-        int* my_count = &s_nlist[WPQ == 1 ? warp : 0];
-        if (gtid == 0) *my_count = 0;
-        if (WPQ == 1) __syncwarp(); else __syncthreads();
-        for (int tbase = t0 + gtid; tbase < t1; tbase += 8 * kGroup) {
-            int64_t top8[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int t = tbase + u * kGroup;
-                const int64_t k = t < t1 ? P.tiles[t].key : kKeyNone, ub = t < t1 ? P.tiles[t].ub_key : kKeyNone;
-                top8[u] = k > ub ? k : ub;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (top8[u] == kKeyNone || top8[u] < threshold) continue;
-                const int slot = atomicAdd(my_count, 1);
-                if (slot < kFinishList) my_list[slot] = tbase + u * kGroup;
-            }
-        }
-        if (WPQ == 1) __syncwarp(); else __syncthreads();
-        const int nlist = *my_count;
-        const bool listed = nlist <= kFinishList;               // else: walk every tile (correct, just slower)
-        const int ntry = listed ? nlist : (t1 - t0);
-        for (int k = 0; k < ntry; k++) {
-            const int t = listed ? my_list[k] : t0 + k;
-            if (!listed) {
-                const TileRec r = P.tiles[t];
-                const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
-                if (top == kKeyNone || top < threshold) continue;
-            }
-            const int64_t* lk = P.lane_keys + int64_t(t) * tile_words;
-            const int64_t tb = tile_base(first) + int64_t(t - t0) * G.tile;
-            for (int w0 = 0; w0 < tile_words; w0 += 32) {
-                // which of the next 32 words are candidates (one ballot instead of 32 broadcast loads)
-                const int64_t k = (w0 + lane) < tile_words ? lk[w0 + lane] : kKeyNone;
-                uint32_t cand = __ballot_sync(0xFFFFFFFFu, k != kKeyNone && k >= threshold);
-                while (cand) {
-                    const int w = w0 + __ffs(int(cand)) - 1;
-                    cand &= cand - 1u;
-                    if (WPQ > 1 && (w % WPQ) != gwarp) continue;       // candidate words go round the warps of the block
-                    words++;
-                    const int64_t n0 = tb + 32 * w;                    // the word's first offset; this lane owns n0 + lane
-                    const int64_t n = n0 + lane;
-                    double total = 0.0;
-                    uint32_t best_rank = 0;
-                    for (int c0 = 0; c0 < len2; c0 += kFinishChunk) {
-                        const int cl = (len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk;
-                        __syncwarp();
-                        // symbols of this chunk, 16 bytes per lane per load (both device buffers carry 64 bytes of padding;
-                        // the Seq1 window starts on a multiple of 32, the query start may be anywhere)
-                        const uint8_t* qsrc = b + c0;
-                        if ((reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
-                            for (int i = lane * 16; i < cl; i += 512) {
-                                const uint4 v = *reinterpret_cast<const uint4*>(qsrc + i);
-                                const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                                for (int t = 0; t < 16; t++) {
-                                    uint32_t c2 = symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3))));
-                                    if (c2 == 0xFFu) c2 = 0;           // flagged by the kernels before us
-                                    if (i + t < cl) s_q[warp][i + t] = uint16_t(c2 * kRowPad);
-                                }
-                            }
-                        } else {
-#pragma unroll 8
-                            for (int i = lane; i < cl; i += 32) {
-                                uint32_t c2 = symbol_of(qsrc[i]);
-                                if (c2 == 0xFFu) c2 = 0;
-                                s_q[warp][i] = uint16_t(c2 * kRowPad);
-                            }
-                        }
-                        const int64_t p0 = n0 + c0;                    // multiple of 32
-                        for (int i = lane * 16; i < cl + 31; i += 512) {
-                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                            if (p0 + i < G.len1) v = *reinterpret_cast<const uint4*>(P.seq1 + p0 + i);
-                            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                            for (int t = 0; t < 16; t++) {
-                                uint32_t c1 = (p0 + i + t) < G.len1 ? symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3)))) : 0u;
-                                if (c1 == 0xFFu) c1 = 0;
-                                if (i + t < cl + 31) s_win[warp][i + t] = uint8_t(c1);
-                            }
-                        }
-                        __syncwarp();
-                        const uint8_t* wv = &s_win[warp][lane];
-                        // The sum must be the reference's: one rounding per step, in step order -- a chain of dependent
-                        // double adds run by one warp, with nothing to hide latency behind.  Measured on B200
-                        // (tools/probes/dadd_probe.cu): 8 cycles per step when each addend is a plain shared-memory load
-                        // issued well ahead, 36-45 when a select or a constant-bank operand sits on the chain.  So 32 steps
-                        // at a time: all symbol loads, then all weight loads (one table indexed by the symbol pair), then
-                        // the 32 adds.  (A hand-pipelined version with the next block's loads between the adds was slower:
-                        // ptxas places the address adds right behind their loads and a lone warp stalls on each.)
-                        for (int i0 = 0; i0 < cl; i0 += 32) {
-                            if (i0 + 32 <= cl) {
-                                uint32_t idx[32];
-                                double w32[32];
-#pragma unroll
-                                for (int u = 0; u < 32; u++) idx[u] = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
-#pragma unroll
-                                for (int u = 0; u < 32; u++) {
-                                    w32[u] = s_wtab[idx[u]];
-                                    best_rank = max(best_rank, uint32_t(s_code[idx[u]]) >> 2);
-                                }
-#pragma unroll
-                                for (int u = 0; u < 32; u++) total += w32[u];
-                            } else {
-                                for (int i = i0; i < cl; i++) {
-                                    const uint32_t code = s_code[uint32_t(s_q[warp][i]) + wv[i]];
-                                    total += s_w[code & 3u];
-                                    best_rank = max(best_rank, code >> 2);
-                                }
-                            }
-                        }
-                    }
-                    if (best_rank && n >= first && n < last) {
-                        const double score = total + T.wdiff[best_rank];                   // cpu_funcs.c:299
-                        const int64_t key = sortable_from_double(T.is_max ? score : -score);
-                        if (better(key, int32_t(n), mine2.key, mine2.off)) { mine2.key = key; mine2.off = int32_t(n); }
-                    }
-                }
-            }
-        }
-        if (lane == 0 && words) atomicAdd(P.cand_count, words);
-        win = WPQ == 1 ? warp_best(mine2) : block_best<kFinishThreads>(mine2, s_part);
-    }
-
-    QueryRec out;
-    out.score = T.is_max ? -INFINITY : INFINITY;      // what the reference returns when nothing can be mutated
-    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
-    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
-    if (win.key == kKeyNone) {            // no mutation possible at any offset (never seen in practice)
-        if (gtid == 0) P.out[q] = out;
-        return;
-    }
-
-    PSA_CHECK(win.off >= first && win.off < last && int64_t(win.off) + len2 <= G.len1);
-    const uint8_t* a = P.seq1 + win.off;
-    int cnt[4] = { 0, 0, 0, 0 };
-    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
-#pragma unroll 4
-    for (int i = gtid; i < len2; i += kGroup) {
-        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
-        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-        const uint32_t code = s_code[c2 * kRowPad + c1];
-        cnt[code & 3u]++;
-        const unsigned long long p = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
-        pos = p > pos ? p : pos;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
-        pos = o > pos ? o : pos;
-#pragma unroll
-        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
-    }
-    if (WPQ > 1) {
-        if (lane == 0) {
-            atomicMax(&s_pos, pos);
-#pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
-        }
-        __syncthreads();
-        pos = s_pos;
-#pragma unroll
-        for (int c = 0; c < 4; c++) cnt[c] = s_cnt[c];
-    }
-    if (gtid == 0) {
-        const int rank = int(pos >> 32);
-        const int i = int(~uint32_t(pos));
-        uint32_t c1 = symbol_of(a[i]), c2 = symbol_of(b[i]);
-        if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
-        out.offset = win.off;
-        out.char_offset = i;
-        out.ch = T.sub[c2][c1];
-        out.rank = rank;
-        for (int c = 0; c < 4; c++) out.counts[c] = cnt[c];
-        if (T.exact) {
-            // every product and partial sum is exactly representable (psa_table.cpp), so this IS the reference's
-            // sequential sum + difference, bit for bit; explicit _rn ops keep the compiler from contracting to FMA
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) s = __dadd_rn(s, __dmul_rn(double(cnt[c]), T.wcls[c]));
-            out.score = __dadd_rn(__dadd_rn(s, T.wdiff[rank]), 0.0);
-        } else {
-            // engine 1 tile keys and re-scored keys are sortable images of the reference's double
-            out.score = __dadd_rn((T.is_max ? 1.0 : -1.0) * double_from_sortable(win.key), 0.0);
-        }
-        if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
-        P.out[q] = out;
-    }
+    finish_body<WPQ, true>(T, G, P, scan_records, int(blockIdx.x));
 }
 
 } // namespace

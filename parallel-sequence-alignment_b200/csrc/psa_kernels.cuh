@@ -48,6 +48,7 @@ struct SliceGeom {
     int scan_tiles = 0;    // scan blocks per slice
     bool fused_finish = false;  // long mode, exact order, one tile per query: the scan block also finishes its query
     bool allow_derive = true;   // option "derive_rank": take the top-rank bit from the class planes when the table allows it
+    bool fused_combine = false; // slice mode on a small grid: k_combine's last block runs the finish step (no k_finish launch)
     int pack_q = 0;             // packed mode (k_scan_packed): queries per block, 0 = off
     int pack_warps = 0;         //   and warps per block = ceil(pack_q * lanes per query / 32)
 };

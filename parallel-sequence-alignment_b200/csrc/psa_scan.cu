@@ -20,6 +20,7 @@
 // upper bound for them and k_select sends the tile to the exact kernel only if that bound could win.
 #include "psa_kernels.cuh"
 #include "psa_device.cuh"
+#include "psa_finish.cuh"
 #include "psa_bitslice.h"
 
 #include <algorithm>
@@ -48,7 +49,10 @@ k_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
 {
     __shared__ uint32_t s_col[2 + (K > 0 ? K : 1)][32];           // [plane kind][Seq1 symbol] -> bit r = row symbol r
     pdl_launch_dependents();                                        // the scan may set itself up while we run
-    if (blockIdx.x == 0 && threadIdx.x == 0) *P.cand_count = 0;     // first kernel of the chain: only k_finish adds to it
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                      // first kernel of the chain:
+        P.cand_count[0] = 0;                                        //   only the finish step adds to the re-score counter
+        P.cand_count[2] = 0;                                        //   k_combine's "last block" ticket
+    }
     for (int k = threadIdx.x; k < (2 + K) * 32; k += kProfileThreads)       // columns resolved on the host (psa_table.cpp)
         s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
     __syncthreads();
@@ -728,7 +732,9 @@ k_scan(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs
 // -------------------------------------------------------------------------------------------------
 constexpr int kCombineThreads = 256;
 
-template <int K>
+// FUSE (small grids only): the block that finishes last also runs the finish step -- its registers would cost the
+// many-block case its occupancy, and there one more launch does not matter.
+template <int K, bool FUSE>
 __global__ void __launch_bounds__(kCombineThreads)
 k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int slices)
 {
@@ -811,6 +817,19 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
             for (int w = 0; w < kCombineThreads / 32; w++) rec.ub_key = s_top[w] > rec.ub_key ? s_top[w] : rec.ub_key;
         rec.ub_offset = 0x7FFFFFFF; rec.score = 0.0; rec.flags = 0; rec.pad = 0;
         P.tiles[blockIdx.x] = rec;
+    }
+    if (FUSE) {
+        // the last block to get here has every tile record (and lane key) of the query in front of it
+        __shared__ int s_last;
+        __syncthreads();                                        // this block's lane keys and record are written
+        if (tid == 0) {
+            __threadfence();
+            s_last = atomicAdd(P.cand_count + 2, 1) == int(gridDim.x) - 1;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        finish_body<kFinishWarps, false>(T, G, P, 1, 0);
     }
 }
 
@@ -1217,14 +1236,16 @@ void launch_scan_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
                 allow_big_smem(k_scan<NB, K, false, true, true>, done_dr);
                 launch_dependent(k_scan<NB, K, false, true, true>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P,
                                  nwords, chunk, 0, int64_t(0), SG.slice_len, 0);
-                launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
+                if (SG.fused_combine) launch_dependent(k_combine<K, true>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
+                else launch_dependent(k_combine<K, false>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
                 return;
             }
         }
         allow_big_smem(k_scan<NB, K, false, true, false>, done);
         launch_dependent(k_scan<NB, K, false, true, false>, dim3(Gs.total_tiles, SG.slices), dim3(warps * 32), smem, stream, T, Gs, P, nwords, chunk, 0,
                          int64_t(0), SG.slice_len, 0);
-        launch_dependent(k_combine<K>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
+        if (SG.fused_combine) launch_dependent(k_combine<K, true>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
+        else launch_dependent(k_combine<K, false>, dim3(G.total_tiles), dim3(kCombineThreads), 0, stream, T, G, P, SG.slices);
         return;
     }
     if constexpr (NB <= 10) {

@@ -256,12 +256,14 @@ def test_all_stacked_blocks(psa, ctx, tmp_path, input_blocks):
     assert p.returncode == 0 and (tmp_path / "output.txt").read_text().split("\n") == lines
 
 
-@pytest.mark.parametrize("slices,planes", [(0, -1), (2, -1), (5, 0), (16, 1)])
-def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes):
+@pytest.mark.parametrize("slices,planes,fused", [(0, -1, 1), (2, -1, 1), (5, 0, 1), (16, 1, 1), (0, -1, 0), (4, 1, 0)])
+def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes, fused):
     """One query cut along its alignment steps (k_scan slices + k_combine): same answers as the oracle for exact
-    and re-scored weights, explicit ranges, unresolved ranks (0 planes) and ties."""
+    and re-scored weights, explicit ranges, unresolved ranks (0 planes) and ties -- with the finish step run by
+    k_combine's last block (small grids, the default) or by its own kernel."""
     _set_engine(ctx, 2, planes)
     ctx.set_option("slices", slices)
+    ctx.set_option("fused_finish", fused)
     try:
         for b in (input_blocks[0], input_blocks[4], input_blocks[6], input_blocks[9]):
             r = ctx.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"])
@@ -276,8 +278,11 @@ def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes)
                 assert same_answer(ctx.search(w, is_max, tied, core), port.search(w, is_max, tied, core))
         if slices >= 2:
             assert ctx.stat("slices") >= 2
+        # the last search (9 000 offsets = 36 combine blocks): profile + scan + combine, + finish when not fused
+        assert ctx.stat("kernel_launches") == (3 if fused else 4)
     finally:
         ctx.set_option("slices", 0)
+        ctx.set_option("fused_finish", 1)
         _set_engine(ctx, 0)
 
 
