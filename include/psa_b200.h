@@ -197,6 +197,23 @@ void  psa_free_pinned(void* p);
  */
 double psa_gpu_run_program(void* program_data, void* returned_mutant, int first_offset, int last_offset);
 
+/* The six host primitives the reference's cpu_funcs.c imports from cuda_funcs.cu (cuda_funcs.h:44-61), C spellings.
+   The library also exports them under the reference's C++-mangled names (include/cuda_funcs.h lists them), so the
+   reference program links with no cuda_funcs.o at all.  Host only, no GPU needed; answers come from the pair-table
+   resolver (psa_build_pair_table), never from the reference's hashtable_cpu.
+     psa_get_hashtable_sign  cuda_funcs.cu:424-439  '*' ':' '.' '_' over [A-Z-], '\0' for anything else
+     psa_get_pair_sign       cuda_funcs.cu:495-502  group membership only ('-' is in no group)
+     psa_get_weight          cuda_funcs.cu:442-452  '*' -> +w[0], ':' -> -w[1], '.' -> -w[2], '_' -> -w[3], else 0
+     psa_get_substitute      cuda_funcs.cu:310-421  best replacement for c2 facing c1 ('\0' outside [A-Z-])
+     psa_is_swapable         cuda_funcs.cu:290-307  1 if (m2, score2) beats (m1, score1) under the reference order
+     psa_strlen              cuda_funcs.cu:534-545  */
+char   psa_get_hashtable_sign(char c1, char c2);
+char   psa_get_pair_sign(char a, char b);
+double psa_get_weight(char sign, const double* w);
+char   psa_get_substitute(char c1, char c2, const double* w, int is_max);
+int    psa_is_swapable(const psa_mutant* m1, const psa_mutant* m2, double score1, double score2, int is_max);
+int    psa_strlen(const char* str);
+
 /* input.txt / output.txt in the reference's format (cpu_funcs.c:353-378): four weights, Seq1,
    Seq2, "maximum"|"minimum" (anything else = minimum), whitespace separated; output
    "<mutant>\n<offset> <score %g>" without trailing newline.  seq buffers are malloc()ed. */

@@ -37,6 +37,13 @@ typedef struct _mutant {
 #ifdef __cplusplus
 /* the symbol the reference's cpu_funcs.c (compiled as C++ by mpicxx, Makefile:9-11) imports */
 double gpu_run_program(ProgramData* cpu_data, Mutant* returned_mutant, int first_offset, int last_offset);
+/* ... and the six host primitives it imports from cuda_funcs.cu (cuda_funcs.h:44-61); see include/cuda_funcs.h */
+char   get_substitute(char c1, char c2, double* w, int is_max);
+char   get_hashtable_sign(char c1, char c2);
+double get_weight(char sign, double* w);
+char   get_pair_sign(char a, char b);
+int    is_swapable(Mutant* m1, Mutant* m2, double score1, double score2, int is_max);
+int    strlen_gpu(char* str);
 #endif
 
 #endif /* PSA_REFERENCE_ABI_H */

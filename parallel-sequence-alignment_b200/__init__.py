@@ -143,6 +143,17 @@ def _sig():
     _lib.psa_write_output_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double]
     _lib.psa_run_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(_CResult)]
     _lib.psa_run_files_all.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    # the six host primitives of cuda_funcs.h:44-61 (C spellings)
+    _lib.psa_get_hashtable_sign.restype = C.c_char
+    _lib.psa_get_hashtable_sign.argtypes = [C.c_char, C.c_char]
+    _lib.psa_get_pair_sign.restype = C.c_char
+    _lib.psa_get_pair_sign.argtypes = [C.c_char, C.c_char]
+    _lib.psa_get_weight.restype = C.c_double
+    _lib.psa_get_weight.argtypes = [C.c_char, dp]
+    _lib.psa_get_substitute.restype = C.c_char
+    _lib.psa_get_substitute.argtypes = [C.c_char, C.c_char, dp, C.c_int]
+    _lib.psa_is_swapable.argtypes = [C.POINTER(Mutant), C.POINTER(Mutant), C.c_double, C.c_double, C.c_int]
+    _lib.psa_strlen.argtypes = [C.c_char_p]
 
 
 _sig()
@@ -429,6 +440,35 @@ def gpu_run_program(data: ProgramData, first_offset: int, last_offset: int):
     m = Mutant()
     score = _lib.psa_gpu_run_program(C.byref(data), C.byref(m), first_offset, last_offset)
     return score, m
+
+
+def _ch(r: bytes) -> str:
+    return r.decode("latin1") if r != b"\x00" else ""
+
+
+# The host primitives cpu_funcs.c imports from cuda_funcs.cu (cuda_funcs.h:44-61), same names and argument meaning.
+def get_hashtable_sign(c1: str, c2: str) -> str:
+    return _ch(_lib.psa_get_hashtable_sign(_b(c1), _b(c2)))
+
+
+def get_pair_sign(a: str, b: str) -> str:
+    return _ch(_lib.psa_get_pair_sign(_b(a), _b(b)))
+
+
+def get_weight(sign: str, weights) -> float:
+    return _lib.psa_get_weight(_b(sign) if sign else b"\x00", _w(weights))
+
+
+def get_substitute(c1: str, c2: str, weights, is_max: bool) -> str:
+    return _ch(_lib.psa_get_substitute(_b(c1), _b(c2), _w(weights), int(bool(is_max))))
+
+
+def is_swapable(m1: Mutant, m2: Mutant, score1: float, score2: float, is_max: bool) -> bool:
+    return bool(_lib.psa_is_swapable(C.byref(m1), C.byref(m2), score1, score2, int(bool(is_max))))
+
+
+def strlen_gpu(s) -> int:
+    return _lib.psa_strlen(_b(s))
 
 
 def read_seq_and_weights_from_file(path: str):

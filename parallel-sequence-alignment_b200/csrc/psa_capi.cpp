@@ -73,7 +73,75 @@ double gpu_run_program(ProgramData* cpu_data, Mutant* returned_mutant, int first
     return r.mutant.ch == '\0' ? none : r.score;           // cuda_funcs.cu:143-145
 }
 
+// -------------------------------------------------------------------------------------------------
+// The six host primitives cpu_funcs.c imports from the reference's cuda_funcs.cu (cuda_funcs.h:44-61; nm -u of its
+// object file: get_weight, strlen_gpu, is_swapable, get_pair_sign, get_substitute, get_hashtable_sign).  Exported
+// under the same C++-mangled names so that the reference links with NO cuda_funcs.o at all (include/cuda_funcs.h,
+// INTEGRATION.md 1b).  Host only; every answer comes from the resolver in psa_table.cpp, none from the reference's
+// hashtable_cpu -- so its racy fill_hash (cpu_funcs.c:306-307) cannot reach a score any more.
+// -------------------------------------------------------------------------------------------------
+char get_hashtable_sign(char c1, char c2)
+{
+    // cuda_funcs.cu:424-439: the gap symbol pairs only with itself, anything else outside A..Z has no sign
+    if (c1 == '-' || c2 == '-') return c1 == c2 ? '*' : '_';
+    const int a = psa::symbol_index(c1), b = psa::symbol_index(c2);
+    if (a < 0 || b < 0) return '\0';
+    return psa::sign_of(a, b);
+}
+
+char get_pair_sign(char a, char b)
+{
+    // cuda_funcs.cu:495-502: group membership only; characters in no group (including '-') are '_' unless identical
+    if (a == b) return '*';
+    const int x = psa::symbol_index(a), y = psa::symbol_index(b);
+    if (x < 0 || y < 0 || x == psa::kGap || y == psa::kGap) return '_';
+    return psa::sign_of(x, y);
+}
+
+double get_weight(char sign, double* w)
+{
+    // cuda_funcs.cu:442-452
+    return sign == '*' ? w[0] : sign == ':' ? -w[1] : sign == '.' ? -w[2] : sign == '_' ? -w[3] : 0.0;
+}
+
+char get_substitute(char c1, char c2, double* w, int is_max)
+{
+    // cuda_funcs.cu:310-421 as one lookup; undefined in the reference for symbols outside [A-Z-]: '\0' here
+    const int a = psa::symbol_index(c1), b = psa::symbol_index(c2);
+    if (a < 0 || b < 0 || !w) return '\0';
+    const int s = psa::best_substitute(a, b, w, is_max != 0);
+    return s < 0 ? '\0' : psa::symbol_char(s);
+}
+
+int is_swapable(Mutant* m1, Mutant* m2, double score1, double score2, int is_max)
+{
+    // cuda_funcs.cu:290-307: strictly better score, else on equal scores the lower (offset, char_offset)
+    if (is_max ? score2 > score1 : score2 < score1) return 1;
+    if (score2 != score1) return 0;
+    if (m2->offset != m1->offset) return m2->offset < m1->offset;
+    return m2->char_offset < m1->char_offset;
+}
+
+int strlen_gpu(char* str)
+{
+    int n = 0;
+    while (str[n]) n++;
+    return n;
+}
+
 extern "C" {
+
+// C spellings of the same six, for ctypes / C callers
+char   psa_get_hashtable_sign(char c1, char c2) { return get_hashtable_sign(c1, c2); }
+char   psa_get_pair_sign(char a, char b) { return get_pair_sign(a, b); }
+double psa_get_weight(char sign, const double* w) { return get_weight(sign, const_cast<double*>(w)); }
+char   psa_get_substitute(char c1, char c2, const double* w, int is_max) { return get_substitute(c1, c2, const_cast<double*>(w), is_max); }
+int    psa_is_swapable(const psa_mutant* m1, const psa_mutant* m2, double score1, double score2, int is_max)
+{
+    Mutant a = { m1->offset, m1->char_offset, m1->ch }, b = { m2->offset, m2->char_offset, m2->ch };
+    return is_swapable(&a, &b, score1, score2, is_max);
+}
+int    psa_strlen(const char* str) { return strlen_gpu(const_cast<char*>(str)); }
 
 double psa_gpu_run_program(void* program_data, void* returned_mutant, int first_offset, int last_offset)
 {

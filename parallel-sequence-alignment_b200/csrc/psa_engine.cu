@@ -193,8 +193,11 @@ int pick_rank_planes(const psa_context* ctx)
     // speed knob: long queries saturate the top rank within a few dozen steps, short ones benefit from two
     // measured (tools/stats.py): one plane is best at every length once unresolved offsets are settled in-kernel
     int want = ctx->opt_rank_planes >= 0 ? ctx->opt_rank_planes : 1;
-    if (want > 2) want = 4;                                          // supported widths: 0,1,2,4
-    return std::min(want, std::max(avail, 0));
+    int k = std::min(want, std::max(avail, 0));
+    // the kernels are instantiated for 0, 1, 2 and 4 planes and the plane buffer is sized from this number: 3 (e.g. four
+    // planes asked for, three ranks to resolve) becomes 4 -- a plane for a rank that does not exist is simply all zero
+    if (k == 3 || k > 4) k = 4;
+    return k;
 }
 
 // Run fn(device) for every GPU of the context: GPU 0 on the calling thread, the others on their worker threads.
@@ -730,7 +733,8 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
         probe.last = last;
         probe.len1 = len1;
         probe.nq = (nq + (int)ctx->devs.size() - 1) / (int)ctx->devs.size();
-        ctx->batch_mode = ctx->opt_batch_mode != 0 && (ctx->opt_batch_mode == 1 || ctx->opt_scan_warps == 0) &&
+        // (a single query always runs on an explicit offset range per GPU, which batch mode does not take)
+        ctx->batch_mode = nq > 1 && ctx->opt_batch_mode != 0 && (ctx->opt_batch_mode == 1 || ctx->opt_scan_warps == 0) &&
                           scan_batch_mode(probe, max_len2, ctx->opt_batch_mode == 1 ? 0 : ctx->devs[0].sm_count);
         if (ctx->batch_mode) ctx->scan_tile = 1024;
     }

@@ -25,6 +25,8 @@ constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kFinishChunk = 1024;
 constexpr int kFinishList = 32;       // candidate tiles remembered per query before falling back to a full walk
 
+// Tile records and lane keys are read with ld.global.cg (L2): when this runs as the tail of k_combine's last block they
+// were written by OTHER blocks of the same launch, and an L1 line filled earlier in the launch would be stale.
 // The body is a device function so that k_combine's last block can run it too (slice mode on a small grid: one launch
 // fewer per single query).  `block_index` stands for blockIdx.x of a k_finish launch; WAIT: the caller has not yet waited
 // for the kernels before it.
@@ -76,8 +78,8 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int t = tbase + u * kGroup;
-            k8[u] = t < t1 ? P.tiles[t].key : kKeyNone;
-            o8[u] = t < t1 ? P.tiles[t].offset : 0x7FFFFFFF;
+            k8[u] = t < t1 ? __ldcg(&P.tiles[t].key) : kKeyNone;
+            o8[u] = t < t1 ? __ldcg(&P.tiles[t].offset) : 0x7FFFFFFF;
         }
 #pragma unroll
         for (int u = 0; u < 8; u++)
@@ -100,7 +102,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int t = tbase + u * kGroup;
-                const int64_t k = t < t1 ? P.tiles[t].key : kKeyNone, ub = t < t1 ? P.tiles[t].ub_key : kKeyNone;
+                const int64_t k = t < t1 ? __ldcg(&P.tiles[t].key) : kKeyNone, ub = t < t1 ? __ldcg(&P.tiles[t].ub_key) : kKeyNone;
                 top8[u] = k > ub ? k : ub;
             }
 #pragma unroll
@@ -117,15 +119,15 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
         for (int k = 0; k < ntry; k++) {
             const int t = listed ? my_list[k] : t0 + k;
             if (!listed) {
-                const TileRec r = P.tiles[t];
-                const int64_t top = r.key > r.ub_key ? r.key : r.ub_key;
+                const int64_t rk = __ldcg(&P.tiles[t].key), rub = __ldcg(&P.tiles[t].ub_key);
+                const int64_t top = rk > rub ? rk : rub;
                 if (top == kKeyNone || top < threshold) continue;
             }
             const int64_t* lk = P.lane_keys + int64_t(t) * tile_words;
             const int64_t tb = tile_base(first) + int64_t(t - t0) * G.tile;
             for (int w0 = 0; w0 < tile_words; w0 += 32) {
                 // which of the next 32 words are candidates (one ballot instead of 32 broadcast loads)
-                const int64_t k = (w0 + lane) < tile_words ? lk[w0 + lane] : kKeyNone;
+                const int64_t k = (w0 + lane) < tile_words ? __ldcg(lk + w0 + lane) : kKeyNone;
                 uint32_t cand = __ballot_sync(0xFFFFFFFFu, k != kKeyNone && k >= threshold);
                 while (cand) {
                     const int w = w0 + __ffs(int(cand)) - 1;

@@ -16,8 +16,10 @@
 //              is the OR of the rank planes.  Counts are exact integers; the score key is formed once
 //              per offset in the epilogue (after a 32x32 bit transpose) as an int64.
 //
-// Offsets whose best rank is below the K tracked planes are "unresolved": the tile record carries an
-// upper bound for them and k_select sends the tile to the exact kernel only if that bound could win.
+// Offsets whose best rank is below the K tracked planes are "unresolved": in exact mode the warp that owns them
+// settles the few whose upper bound could still win by walking their alignment once (settle_unresolved); in
+// re-score mode the per-word upper estimates go to the finish step (finish_body, psa_finish.cuh), which re-scores
+// every candidate word in the reference's summation order.
 #include "psa_kernels.cuh"
 #include "psa_device.cuh"
 #include "psa_finish.cuh"
@@ -819,7 +821,8 @@ k_combine(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchP
         P.tiles[blockIdx.x] = rec;
     }
     if (FUSE) {
-        // the last block to get here has every tile record (and lane key) of the query in front of it
+        // the last block to get here has every tile record (and lane key) of the query in front of it: the ticket is taken
+        // after this block's stores + __threadfence, and finish_body reads the records with ld.cg (never from L1)
         __shared__ int s_last;
         __syncthreads();                                        // this block's lane keys and record are written
         if (tid == 0) {
@@ -1342,8 +1345,9 @@ int scan_chunk_steps(int, int64_t max_len2)
 // and there are enough (query, tile) tasks that sharing a staged window among the queries of a block pays off
 bool scan_batch_mode(const BatchGeom& G, int64_t max_len2, int sm_count)
 {
-    const int64_t tasks = int64_t(G.nq) * ((G.len1 + 1023) / 1024);
-    return max_len2 <= 1023 && G.last < 0 && tasks >= int64_t(sm_count) * 64;
+    const int64_t tiles = (G.len1 + 1023) / 1024;                   // gridDim.y of k_scan_batch
+    const int64_t tasks = int64_t(G.nq) * tiles;
+    return max_len2 <= 1023 && G.last < 0 && tiles <= 65535 && tasks >= int64_t(sm_count) * 64;
 }
 
 size_t scan_smem_bytes(int rank_planes, int chunk, int warps)

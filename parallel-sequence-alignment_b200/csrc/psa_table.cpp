@@ -15,7 +15,7 @@
 // representable ("exact" mode: integer or dyadic weights, the common case) the two orders are
 // identical.  Otherwise key_slack bounds how far the two can disagree, and every offset whose key
 // is within that window of the best key is re-scored on the device in the reference's own
-// summation order (k_exact_tiles in psa_kernels.cu), so the final order is again the reference's.
+// summation order (finish_body in psa_finish.cuh), so the final order is again the reference's.
 #include "psa_host.h"
 
 #include <algorithm>
@@ -156,6 +156,9 @@ int build_tables(const double* w, int is_max, long long max_len2, psa_pair_table
     double maxabs = 0;
     for (int k = 0; k < 4; k++) maxabs = std::max(maxabs, std::fabs(w[k]));
     const double terms = double(max_len2) + 2.0;   // len2 pair weights + the two weights inside the difference
+    // magnitudes whose sums leave the double range (the reference just produces +-inf scores there) have no
+    // fixed-point image: refuse them instead of deriving a scale from an infinite bound
+    if (!std::isfinite(maxabs * terms) || maxabs * terms > std::ldexp(1.0, 1000)) return PSA_ERR_WEIGHTS;
     int frac = -1;
     for (int j = 0; j <= 60 && frac < 0; j++) {
         bool integral = true;

@@ -33,6 +33,75 @@ def test_reference_mangled_entry_point(psa):
     assert re.search(r" T psa_gpu_run_program$", out, flags=re.M)
 
 
+MANGLED = ["_Z15gpu_run_programP5_dataP7_mutantii", "_Z14get_substituteccPdi", "_Z18get_hashtable_signcc", "_Z10get_weightcPd",
+           "_Z13get_pair_signcc", "_Z11is_swapableP7_mutantS0_ddi", "_Z10strlen_gpuPc"]
+
+
+def test_every_symbol_cpu_funcs_imports_is_exported(psa):
+    """cpu_funcs.o of the reference (built as C++) imports gpu_run_program + six host primitives from cuda_funcs.cu
+    (cuda_funcs.h:33, 44-61).  The library exports all seven under the same mangled names, so cuda_funcs.cu can leave
+    the reference's link altogether; include/cuda_funcs.h declares them."""
+    out = subprocess.run(["nm", "-D", "--defined-only", psa.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for name in MANGLED:
+        assert re.search(r" T %s$" % re.escape(name), out, flags=re.M), name
+    hdr = open(os.path.join(ROOT, "include", "cuda_funcs.h")).read()
+    for fn in ("gpu_run_program", "get_substitute", "get_hashtable_sign", "get_weight", "get_pair_sign", "is_swapable", "strlen_gpu"):
+        assert re.search(r"\b%s\s*\(" % fn, hdr), fn
+    assert "__constant__" not in re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)      # no definitions in the header any more
+    # what the reference's own object file asks for (when the reference is present): nothing else out of cuda_funcs.cu
+    obj = os.path.join(ROOT, "oracle", "_ref", "d2_c_funcs.o")
+    if os.path.exists(obj):
+        und = subprocess.run(["nm", "-u", obj], capture_output=True, text=True, check=True).stdout
+        wanted = set(re.findall(r"\bU (_Z\S+)", und))
+        assert wanted <= set(MANGLED), wanted - set(MANGLED)
+
+
+def test_host_primitives_match_the_reference(psa, ref):
+    """The six exported primitives against the reference's own (compiled from cuda_funcs.cu) on every symbol pair."""
+    import itertools
+    alpha = [chr(65 + i) for i in range(26)] + ["-"]
+    for a, b in itertools.product(alpha, alpha):
+        assert psa.get_hashtable_sign(a, b) == ref.sign(a, b), (a, b)
+    for a, b in itertools.product(alpha + ["a", "*", "[", "@", " "], repeat=2):
+        assert psa.get_pair_sign(a, b) == chr(ref.lib.ref_pair_sign(a.encode(), b.encode())[0]), (a, b)
+    for a in ("a", "[", "@", "*", "1"):                                   # outside A..Z and not '-': no sign (cuda_funcs.cu:428-429)
+        assert psa.get_hashtable_sign(a, "A") == "" == ref.sign(a, "A") and psa.get_hashtable_sign("Q", a) == "" == ref.sign("Q", a)
+    wsets = [[1, 3, 4, 2], [2, 1.5, 1.1, 1.3], [1.5, 2.6, 0.1, 0.2], [0.8, 0.54, 2.6, 13.7], [1, 1, 1, 1], [0, 0, 0, 0], [-1, 2, -3, 0.5]]
+    for w in wsets:
+        for sign in ("*", ":", ".", "_", "", "x"):
+            assert psa.get_weight(sign, w) == ref.weight(sign, w)
+        for is_max in (0, 1):
+            for a, b in itertools.product(alpha, alpha):
+                assert psa.get_substitute(a, b, w, is_max) == ref.substitute(a, b, w, is_max), (w, is_max, a, b)
+    M = psa.Mutant
+    for (o1, c1, o2, c2) in ((5, 1, 5, 1), (5, 1, 4, 9), (4, 9, 5, 1), (5, 2, 5, 1), (5, 1, 5, 2), (-1, -1, 0, 0)):
+        for s1, s2 in ((1.0, 2.0), (2.0, 1.0), (1.5, 1.5), (float("-inf"), 0.0), (float("inf"), float("inf"))):
+            for is_max in (0, 1):
+                assert psa.is_swapable(M(o1, c1, b"A"), M(o2, c2, b"B"), s1, s2, is_max) == ref.is_swapable(o1, c1, o2, c2, s1, s2, is_max)
+    assert psa.strlen_gpu("") == 0 and psa.strlen_gpu("HELLO") == 5 and psa.strlen_gpu("A" * 9999) == 9999
+
+
+def test_reference_cpu_loops_over_our_primitives(tmp_path, input_blocks):
+    """No GPU needed: the reference program linked with NO cuda_funcs.o (oracle/_ref/mpiCudaOpenMP_dropin2, see
+    oracle/Makefile) run with argv[1] = 0 (its OpenMP loop) and -100 (its sequential loop): find_best_mutant_cpu then
+    calls get_hashtable_sign / get_substitute / get_weight / is_swapable / strlen_gpu out of libpsa_b200.so for every
+    pair.  output.txt must be byte-identical to the reference's own answers."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mpiCudaOpenMP_dropin2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mpiCudaOpenMP_dropin2 not built (needs /root/reference)")
+    for k in (1, 2, 3, 5, 7, 8):
+        b = input_blocks[k]
+        d = tmp_path / f"blk{k}"
+        d.mkdir()
+        (d / "input.txt").write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n")
+        e = b["expect"]
+        mut = b["seq2"][: e["char_offset"]] + e["ch"] + b["seq2"][e["char_offset"] + 1:]
+        for argv in ("0", "-100"):
+            p = subprocess.run([exe, argv], cwd=d, capture_output=True, text=True, timeout=300)
+            assert p.returncode == 0, (k, argv, p.stderr[-300:])
+            assert (d / "output.txt").read_text() == "%s\n%d %s" % (mut, e["offset"], e["score_g"]), (k, argv)
+
+
 def test_library_contains_sm100a_code_only(psa):
     out = subprocess.run(["cuobjdump", "-lelf", psa.LIB_PATH], capture_output=True, text=True)
     if out.returncode != 0:

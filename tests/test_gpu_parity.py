@@ -215,27 +215,63 @@ def test_config4_long_seq1(ctx, port, synth):
     assert same_answer(r2, port.search([1, 3, 4, 2], False, wl.seq1, wl.queries[0], nthreads=8))
 
 
-def test_multi_gpu_single_process(psa, port, synth):
-    """One process driving every visible GPU (the replacement of the reference's MPI ranks): offset ranges of
-    one query and query blocks of a batch must give the single-GPU / oracle answer.  Needs >= 2 GPUs."""
-    n = psa.device_count()
-    if n < 2:
-        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+def _multi_device_body(psa, port, synth, devices):
+    """Offset ranges of one query and query blocks of a batch over the devices of ONE context must give the
+    single-GPU / oracle answer: worker threads (one per extra device), per-device shards with their halo, and the
+    host merge of the per-device candidates all run here."""
     s1 = synth.letters(61, 200_000)
     s2 = synth.letters(62, 1500)
     qs = [synth.letters(70 + k, 64 + 8 * k) for k in range(97)]
-    with psa.Context(ngpus=n) as c:
+    eq = [synth.letters(170 + k, 200) for k in range(300)]                # equal lengths: packed / batch mode per device
+    with psa.Context(devices=devices) as c:
+        assert c.ngpus == len(devices)
         for w, is_max in (([1, 3, 4, 2], False), ([2, 1.5, 1.1, 1.3], True), ([1, 1, 1, 1], True)):
             r = c.search(w, is_max, s1, s2)
             assert same_answer(r, port.search(w, is_max, s1, s2, nthreads=8)), (w, is_max)
             got = c.search_batch(w, is_max, s1[:20000], qs)
             exp = port.search_batch(w, is_max, s1[:20000], qs)
             assert all(same_answer(g, e) for g, e in zip(got, exp)), (w, is_max)
-        # planted ties across the GPU boundary: the lowest offset must win wherever the split falls
+            got = c.search_batch(w, is_max, s1[:3000], eq)
+            exp = port.search_batch(w, is_max, s1[:3000], eq)
+            assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp)), (w, is_max)
+        # an explicit offset range is split too (the gpu_run_program contract on a multi-device context)
+        r = c.search_range([1, 3, 4, 2], True, s1, s2, 777, 150_001)
+        assert same_answer(r, port.search([1, 3, 4, 2], True, s1, s2, 777, 150_001, nthreads=8))
+        # fewer queries than devices: the surplus devices stay idle
+        got = c.search_batch([1, 3, 4, 2], False, s1[:5000], qs[:3])
+        assert all(same_answer(g, e) for g, e in zip(got, port.search_batch([1, 3, 4, 2], False, s1[:5000], qs[:3])))
+        # planted ties across the device boundary: the lowest offset must win wherever the split falls
         core = synth.letters(63, 700)
         tied = synth.letters(64, 50_000) + core + synth.letters(65, 80_000) + core + synth.letters(66, 30_000)
         r = c.search([1, 3, 4, 2], True, tied, core)
         assert r.offset == 50_000 and same_answer(r, port.search([1, 3, 4, 2], True, tied, core, nthreads=8))
+        # split-phase form on several devices
+        b = psa.Batch(s1[:3000], eq)
+        c.prepare([1, 3, 4, 2], True, b)
+        assert c.run() > 0
+        exp = port.search_batch([1, 3, 4, 2], True, s1[:3000], eq)
+        assert all(same_answer(g, e) for g, e in zip(c.fetch(), exp))
+        # a bad symbol on a shard that is not the first device's
+        with pytest.raises(psa.PsaError) as e:
+            c.search_batch([1, 3, 4, 2], True, s1[:3000], eq[:-1] + [b"AB?D" * 50])
+        assert e.value.status == psa.PSA_ERR_ALPHABET
+        assert same_answer(c.search([1, 3, 4, 2], True, s1[:3000], eq[0]), exp[0])
+
+
+@pytest.mark.parametrize("copies", [2, 3, 8])
+def test_multi_device_context_on_one_gpu(psa, port, synth, copies):
+    """The north_star split (one process, (query | offset range) shards over the context's devices, host merge) with the
+    SAME ordinal repeated: every device slot has its own stream, buffers and worker thread, so the whole multi-device
+    path -- psa_plan_shards, the per-shard copies, the concurrent enqueue and psa_merge_results -- runs on a 1-GPU box."""
+    _multi_device_body(psa, port, synth, [0] * copies)
+
+
+def test_multi_gpu_single_process(psa, port, synth):
+    """The same on every visible GPU (the replacement of the reference's MPI ranks).  Needs >= 2 GPUs."""
+    n = psa.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    _multi_device_body(psa, port, synth, list(range(n)))
 
 
 def test_all_stacked_blocks(psa, ctx, tmp_path, input_blocks):
@@ -492,4 +528,27 @@ def test_reference_program_links_against_the_library(tmp_path, input_blocks):
             p = subprocess.run([exe] + argv, cwd=d, capture_output=True, text=True, timeout=120)
             assert p.returncode == 0, (k, argv, p.stderr[-500:])
             assert "CUDA percentage set to 100" in p.stdout, (k, argv, p.stdout)
+            assert (d / "output.txt").read_text() == "%s\n%d %s" % (mut, e["offset"], e["score_g"]), (k, argv)
+
+
+def test_reference_program_links_with_no_reference_cuda_file(tmp_path, input_blocks):
+    """The full drop-in: main.c + cpu_funcs.c + mpi_funcs.c of the reference compiled against OUR
+    include/cuda_funcs.h and linked against libpsa_b200.so only -- no reference cuda_funcs.o in the link; gpu_run_program
+    AND the six host primitives of cuda_funcs.h:44-61 resolve to the library.  output.txt must be byte-identical to the
+    reference's own answer for all offsets on the GPU (100), all on the reference's OpenMP loop (0) and its sequential
+    loop (-100) -- the CPU loops then run the reference's find_best_mutant_cpu over our primitives."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "mpiCudaOpenMP_dropin2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mpiCudaOpenMP_dropin2 not built (needs /root/reference)")
+    for k, b in enumerate(input_blocks):
+        d = tmp_path / f"blk{k}"
+        d.mkdir()
+        (d / "input.txt").write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n")
+        e = b["expect"]
+        mut = b["seq2"][: e["char_offset"]] + e["ch"] + b["seq2"][e["char_offset"] + 1:]
+        for argv in (["100"], ["0"], ["-100"]) if k in (1, 2, 3, 5, 7, 8, 9) else (["100"],):
+            p = subprocess.run([exe] + argv, cwd=d, capture_output=True, text=True, timeout=300)
+            assert p.returncode == 0, (k, argv, p.stderr[-500:])
             assert (d / "output.txt").read_text() == "%s\n%d %s" % (mut, e["offset"], e["score_g"]), (k, argv)
