@@ -93,6 +93,10 @@ const char* psa_last_error(const psa_context* ctx);
      "rank_planes"   -1 auto | 0,1,2,4 rank bit planes tracked by the scan (the rest is settled in-kernel)
      "scan_warps"    0 auto | 1..4 warps (x1024 offsets) per scan block in long mode
      "batch_mode"    -1 auto | 0 never | 1 whenever every query fits one window (len2 <= 1023)
+     "stripe_mode"   -1 auto | 0 never | 1 whenever the batch qualifies: equal-length queries (len2 <= 1023), exact integer
+                     order with small keys, all offsets, window within shared memory.  Then ONE kernel does everything:
+                     each persistent block builds a striped bit-plane window of Seq1 in shared memory and its warp teams
+                     scan and finish their queries against it (no k_profile / k_finish launch)
      "slices"        0 auto | 1 never | n>=2 cut a single query into n ranges of alignment steps
      "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
      "fused_finish"  1 the finish step runs inside the kernel before it where that saves a launch: in the scan block when
@@ -106,7 +110,9 @@ const char* psa_last_error(const psa_context* ctx);
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
-   order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact".
+   order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact",
+   "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", and the host-side split of the
+   last psa_search_batch in ns: "host_plan_ns", "host_prepare_ns", "host_enqueue_ns", "host_wait_ns", "host_total_ns".
    Unknown -> -1. */
 long long psa_get_stat(const psa_context* ctx, const char* name);
 
@@ -138,6 +144,12 @@ int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards,
    `force` = 0 picks the shape with the fewest idle lanes and requires >= 5 % over whole warps per query;
    2..8 forces that many queries per block when it fits.  Pure host arithmetic. */
 int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* queries_per_block, int* warps);
+
+/* The launch shape of stripe mode (one launch per batch) for `nq` queries of `len2` symbols against
+   `len1` on a GPU with `sm_count` SMs; rank_pass = 1 when a rank bit plane has to be read (the top rank is not derivable
+   from the sign classes).  shape[] = { applies (0/1), lanes per query S = ceil(offsets / 32), queries per task, warp
+   passes per task, warps per team, teams per block, blocks, dynamic shared memory in bytes }.  Pure host arithmetic. */
+int psa_plan_stripes(int64_t len1, int64_t len2, int32_t nq, int rank_pass, int sm_count, int shape[8]);
 
 /* Merge per-shard answers of ONE query given in ascending offset-range order, under the reference
    order: strictly better score wins, ties keep the earlier shard = lower offsets

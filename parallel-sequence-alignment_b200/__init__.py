@@ -125,6 +125,7 @@ def _sig():
                                      C.POINTER(_CShard)]
     _lib.psa_merge_results.argtypes = [C.c_int, C.POINTER(_CResult), C.c_int, C.POINTER(_CResult)]
     _lib.psa_plan_packing.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib.psa_plan_stripes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_int)]
     batch = [C.c_void_p, dp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     _lib.psa_search_batch.argtypes = batch + [C.POINTER(_CResult)]
     _lib.psa_batch_prepare.argtypes = batch
@@ -224,6 +225,15 @@ def plan_packing(len1: int, len2: int, nq: int, force: int = 0):
     if rc:
         raise PsaError(rc, "psa_plan_packing")
     return q.value, w.value
+
+
+def plan_stripes(len1: int, len2: int, nq: int, rank_pass: bool = False, sm_count: int = 148) -> dict:
+    """Launch shape of stripe mode (host only, no GPU needed); {"ok": 0, ...} when the mode does not apply."""
+    shape = (C.c_int * 8)()
+    rc = _lib.psa_plan_stripes(len1, len2, nq, int(bool(rank_pass)), sm_count, shape)
+    if rc:
+        raise PsaError(rc, "psa_plan_stripes")
+    return dict(zip(("ok", "lanes", "queries_per_task", "passes", "team_warps", "teams", "blocks", "smem_bytes"), list(shape)))
 
 
 def merge_results(is_max: bool, parts: Sequence[Result]) -> Result:

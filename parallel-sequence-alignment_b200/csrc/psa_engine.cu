@@ -52,6 +52,7 @@ struct DeviceState {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
     DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table;
     SliceGeom SG{};
+    StripeGeom stripe{};       // ok != 0: this shard runs in stripe mode (one launch: window + scan + finish)
     PinBuf h_qoff, h_tile_start, h_out;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
@@ -59,6 +60,7 @@ struct DeviceState {
     BatchPtrs P{};
     bool active = false;
     long long st_launches = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
+    long long st_prepare_ns = 0, st_enqueue_ns = 0, st_wait_ns = 0;   // host time of the last one-shot search on this GPU's thread
     int32_t* h_err = nullptr;  // mapped page-locked word the kernels write the run's tag into on a bad symbol (no copy, no memset)
     int32_t run_tag = 0;
     long long table_epoch = -1;   // ctx->table_epoch whose pair table is in code_table
@@ -100,6 +102,7 @@ struct psa_context {
     int opt_slices = 0;        // 0 auto, 1 never cut a query along its alignment steps, n >= 2: ask for n slices
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
     int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
+    int opt_stripe_mode = -1;  // -1 auto, 0 never, 1 whenever the batch qualifies (equal lengths, exact order, window fits)
     // current batch
     bool prepared = false, ran = false;
     bool range_split = false;  // single query split by offset range over the GPUs
@@ -115,6 +118,7 @@ struct psa_context {
     bool batch_mode = false;     // scan engine: queries share staged windows (k_scan_batch)
     int64_t max_len2 = 0;
     int64_t uniform_len2 = 0;    // > 0: all queries of the batch have this length
+    long long st_plan_ns = 0, st_total_ns = 0;   // host time of the last one-shot search: planning / the whole call
     const char* in_seq1 = nullptr;       // the caller's buffers of the batch being prepared (read by the per-GPU copies)
     const char* in_seq2s = nullptr;
     const int64_t* in_qoff = nullptr;
@@ -319,6 +323,15 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         psa_plan_packing(len1, ctx->uniform_len2, nq, ctx->opt_pack_queries >= 2 ? ctx->opt_pack_queries : 0, &d.SG.pack_q,
                          &d.SG.pack_warps);
 
+    // Stripe mode: equal-length queries, exact integer order, all offsets, window fits shared memory -> one launch
+    d.stripe = StripeGeom{};
+    if (scan && uniform_len && last < 0 && ctx->table.exact && ctx->rank_planes <= 1 && ctx->opt_stripe_mode != 0 &&
+        ctx->opt_sliced_keys != 0 && stripe_keys_ok(ctx->table, ctx->uniform_len2) && (nq >= 2 || ctx->opt_stripe_mode == 1)) {
+        const bool rank_pass = ctx->rank_planes == 1 && !stripe_derives_rank(ctx->table, ctx->rank_planes, ctx->opt_derive_rank != 0);
+        d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass, d.sm_count, ctx->opt_stripe_mode == 1);
+        if (d.stripe.ok) { d.SG.fused_finish = false; d.SG.fused_combine = false; d.SG.pack_q = d.SG.pack_warps = 0; }
+    }
+
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
     if (d.table_epoch != ctx->table_epoch) {
@@ -399,6 +412,16 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     d.P.run_tag = next_run_tag(d);
+    if (ctx->engine == 2 && d.stripe.ok) {
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
+        launch_stripe(ctx->table, d.G, d.P, ctx->rank_planes, ctx->opt_derive_rank != 0, d.stripe, d.stream);
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
+        d.st_launches += 1;
+        PSA_CUDA(ctx, cudaGetLastError());
+        if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+        d.st_tiles += d.G.total_tiles;
+        return PSA_OK;
+    }
     if (ctx->engine == 2) {
         launch_profile(ctx->table, d.G, d.P, ctx->rank_planes, d.sm_count, d.stream);
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
@@ -537,6 +560,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "stripe_mode") && value >= -1 && value <= 1) { ctx->opt_stripe_mode = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
     return PSA_ERR_ARG;
 }
@@ -550,6 +574,16 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
         main_ns = std::max(main_ns, d.st_main_ns);
     }
     if (!std::strcmp(name, "kernel_launches")) return launches;
+    // host-side split of the last psa_search_batch (ns): planning on the calling thread, then per device slot (max over
+    // slots) H2D enqueue, kernel launches, and the wait for the stream + results
+    if (!std::strcmp(name, "host_plan_ns")) return ctx->st_plan_ns;
+    if (!std::strcmp(name, "host_total_ns")) return ctx->st_total_ns;
+    if (!std::strcmp(name, "host_prepare_ns") || !std::strcmp(name, "host_enqueue_ns") || !std::strcmp(name, "host_wait_ns")) {
+        long long worst = 0;
+        for (const DeviceState& d : ctx->devs)
+            if (d.active) worst = std::max(worst, name[5] == 'p' ? d.st_prepare_ns : name[5] == 'e' ? d.st_enqueue_ns : d.st_wait_ns);
+        return worst;
+    }
     if (!std::strcmp(name, "candidate_tiles")) {
         // a statistic nobody waits for: the counter stays on the device and is read only when asked
         long long cand = 0;
@@ -567,7 +601,13 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "engine")) return ctx->engine;
     if (!std::strcmp(name, "rank_planes")) return ctx->rank_planes;
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
-    if (!std::strcmp(name, "batch_mode")) return ctx->batch_mode ? 1 : 0;
+    auto first_active = [ctx]() -> const DeviceState* { for (const DeviceState& d : ctx->devs) if (d.active) return &d; return nullptr; };
+    if (!std::strcmp(name, "stripe_mode")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? 1 : 0; }
+    if (!std::strcmp(name, "stripe_queries_per_task")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.Q : 0; }
+    if (!std::strcmp(name, "stripe_team_warps")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.T : 0; }
+    if (!std::strcmp(name, "stripe_teams")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.teams : 0; }
+    if (!std::strcmp(name, "stripe_lanes")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.S : 0; }
+    if (!std::strcmp(name, "batch_mode")) { const DeviceState* d = first_active(); return ctx->batch_mode && !(d && d->stripe.ok) ? 1 : 0; }
     if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.slices; return 1; }
     if (!std::strcmp(name, "packed_queries")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_q; return 0; }
     if (!std::strcmp(name, "packed_warps")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_warps; return 0; }
@@ -603,6 +643,15 @@ int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* que
     return PSA_OK;
 }
 
+int psa_plan_stripes(int64_t len1, int64_t len2, int32_t nq, int rank_pass, int sm_count, int shape[8])
+{
+    if (!shape || len1 < 1 || len2 < 1 || len2 > len1 || nq < 0 || sm_count < 1) return PSA_ERR_ARG;
+    const StripeGeom g = stripe_plan(len1, len2, nq, rank_pass != 0, sm_count);
+    const int v[8] = { g.ok, g.S, g.Q, g.passes, g.T, g.teams, g.blocks, int(g.smem) };
+    for (int k = 0; k < 8; k++) shape[k] = v[k];
+    return PSA_OK;
+}
+
 int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards, int64_t granule,
                     int64_t first, int64_t last, psa_shard* out)
 {
@@ -633,20 +682,43 @@ int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards,
         out[0].q_begin = 0; out[0].q_end = nq;
         return PSA_OK;
     }
-    std::vector<double> work(nq + 1, 0.0);
+    // one pass: validate, total work, and whether every query has the same length (then the balanced split is arithmetic
+    // -- a batch of 65 536 equal-length queries must not pay for a prefix-sum array on every call)
+    const int64_t len_first = q_off[1] - q_off[0];
+    bool uniform = true;
+    double total = 0.0;
     for (int q = 0; q < nq; q++) {
         const int64_t len2 = q_off[q + 1] - q_off[q];
         if (len2 < 1 || len2 > len1) return PSA_ERR_ARG;
-        work[q + 1] = work[q] + double(offsets_of(len1, len2)) * double(len2);
+        uniform = uniform && len2 == len_first;
+        total += double(offsets_of(len1, len2)) * double(len2);
     }
-    int qb = 0;
+    if (uniform) {
+        for (int g = 0; g < nshards; g++) {
+            out[g].q_begin = int32_t(int64_t(nq) * g / nshards);
+            out[g].q_end = int32_t(int64_t(nq) * (g + 1) / nshards);
+        }
+        return PSA_OK;
+    }
+    // ragged: walk the running sum once more; a shard ends at the query boundary nearest to its share of the work
+    int qb = 0, q = 0;
+    double done = 0.0;                               // work of queries [0, q)
     for (int g = 0; g < nshards; g++) {
         int qe;
         if (g == nshards - 1) qe = nq;
         else {
-            const double target = work[nq] * double(g + 1) / double(nshards);
-            qe = int(std::lower_bound(work.begin(), work.end(), target) - work.begin());
-            if (qe > 0 && target - work[qe - 1] < work[std::min(qe, nq)] - target) qe--;     // nearest boundary
+            const double target = total * double(g + 1) / double(nshards);
+            double next = done;
+            while (q < nq) {
+                const int64_t len2 = q_off[q + 1] - q_off[q];
+                next = done + double(offsets_of(len1, len2)) * double(len2);
+                if (next >= target) break;
+                done = next;
+                q++;
+            }
+            // boundary q (work `done` before it) or q + 1 (work `next`), whichever is nearer to the target
+            qe = q;
+            if (q < nq && next - target <= target - done) { qe = q + 1; done = next; q++; }
             qe = std::max(qb, std::min(qe, nq));
         }
         out[g].q_begin = qb; out[g].q_end = qe;
@@ -879,6 +951,9 @@ static int search_prepared(psa_context* ctx, psa_result* out)
     const bool direct = result_array_is_pinned(ctx, out);
     ctx->one_shot = true;
     int rc = for_each_device(ctx, [ctx, out, direct](DeviceState& d) {
+        using clk = std::chrono::steady_clock;
+        auto ns = [](clk::time_point a, clk::time_point b) { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+        const auto t0 = clk::now();
         int r = prepare_shard(ctx, d);
         if (!r && d.active && d.zc_out && direct) {                 // the caller's array is page-locked: write it in place
             if (void* dv = device_view_of(out + d.q_begin)) {
@@ -886,8 +961,12 @@ static int search_prepared(psa_context* ctx, psa_result* out)
                 d.zc_direct = true;
             }
         }
+        const auto t1 = clk::now();
         if (!r) r = run_device(ctx, d, false);
+        const auto t2 = clk::now();
         if (!r) r = fetch_shard(ctx, d, out, direct);
+        const auto t3 = clk::now();
+        d.st_prepare_ns = ns(t0, t1); d.st_enqueue_ns = ns(t1, t2); d.st_wait_ns = ns(t2, t3);
         if (d.zc_direct) {                                          // the caller's array is theirs again: a later
             d.P.out = (QueryRec*)d.h_out.p;                         // psa_batch_run on this batch writes the staging buffer
             d.zc_direct = false;
@@ -907,10 +986,16 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, cons
     if (rc) return rc;
     const auto t1 = std::chrono::steady_clock::now();
     rc = search_prepared(ctx, out);
+    const auto t2 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    ctx->st_plan_ns = (long long)(us(t0, t1) * 1e3);
+    ctx->st_total_ns = (long long)(us(t0, t2) * 1e3);
     if (trace) {
-        const auto t2 = std::chrono::steady_clock::now();
-        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
         std::fprintf(stderr, "[psa] host planning %.1f us, copies + kernels + copy back %.1f us\n", us(t0, t1), us(t1, t2));
+        for (const DeviceState& d : ctx->devs)
+            if (d.active)
+                std::fprintf(stderr, "[psa]   slot %d (cuda:%d): prepare + H2D enqueue %.1f us, launches %.1f us, wait + results %.1f us\n",
+                             int(&d - ctx->devs.data()), d.dev, d.st_prepare_ns * 1e-3, d.st_enqueue_ns * 1e-3, d.st_wait_ns * 1e-3);
     }
     return rc;
 }

@@ -59,6 +59,35 @@ constexpr int kPackMaxWarps = 8;    //   and warps per block
 // packed mode: does one window hold every offset of a (len1, len2) query, inside the plane buffer?
 bool scan_packed_fits(int64_t len1, int64_t len2);
 
+// Stripe mode (psa_stripe.cu): equal-length queries against a striped window that one persistent block per SM builds
+// in shared memory -- the whole batch in one launch.
+struct StripeGeom {
+    int ok = 0;          // 0: stripe mode does not apply to this batch
+    int S = 0;           // lanes per query = ceil(offsets / 32); bit t of lane l is offset l + t * S
+    int steps = 0;       // len2 rounded up to a multiple of 32
+    int Wn = 0;          // words per window row = S + steps
+    int Q = 0;           // queries per task
+    int passes = 0;      // warp passes per task = ceil(Q * S / 32)
+    int T = 0;           // warps per team (a team owns a task)
+    int teams = 0;       // teams per block
+    int ntasks = 0;
+    int ro_stride = 0;   // words between the row-offset vectors of two queries of a task
+    int blocks = 0;
+    size_t smem = 0;
+};
+constexpr int kStripeThreads = 640;                 // 20 warps, one block per SM (<= 96 registers per thread)
+constexpr int kStripeMaxQ = 32;                     // queries per task
+constexpr int kStripeMaxPasses = 64;                // passes per task
+constexpr size_t kStripeSmemMax = 224 * 1024;        // of the 227 KB a block may have (a little static shared memory on top)
+StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, int sm_count, bool force = false);
+// does the scan take the top-rank bit from the class counts (no rank plane read) for this table / plane count?
+bool stripe_derives_rank(const DeviceTable& T, int rank_planes, bool allow_derive);
+bool stripe_keys_ok(const DeviceTable& T, int64_t len2);     // the bit-sliced key epilogue applies (required by stripe mode)
+void launch_stripe(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, bool allow_derive,
+                   const StripeGeom& SG, cudaStream_t stream);
+// bit-sliced key epilogue: plane count for this table and query length (0 = keys too wide), and the bias that makes keys non-negative
+int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int nb, int64_t* bias_out);
+
 // ---- launchers (all asynchronous on `stream`) -------------------------------------------------
 // exact scalar kernel over every tile (engine 1)
 void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream);

@@ -1,0 +1,631 @@
+// psa_stripe.cu -- stripe mode: the whole batch in ONE launch (sm_100a).
+//
+// For a batch of equal-length queries whose striped window fits shared memory, this kernel replaces the chain
+// k_profile -> k_scan_packed | k_scan_batch -> k_finish (psa_scan.cu, psa_kernels.cu), i.e. everything the reference does
+// in fill_hashtable_gpu + calc_mutants_scores + reduction x2 (cuda_funcs.cu:149-278) per query.
+//
+// Striped bit planes.  A lane still owns 32 offsets as the 32 bits of a register, but they are S apart instead of
+// adjacent: lane l of a query (l < S = ceil(offsets / 32)) holds offsets l, l + S, l + 2S, ...  Word p of plane row r is
+// built so that bit t = fact about (row symbol r, Seq1[p + t*S]); alignment step i of lane l then needs exactly ONE
+// aligned shared-memory word, W[r][l + i] -- no second word and no funnel shift (the linear layout of psa_scan.cu pays
+// 2 loads + 1 SHF per plane per step: 62 of its 327 ALU instructions per 32 steps, and twice the shared-memory traffic).
+// The window has S + steps words per row instead of len1 / 32 (positions repeat across words), which is why it only
+// pays when it can stay resident: one persistent block per SM builds the window ONCE, straight from Seq1 (a 32x32 bit
+// transpose per word and plane kind, as k_profile does for the linear layout), and then serves many queries from it.
+//
+// Work decomposition.  A task is Q consecutive queries = Q*S lanes laid end to end = ceil(Q*S/32) passes of one warp
+// (config 3: S = 79, Q = 2 -> 5 passes, 158 of 160 lanes busy; config 5: S = 311, Q = 1 -> 10 passes).  A team of T warps
+// owns a task (its passes go round the team's warps); a block holds as many teams as fit 20 warps and each team walks
+// its own list of tasks, so teams drift apart and one team's set-up or epilogue overlaps another team's counting --
+// there is no block-wide barrier after the window is built.  Per-(pass, query) bests meet in shared-memory slots, and
+// the team's warps then finish one query each (sign counts, first position of the best rank, letter, score).
+#include "psa_kernels.cuh"
+#include "psa_device.cuh"
+#include "psa_bitslice.h"
+#include "psa_scan_core.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+namespace psa {
+
+#if defined(PSA_STRIPE_TRACE)
+// Debug build only (make EXTRA=-DPSA_STRIPE_TRACE): per block, SM clock at the phase boundaries of k_stripe as seen by
+// warp 0 (tools/stripe_trace.py prints them).  Not compiled into the product.
+__device__ long long g_stripe_trace[256][10];
+#define PSA_TRACE_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_stripe_trace[blockIdx.x][k] = clock64(); } while (0)
+extern "C" int psa_debug_stripe_trace(long long* out, int blocks)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_stripe_trace, sizeof(long long) * 10 * (blocks < 256 ? blocks : 256));
+}
+#else
+#define PSA_TRACE_MARK(k) ((void)0)
+#endif
+
+namespace {
+
+// One group = 32 alignment steps on striped planes.
+//   pw : s_cls + l * 8 (this lane's word for step 0 of the query, row 0)
+//   ro : 32 byte offsets (row * Wn * 8 + step * 8), one per step; the same for every lane of a query
+template <int NUP>
+__device__ __forceinline__ void stripe_class_group(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, const char* pw,
+                                                   const uint32_t* ro)
+{
+    uint32_t pa[5], pb[5], pn[5];
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s4 + u;
+            const uint2 x = *reinterpret_cast<const uint2*>(pw + offs[u]);
+            vc_feed(A, pa, x.x, s);
+            vc_feed(B, pb, x.y, s);
+            vc_feed(C, pn, x.x & x.y, s);
+        }
+    }
+}
+
+//   pr : s_rnk + l * 4;  ro : byte offsets (row * Wn * 4 + step * 4)
+__device__ __forceinline__ void stripe_rank_group(uint32_t& racc, const char* pr, const uint32_t* ro)
+{
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        racc |= *reinterpret_cast<const uint32_t*>(pr + o4.x);
+        racc |= *reinterpret_cast<const uint32_t*>(pr + o4.y);
+        racc |= *reinterpret_cast<const uint32_t*>(pr + o4.z);
+        racc |= *reinterpret_cast<const uint32_t*>(pr + o4.w);
+    }
+}
+
+// bytes of the Seq1 symbol area: the window build gathers positions up to (Wn - 1) + 31 S (rounded up to whole 16-byte stores)
+__host__ __device__ inline int stripe_seq1_span(const StripeGeom& g) { return (g.Wn + 31 * g.S + 16 + 15) & ~15; }
+
+__device__ __forceinline__ void team_sync(int team, int team_threads)
+{
+    if (team_threads == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_threads) : "memory");
+}
+
+// bits t of lane l whose offset l + t*S is a real offset (< noff)
+__device__ __forceinline__ uint32_t stripe_valid_mask(int l, int S, int64_t noff)
+{
+    if (l >= noff) return 0u;
+    const int64_t cnt = (noff - l + S - 1) / S;
+    return cnt >= 32 ? 0xFFFFFFFFu : ((1u << int(cnt)) - 1u);
+}
+
+// What a pass leaves per query segment: the segment's best (key, offset) and -- so that the finish step need not walk the
+// alignment again -- the winner's vertical counters read out at its bit, and whether it met the top rank.
+struct StripeSlot {
+    int64_t key;
+    int32_t off;
+    uint32_t top;           // 1: the winner's best rank is the top rank (nranks)
+    uint32_t na, nb, nc;    // N(b0), N(b1), N(b0 & b1) at the winning offset
+    uint32_t pad;
+};
+
+// The finish step of one query by one warp (what finish_query_warp does for the linear kernels): sign counts, first
+// position carrying the best rank, replacement letter and score of the winning offset.  Seq1 symbols and the pair table
+// come from shared memory (the block staged both for the window), so the only global round trip is the query itself.
+__device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_seq1, const uint8_t* s_code,
+                                                    int q, int64_t qbeg, int len2, const StripeSlot& w)
+{
+    const int lane = threadIdx.x & 31;
+    const Cand r{ w.key, w.off };
+    QueryRec out;
+    out.score = T.is_max ? -INFINITY : INFINITY;
+    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
+    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
+    if (r.key == kKeyNone) {
+        if (lane == 0) P.out[q] = out;
+        return;
+    }
+    if (w.top) {
+        // The usual case: the winner met the top rank, and its sign-class counts came with the slot.  All that is left is
+        // the FIRST position carrying that rank (strict compare in the reference, cpu_funcs.c:287-294) -- 32 positions per
+        // round, normally found in the first round or two -- and the replacement letter there.
+        const uint8_t* a = s_seq1 + r.off;
+        const uint8_t* b = P.seq2s + qbeg;
+        const uint32_t want = uint32_t(T.nranks);
+        int found = -1;
+        uint8_t nxt = lane < len2 ? b[lane] : uint8_t('A');
+        for (int base = 0; base < len2 && found < 0; base += 32) {
+            const uint8_t cur = nxt;
+            if (base + 32 + lane < len2) nxt = b[base + 32 + lane];
+            const int i = base + lane;
+            bool hit = false;
+            if (i < len2) {
+                uint32_t c1 = a[i], c2 = symbol_of(cur);
+                if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+                hit = (uint32_t(s_code[c2 * kRowPad + c1]) >> 2) == want;
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (m) found = base + __ffs(int(m)) - 1;
+        }
+        PSA_CHECK(found >= 0);
+        if (lane == 0 && found >= 0) {
+            uint32_t c1 = a[found], c2 = symbol_of(b[found]);
+            if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+            const int64_t n1 = int64_t(w.na) - w.nc, n2 = int64_t(w.nb) - w.nc, n3 = w.nc;
+            out.offset = r.off;
+            out.char_offset = found;
+            out.ch = T.sub[c2][c1];
+            out.rank = int(want);
+            out.counts[0] = len2 - n1 - n2 - n3; out.counts[1] = n1; out.counts[2] = n2; out.counts[3] = n3;
+            double sc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) sc = __dadd_rn(sc, __dmul_rn(double(out.counts[c]), T.wcls[c]));     // exact (psa_table.cpp)
+            out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[want]), 0.0);
+            P.out[q] = out;
+        }
+        if (found >= 0) return;
+    }
+    const uint8_t* a = s_seq1 + r.off;
+    const uint8_t* b = P.seq2s + qbeg;
+    int cnt[4] = { 0, 0, 0, 0 };
+    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
+    for (int base = lane; base < len2; base += 8 * 32) {
+        uint8_t vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) vb[u] = (base + u * 32) < len2 ? b[base + u * 32] : uint8_t('A');
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = base + u * 32;
+            if (i < len2) {
+                uint32_t c1 = a[i], c2 = symbol_of(vb[u]);
+                if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }                           // a bad symbol: the batch is rejected anyway
+                const uint32_t code = s_code[c2 * kRowPad + c1];
+                cnt[code & 3u]++;
+                const unsigned long long pp = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
+                pos = pp > pos ? pp : pos;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
+        pos = o > pos ? o : pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
+    }
+    if (lane == 0) {
+        const int rank = int(pos >> 32);
+        const int i = int(~uint32_t(pos));
+        uint32_t c1 = a[i], c2 = symbol_of(b[i]);
+        if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+        out.offset = r.off;
+        out.char_offset = i;
+        out.ch = T.sub[c2][c1];
+        out.rank = rank;
+        double sc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            out.counts[c] = cnt[c];
+            sc = __dadd_rn(sc, __dmul_rn(double(cnt[c]), T.wcls[c]));          // exact (psa_table.cpp), same as k_finish
+        }
+        out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
+        if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
+        P.out[q] = out;
+    }
+}
+
+// NB : counter planes (len2 < 2^NB), RANKPASS : a rank plane is read (K = 1 and the top rank is not derivable),
+// K : rank planes tracked (0 or 1), DR : top-rank bit derived from the class counts; keys are always bit-sliced
+template <int NB, int K, bool DR>
+__global__ void __launch_bounds__(kStripeThreads, 1)
+k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const int key_planes,
+         const int64_t key_bias)
+{
+    constexpr int NUP = NB - 5;
+    constexpr bool kRankPass = K > 0 && !DR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Wn = SG.Wn, S = SG.S, steps = SG.steps;
+    unsigned char* s_cls = smem;                                                            // uint2 [28][Wn]
+    unsigned char* s_rnk = s_cls + size_t(kPlaneRows) * Wn * 8;                             // uint32 [28][Wn]
+    unsigned char* s_seq1 = s_rnk + (kRankPass ? size_t(kPlaneRows) * Wn * 4 : 0);          // symbols of Seq1
+    const int seq1_span = stripe_seq1_span(SG);                                             // every position the build gathers
+    uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_seq1 + seq1_span);
+    const int ro_team = SG.Q * SG.ro_stride;                                                // words per team (class offsets)
+    uint32_t* s_ror_all = s_ro_all + size_t(SG.teams) * ro_team;                            // rank offsets (kRankPass)
+    StripeSlot* s_slot_all = reinterpret_cast<StripeSlot*>(s_ror_all + (kRankPass ? size_t(SG.teams) * ro_team : 0));
+    const int slots_team = SG.T * SG.Q;                                                     // [warp of the team][query of the task]
+    __shared__ uint32_t s_col[3][32];
+    __shared__ __align__(16) uint8_t s_code[kSymbols * kRowPad];                            // the pair table, for the finish step
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    const int len2 = G.uniform_len2;
+    const int64_t noff = G.len1 - len2 + 1;
+    PSA_CHECK(len2 > 0 && G.last < 0 && S * 32 >= noff && steps >= len2 && Wn >= S + steps && SG.T * SG.teams * 32 <= nthreads);
+
+    PSA_TRACE_MARK(0);
+    if (blockIdx.x == 0 && tid == 0) { P.cand_count[0] = 0; P.cand_count[2] = 0; }          // statistics of the run (nothing is re-scored here)
+
+    // ---- teams ---------------------------------------------------------------------------------------------
+    const int team = warp / SG.T, tw = warp - team * SG.T;
+    const int team_threads = SG.T * 32;
+    uint32_t* s_ro = s_ro_all + size_t(team) * ro_team;
+    uint32_t* s_ror = s_ror_all + size_t(team) * ro_team;
+    StripeSlot* s_slot = s_slot_all + size_t(team) * slots_team;
+    const Cand none{ kKeyNone, 0x7FFFFFFF };
+    const int groups = steps >> 5;
+    const int task_stride = SG.teams * int(gridDim.x);
+    const int first_task = team * int(gridDim.x) + int(blockIdx.x);
+
+    // Per-step row offsets of a task's queries (needs nothing but the queries): a warp of the team takes whole queries, its
+    // lanes stride the steps; the byte loads of a query are issued together, padding steps read the all-zero row.
+    auto build_row_offsets = [&](int task) {
+        const int q0 = task * SG.Q;
+        const int nqt = (G.nq - q0) < SG.Q ? (G.nq - q0) : SG.Q;
+        bool bad = false;
+        for (int jj = tw; jj < nqt; jj += SG.T) {
+            const uint8_t* src = P.seq2s + int64_t(q0 + jj) * len2;
+            uint32_t* ro = s_ro + jj * SG.ro_stride;
+            uint32_t* ror = s_ror + jj * SG.ro_stride;
+            for (int base = lane; base < steps; base += 8 * 32) {
+                uint8_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = (base + u * 32) < len2 ? src[base + u * 32] : uint8_t('A');
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int st = base + u * 32;
+                    if (st < steps) {
+                        uint32_t row = kZeroRow;
+                        if (st < len2) {
+                            row = symbol_of(v[u]);
+                            if (row == 0xFFu) { bad = true; row = 0; }
+                        }
+                        ro[st] = (row * uint32_t(Wn) + uint32_t(st)) * 8u;
+                        if (kRankPass) ror[st] = (row * uint32_t(Wn) + uint32_t(st)) * 4u;
+                    }
+                }
+            }
+        }
+        if (bad) report_bad_symbol(P);
+    };
+    // the first task's queries are fetched while Seq1 is on its way too (both are cold reads: one wait instead of two)
+    uint4 seq1_first = make_uint4(0u, 0u, 0u, 0u);
+    if (tid * 16 < G.len1)                                          // (volatile: the load must be issued HERE, not sunk to its use)
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(seq1_first.x), "=r"(seq1_first.y), "=r"(seq1_first.z), "=r"(seq1_first.w)
+                     : "l"(P.seq1 + tid * 16));                     // the buffer is padded: vector loads stay inside
+    if (team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
+
+    // ---- the striped window, built once per block ------------------------------------------------------
+    for (int k = tid; k < 3 * 32; k += nthreads) s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
+    for (int k = tid; k < kSymbols * kRowPad / 4; k += nthreads)
+        reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(&T.code[0][0])[k];
+    {
+        // Seq1 as symbol indices; everything past len1 (and any byte outside [A-Z-]) becomes 31, whose columns are all zero
+        bool bad = false;
+        for (int i = tid * 16; i < seq1_span; i += nthreads * 16) {
+            uint4 v = seq1_first;
+            if (i != tid * 16) {
+                v = make_uint4(0u, 0u, 0u, 0u);
+                if (i < G.len1) v = *reinterpret_cast<const uint4*>(P.seq1 + i);
+            }
+            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+            uint32_t o4[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t c = symbol_of(uint8_t(w4[w] >> (8 * b)));
+                    const bool inside = (i + 4 * w + b) < G.len1;
+                    if (c == 0xFFu) { bad = bad || inside; c = 31u; }
+                    o |= (inside ? c : 31u) << (8 * b);
+                }
+                o4[w] = o;
+            }
+            *reinterpret_cast<uint4*>(s_seq1 + i) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        if (bad) report_bad_symbol(P);
+    }
+    __syncthreads();
+    PSA_TRACE_MARK(1);
+    // One task per (stripe column p < S, plane kind): the 32 stripes of column p are one 32x32 bit transpose; the words
+    // p + S, p + 2S, ... of the same column hold the same stripes moved up by one (word p + kS, bit t = position
+    // p + (t + k) S), so each follows from its predecessor by a one-bit shift that takes in ONE new position per row --
+    // 2 ALU instructions per row instead of another transpose (the window has S + steps words, only S distinct columns).
+    {
+        constexpr int nkinds = kRankPass ? 3 : 2;
+        for (int task = tid; task < S * nkinds; task += nthreads) {
+            const int kind = task / S, p = task - kind * S;
+            const uint32_t* col = s_col[kind];
+            uint32_t m[32];
+#pragma unroll
+            for (int t = 0; t < 32; t++) m[t] = col[s_seq1[p + t * S]];
+            transpose32(m);
+            uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk);
+            const int wstep = kind < 2 ? 2 : 1;                                             // words between neighbours of a row
+            for (int k = 0;; k++) {
+                const int word = p + k * S;
+                if (word >= Wn) break;
+                if (k > 0) {
+                    const uint32_t c = col[s_seq1[word + 31 * S]];                          // the position that enters at bit 31
+#pragma unroll
+                    for (int r = 0; r < kPlaneRows; r++) m[r] = __funnelshift_r(m[r], c >> r, 1);
+                }
+#pragma unroll
+                for (int r = 0; r < kPlaneRows; r++) dst[(size_t(r) * Wn + word) * wstep] = m[r];
+            }
+        }
+    }
+    __syncthreads();
+    PSA_TRACE_MARK(2);
+
+    if (team >= SG.teams) return;                                   // spare warps only helped to build the window
+
+    for (int task = first_task; task < SG.ntasks; task += task_stride) {
+        const int q0 = task * SG.Q;
+        const int nqt = (G.nq - q0) < SG.Q ? (G.nq - q0) : SG.Q;    // queries of this task
+        PSA_TRACE_MARK(3);
+
+        const int lanes_task = nqt * S;
+        const int passes = (lanes_task + 31) >> 5;
+        // This warp's slots of the task, one per query: best candidate this warp has seen for it (merged at every flush).
+        StripeSlot* my_slot = s_slot + tw * SG.Q;
+        if (lane < nqt) my_slot[lane] = StripeSlot{ kKeyNone, 0x7FFFFFFF, 0u, 0u, 0u, 0u, 0u };
+        __syncwarp();
+        // Lane-local running best of the lane's current query, carried across this warp's passes: (key, offset), the pass
+        // that produced it, and a warp-uniform floor -- the best RESOLVED key seen so far in the query, as the biased 32-bit
+        // value of the bit-sliced keys -- under which nothing needs a second look.
+        Cand lbest = none;
+        int lpass = -1;
+        uint32_t lfloor = 0u;
+        for (int p = tw; p < passes; p += SG.T) {
+            const int f = p * 32 + lane;
+            const bool lane_on = f < lanes_task;
+            const int j = lane_on ? f / S : 0, l = lane_on ? f - j * S : 0;        // idle lanes shadow lane 0 (addresses stay valid)
+            const uint32_t vmask = lane_on ? stripe_valid_mask(l, S, noff) : 0u;
+            const uint32_t* ro = s_ro + j * SG.ro_stride;
+            uint32_t racc[K > 0 ? K : 1];
+            racc[0] = ~vmask;                                       // offsets outside the range count as saturated
+            if (kRankPass) {
+                const uint32_t* ror = s_ror + j * SG.ro_stride;
+                const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 4;
+                for (int g = 0; g < groups; g++) {
+                    stripe_rank_group(racc[0], pr, ror + g * 32);
+                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+                }
+            }
+            VCounter<NUP> A, B, C;
+            A.clear(); B.clear(); C.clear();
+            const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(l) * 8;
+            for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+            if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
+            PSA_TRACE_MARK(4);
+
+            // ---- keys of the lane's 32 offsets; the lane's best joins its running best ------------------------------
+            SlicedKeys<NB, K> keys;                                 // stripe mode is only entered when the bit-sliced keys apply
+            keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
+            const int jlo = (p * 32) / S;
+            const int jhi = ((p * 32 + 31) / S) < (nqt - 1) ? ((p * 32 + 31) / S) : (nqt - 1);
+            // One arg-max over ALL valid offsets, resolved keys and unresolved bounds alike.  Resolved winner: it is the lane's
+            // candidate and no unresolved offset of the lane can beat it.  Unresolved winner below the floor: nothing in the
+            // lane can matter.  Only an unresolved winner at or above the floor needs the exact treatment below.
+            uint32_t v = 0;
+            int bbit = 0;
+            const bool have = sliced_argmax<SlicedKeys<NB, K>::P>(keys.acc, vmask & ~keys.nokey, v, bbit);
+            const bool res = have && ((keys.rmask >> bbit) & 1u);
+            {
+                // raise the floor of the lane's query with this pass's resolved lane maxima BEFORE anything is judged by it
+                // (lanes of one query share one value; a pass that straddles queries reduces each segment on its own)
+                const uint32_t mine_v = res ? v : 0u;
+                for (int jj = jlo; jj <= jhi; jj++) {               // warp-uniform; one segment unless the pass straddles queries
+                    const bool in = lane_on && j == jj;
+                    const uint32_t seg = __ballot_sync(0xFFFFFFFFu, in);
+                    if (in) {
+                        const uint32_t fl = __reduce_max_sync(seg, mine_v);
+                        lfloor = fl > lfloor ? fl : lfloor;
+                    }
+                }
+            }
+            const bool pend = have && !res && v >= lfloor;
+            if (__any_sync(0xFFFFFFFFu, pend)) {
+                // exact per query segment, as the linear kernels do it: resolved best, then settle every unresolved offset whose
+                // bound could still beat the segment's best (the running bests take part, so settling stops early)
+                Cand mine = none, ub = none;
+                const uint32_t umask = keys.scan(vmask, l, mine, ub, S);
+                if (lane_on && better(mine.key, mine.off, lbest.key, lbest.off)) { lbest = mine; lpass = p; }
+                for (int jj = jlo; jj <= jhi; jj++) {               // warp-uniform
+                    const bool in = lane_on && j == jj;
+                    const Cand wb = settle_unresolved(T, P, keys, in ? lbest : none, in ? ub : none, in ? umask : 0u, l,
+                                                      int64_t(q0 + jj) * len2, len2, S);
+                    // a settled offset that won is carried on by the lane that owns it (it is an offset of this pass)
+                    if (in && wb.key != kKeyNone && wb.off % S == l && better(wb.key, wb.off, lbest.key, lbest.off)) { lbest = wb; lpass = p; }
+                }
+            } else if (res) {
+                const int64_t key = int64_t(v) - keys.bias;
+                const int32_t off = l + bbit * S;
+                if (better(key, off, lbest.key, lbest.off)) { lbest.key = key; lbest.off = off; lpass = p; }
+            }
+            // ---- flush: lanes whose query ends with this pass hand their running best to the warp's slot of that query ----
+            const int pn = p + SG.T;
+            const bool leaving = lane_on && (pn >= passes || (pn * 32 + lane) >= lanes_task || (pn * 32 + lane) / S != j);
+            if (__any_sync(0xFFFFFFFFu, leaving)) {
+                for (int jj = jlo; jj <= jhi; jj++) {               // warp-uniform
+                    const bool in = leaving && j == jj;
+                    if (!__any_sync(0xFFFFFFFFu, in)) continue;
+                    const Cand wb = warp_best(in ? lbest : none);
+                    PSA_CHECK(jj < SG.Q);
+                    if (wb.key != kKeyNone && better(wb.key, wb.off, my_slot[jj].key, my_slot[jj].off)) {
+                        // the lane that owns the winner writes the slot; if the winner comes from THIS pass its counters are
+                        // still in registers: read them out at the winning bit (offset = l + t S) for the finish step
+                        if (in && lbest.key == wb.key && lbest.off == wb.off) {
+                            StripeSlot sl{ wb.key, wb.off, 0u, 0u, 0u, 0u, 0u };
+                            if (lpass == p && wb.off % S == l) {
+                                const int t = (wb.off - l) / S;
+                                uint32_t na = 0, nb = 0, nc = 0;
+#pragma unroll
+                                for (int k = 0; k < NB; k++) {
+                                    na |= ((A.plane(k) >> t) & 1u) << k;
+                                    nb |= ((B.plane(k) >> t) & 1u) << k;
+                                    nc |= ((C.plane(k) >> t) & 1u) << k;
+                                }
+                                sl.top = K > 0 ? (racc[0] >> t) & (vmask >> t) & 1u : 0u;
+                                sl.na = na; sl.nb = nb; sl.nc = nc;
+                            }
+                            my_slot[jj] = sl;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (leaving) { lbest = none; lpass = -1; lfloor = 0u; }
+            }
+        }
+        PSA_TRACE_MARK(5);
+        team_sync(team, team_threads);                              // slots complete; nobody reads this task's row offsets any more
+        PSA_TRACE_MARK(6);
+        if (task + task_stride < SG.ntasks) build_row_offsets(task + task_stride);       // in flight while the queries are finished
+        // finish: one warp per query of the task -- best over the team's warps, then the record
+        for (int jj = tw; jj < nqt; jj += SG.T) {
+            StripeSlot r = s_slot[jj];
+            for (int w = 1; w < SG.T; w++) {
+                const StripeSlot& o = s_slot[w * SG.Q + jj];
+                if (better(o.key, o.off, r.key, r.off)) r = o;
+            }
+            PSA_CHECK(q0 + jj < G.nq);
+            stripe_finish_query(T, P, s_seq1, s_code, q0 + jj, int64_t(q0 + jj) * len2, len2, r);
+        }
+        PSA_TRACE_MARK(7);
+        team_sync(team, team_threads);                              // next task's row offsets are in place, this task's slots are consumed
+    }
+}
+
+size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, bool rank_pass)
+{
+    size_t b = size_t(kPlaneRows) * g.Wn * (rank_pass ? 12 : 8);
+    b += size_t(std::max<int64_t>(stripe_seq1_span(g), (len1 + 15) & ~int64_t(15)));
+    b += size_t(g.teams) * g.Q * g.ro_stride * 4 * (rank_pass ? 2 : 1);
+    b += size_t(g.teams) * g.T * g.Q * sizeof(StripeSlot);
+    return b;
+}
+
+} // namespace
+
+// Shape of a stripe-mode launch for nq queries of len2 symbols against len1, or ok = 0 when the mode does not apply
+// (window beyond shared memory, or so few lanes per query that whole warps would idle).
+StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, int sm_count, bool force)
+{
+    StripeGeom g{};
+    const int64_t noff = len1 - len2 + 1;
+    if (noff < 1 || len2 < 1 || nq < 1 || len2 > 1023 || sm_count < 1) return g;        // NB <= 10 instantiated
+    const int64_t S = (noff + 31) / 32, steps = (len2 + 31) & ~int64_t(31);
+    if (S + steps > 4096) return g;
+    g.S = int(S); g.steps = int(steps); g.Wn = int(S + steps); g.ro_stride = int(steps) + 4;
+    // Candidates: Q queries per task (lane utilisation) x T warps per team (a task's passes in parallel or in sequence).
+    // Cost model in cycles for the busiest block: a pass is `groups` unrolled 32-step groups (~265 ALU instructions at one
+    // per two cycles per scheduler) plus its epilogue; a task adds row offsets, barriers and the finish.  The block takes
+    // the larger of (all its work spread over 4 schedulers) and (the longest chain one team runs in sequence, stretched
+    // when fewer than four warps per scheduler are counting and the ALU pipe cannot be kept full).
+    const double pass_c = double(steps / 32) * 560.0 + 700.0;
+    double best_cost = 0, best_busy = 0;
+    bool have = false;
+    const int warps_max = kStripeThreads / 32;
+    static const int dbg_q = std::getenv("PSA_STRIPE_Q") ? std::atoi(std::getenv("PSA_STRIPE_Q")) : 0;      // experiments only
+    static const int dbg_t = std::getenv("PSA_STRIPE_T") ? std::atoi(std::getenv("PSA_STRIPE_T")) : 0;
+    for (int Q = 1; Q <= kStripeMaxQ && Q <= nq; Q++) {
+        if (dbg_q > 0 && Q != dbg_q) continue;
+        const int passes = int((Q * S + 31) / 32);
+        if (passes > kStripeMaxPasses) break;
+        const int ntasks = (nq + Q - 1) / Q;
+        const int blocks = std::min(sm_count, ntasks);
+        const int tasks_b = (ntasks + blocks - 1) / blocks;                              // tasks of the busiest block
+        for (int Tw = 1; Tw <= std::min(passes, warps_max); Tw++) {
+            const int teams = Tw == 1 ? warps_max : std::min(warps_max / Tw, 15);        // named barriers 1..15
+            if (teams < 1 || (dbg_t > 0 && Tw != dbg_t)) continue;
+            StripeGeom c = g;
+            c.Q = Q; c.passes = passes; c.T = Tw; c.teams = teams; c.ntasks = ntasks;
+            if (stripe_smem_bytes(c, len1, rank_pass) > kStripeSmemMax) continue;
+            const int ppw = (passes + Tw - 1) / Tw;                                      // passes per warp, in sequence
+            const int rounds = (tasks_b + teams - 1) / teams;                            // tasks per team, in sequence
+            const double busy = double(std::min(teams, tasks_b)) * Tw;                   // warps counting at the same time
+            const double stretch = std::max(1.0, 16.0 / busy);
+            const double task_c = 500.0 + (Tw > 1 ? 300.0 : 0.0);
+            const double util = double(Q) * double(S) / (32.0 * passes);                 // lanes that hold offsets
+            const double spread = std::ceil(double(tasks_b) * passes / 4.0) * pass_c;    // warp w issues on scheduler w % 4
+            const double chain = double(rounds) * (ppw * pass_c * stretch + task_c);
+            const double cost = std::max(spread, chain) + (1.0 - util) * 0.5 * pass_c;   // time of the busiest block = time of the launch
+            const bool better_cost = !have || cost < best_cost * 0.99;
+            const bool tie = have && !better_cost && cost <= best_cost * 1.01 && busy > best_busy;
+            if (better_cost || tie) {
+                best_cost = have && tie ? std::min(best_cost, cost) : cost;
+                best_busy = busy;
+                g.Q = Q; g.passes = passes; g.T = Tw; g.teams = teams; g.ntasks = ntasks;
+                have = true;
+            }
+        }
+    }
+    if (!have) return g;
+    // lanes that idle in the last pass of a task: below ~70 % the linear kernels' packing does better
+    if (!force && double(g.Q) * double(S) / (32.0 * g.passes) < 0.70) return g;
+    g.smem = stripe_smem_bytes(g, len1, rank_pass);
+    g.blocks = std::min(sm_count, g.ntasks);
+    g.ok = 1;
+    return g;
+}
+
+namespace {
+
+template <int NB, int K>
+void launch_stripe_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, const StripeGeom& SG, bool derive,
+                        int key_planes, int64_t key_bias, cudaStream_t stream)
+{
+    auto go = [&](auto kernel, bool (&done)[64]) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(dev >= 0 && dev < 64 && done[dev])) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripeSmemMax));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+        kernel<<<SG.blocks, kStripeThreads, SG.smem, stream>>>(T, G, P, SG, key_planes, key_bias);
+    };
+    if constexpr (K == 1) {
+        if (derive) {
+            static bool done_dr[64];
+            go(k_stripe<NB, K, true>, done_dr);
+            return;
+        }
+    }
+    static bool done[64];
+    go(k_stripe<NB, K, false>, done);
+}
+
+} // namespace
+
+bool stripe_derives_rank(const DeviceTable& T, int rank_planes, bool allow_derive)
+{
+    return rank_planes == 1 && T.top_rank_lut > 0 && (T.top_rank_lut & 1) == 0 && allow_derive;
+}
+
+// stripe mode needs the bit-sliced key epilogue (small integer keys in exact order)
+bool stripe_keys_ok(const DeviceTable& T, int64_t len2)
+{
+    int64_t bias = 0;
+    return len2 <= 1023 && sliced_key_planes(T, len2, len2 <= 127 ? 7 : 10, &bias) > 0;
+}
+
+void launch_stripe(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, bool allow_derive,
+                   const StripeGeom& SG, cudaStream_t stream)
+{
+    const int64_t len2 = G.uniform_len2;
+    int64_t key_bias = 0;
+    const int nb = len2 <= 127 ? 7 : 10;
+    const int key_planes = sliced_key_planes(T, len2, nb, &key_bias);
+    const bool derive = stripe_derives_rank(T, rank_planes, allow_derive);
+    if (nb == 7) {
+        if (rank_planes == 0) launch_stripe_inst<7, 0>(T, G, P, SG, derive, key_planes, key_bias, stream);
+        else launch_stripe_inst<7, 1>(T, G, P, SG, derive, key_planes, key_bias, stream);
+    } else {
+        if (rank_planes == 0) launch_stripe_inst<10, 0>(T, G, P, SG, derive, key_planes, key_bias, stream);
+        else launch_stripe_inst<10, 1>(T, G, P, SG, derive, key_planes, key_bias, stream);
+    }
+}
+
+} // namespace psa

@@ -10,29 +10,29 @@ from conftest import same_answer
 
 pytestmark = pytest.mark.gpu
 ALPHA = [chr(65 + i) for i in range(26)] + ["-"]
-# (engine, rank planes, warps per block): the scalar engine, and the bit-sliced scan with every plane count
-# (0 planes = every offset unresolved -> the select + exact-candidate path carries the result)
-# (engine, rank planes, warps per block, batch mode): the scalar engine, and the bit-sliced scan with every plane
-# count (0 planes = every offset unresolved -> the in-kernel settle path carries the result), both tile shapes
-# (engine, rank planes, warps per block, batch mode, bit-sliced epilogue): the scalar engine, and the bit-sliced
-# scan with every plane count (0 planes = every offset unresolved -> the in-kernel settle path carries the result),
-# both tile shapes and both epilogues
-# The last field switches off deriving the top-rank bit from the class planes (default on when the table allows it).
-ENGINES = [(1, -1, 0, -1, 1, 1), (2, -1, 0, -1, 1, 1), (2, 0, 1, 0, 1, 1), (2, 1, 2, 0, 0, 1), (2, 4, 3, 0, 1, 1), (2, 2, 4, 0, 0, 1),
-           (2, 0, 0, 1, 0, 1), (2, 2, 0, 1, 1, 1), (2, 4, 0, 1, 0, 1), (2, 1, 0, 1, 1, 1), (2, 1, 0, 0, 1, 0), (2, 1, 0, 1, 1, 0)]
+# (engine, rank planes, warps per block, batch mode, bit-sliced epilogue, derive top rank from class planes, stripe mode):
+# the scalar engine; the default dispatch; the linear-plane scan kernels with every plane count (0 planes = every offset
+# unresolved -> the in-kernel settle path carries the result), both tile shapes and both epilogues, with and without
+# deriving the top-rank bit; and stripe mode forced wherever a batch qualifies (single queries included).
+ENGINES = [(1, -1, 0, -1, 1, 1, 0), (0, -1, 0, -1, 1, 1, -1), (2, 0, 1, 0, 1, 1, 0), (2, 1, 2, 0, 0, 1, 0), (2, 4, 3, 0, 1, 1, 0),
+           (2, 2, 4, 0, 0, 1, 0), (2, 0, 0, 1, 0, 1, 0), (2, 2, 0, 1, 1, 1, 0), (2, 4, 0, 1, 0, 1, 0), (2, 1, 0, 1, 1, 1, 0),
+           (2, 1, 0, 0, 1, 0, 0), (2, 1, 0, 1, 1, 0, 0), (2, 1, 0, -1, 1, 1, 1), (2, 0, 0, -1, 1, 1, 1), (2, 1, 0, -1, 1, 0, 1)]
+ENGINE_IDS = ["scalar", "auto", "scan-k0-w1-bs", "scan-k1-w2", "scan-k4-w3-bs", "scan-k2-w4", "batch-k0", "batch-k2-bs", "batch-k4",
+              "batch-k1-bs", "scan-k1-planes", "batch-k1-planes", "stripe-k1", "stripe-k0", "stripe-k1-planes"]
 
 
-def _set_engine(ctx, engine, planes=-1, warps=0, batch=-1, sliced=1, derive=1):
+def _set_engine(ctx, engine, planes=-1, warps=0, batch=-1, sliced=1, derive=1, stripe=None):
+    """stripe: None = auto (-1) under the default dispatch (engine 0), off (0) when a test names the linear-plane kernels."""
     ctx.set_option("engine", engine)
     ctx.set_option("rank_planes", planes)
     ctx.set_option("scan_warps", warps)
     ctx.set_option("batch_mode", batch)
     ctx.set_option("sliced_keys", sliced)
     ctx.set_option("derive_rank", derive)
+    ctx.set_option("stripe_mode", (-1 if engine == 0 else 0) if stripe is None else stripe)
 
 
-@pytest.fixture(params=ENGINES, ids=["scalar", "scan", "scan-k0-w1-bs", "scan-k1-w2", "scan-k4-w3-bs", "scan-k2-w4", "batch-k0",
-                                     "batch-k2-bs", "batch-k4", "batch-k1-bs", "scan-k1-planes", "batch-k1-planes"])
+@pytest.fixture(params=ENGINES, ids=ENGINE_IDS)
 def engine(request, ctx):
     _set_engine(ctx, *request.param)
     yield request.param[0]
@@ -441,14 +441,74 @@ def test_packed_mode_is_chosen_for_config3_shape(ctx, port, synth):
     changes nothing but the launch shape."""
     wl = synth.workload("c3", nq=65)                                      # odd count: the last block holds one query
     res = {}
+    ctx.set_option("stripe_mode", 0)                                      # (stripe mode would take this batch first)
     for pack in (1, 0):
         ctx.set_option("pack_queries", pack)
         res[pack] = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
         assert (ctx.stat("packed_queries"), ctx.stat("packed_warps")) == ((2, 5) if pack else (0, 0))
     ctx.set_option("pack_queries", 1)
+    ctx.set_option("stripe_mode", -1)
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     for a, b, e in zip(res[1], res[0], exp):
         assert same_answer(a, e) and same_answer(b, e) and a.counts == b.counts == e.counts
+
+
+STRIPE_SHAPES = [(3000, 500, 96), (3000, 500, 1), (700, 300, 37), (2100, 1000, 11), (330, 64, 50), (1500, 1023, 9), (4200, 200, 7),
+                 (10000, 64, 150), (1055, 32, 5), (640, 129, 2), (2000, 1, 19), (9000, 33, 23), (5000, 777, 3), (96, 64, 300), (20000, 100, 6)]
+
+
+@pytest.mark.parametrize("planes,derive", [(-1, 1), (0, 1), (1, 0)])
+def test_stripe_mode(ctx, port, planes, derive):
+    """Stripe mode (k_stripe): one launch per batch -- every block builds the striped window of Seq1 in shared memory, warp
+    teams scan Q queries per task against it and finish them.  Every shape (lanes per query from 1 to 622, tasks that
+    straddle queries, a last task with fewer queries, steps padded to 32), plane count and both sources of the top-rank
+    bit must give the oracle's answers, on random letters and on low-entropy letters (exact ties, unresolved offsets)."""
+    rng = random.Random(4321 + planes)
+    used = 0
+    for len1, len2, nq in STRIPE_SHAPES:
+        for w, is_max in (([1, 3, 4, 2], True), ([1, 3, 4, 2], False), ([1, 1, 1, 1], True), ([5, 1, 2, 3], False), ([10, 2, 3, 4], True)):
+            alpha = rng.choice([ALPHA, ALPHA[:26], "ACDG", "AB", "A"])
+            s1 = "".join(rng.choice(alpha) for _ in range(len1))
+            qs = ["".join(rng.choice(alpha) for _ in range(len2)) for _ in range(nq)]
+            if len2 <= len1 // 2:
+                qs[nq // 2] = s1[len1 // 3: len1 // 3 + len2]            # one query that occurs verbatim
+            _set_engine(ctx, 2, planes=planes, derive=derive, stripe=1)
+            try:
+                got = ctx.search_batch(w, is_max, s1, qs)
+                on = ctx.stat("stripe_mode")
+                used += on
+                if on:
+                    assert ctx.stat("kernel_launches") == 1
+                    assert ctx.stat("stripe_lanes") == (len1 - len2 + 1 + 31) // 32
+            finally:
+                _set_engine(ctx, 0)
+            exp = port.search_batch(w, is_max, s1, qs)
+            for k, (g, e) in enumerate(zip(got, exp)):
+                assert same_answer(g, e), (len1, len2, nq, w, is_max, alpha, k, g, e)
+                assert g.counts == e.counts
+    assert used >= 40, used
+
+
+def test_stripe_mode_is_chosen_for_configs_3_and_5(ctx, port, synth):
+    """The default dispatch takes equal-length batches with exact small keys in stripe mode: config 3's shape as teams of
+    5 warps on 2 queries (79 lanes each), config 5's as one warp per query (311 lanes, 10 passes); a batch whose weights
+    need the re-score path or whose lengths differ keeps the linear-plane kernels."""
+    _set_engine(ctx, 0)
+    wl = synth.workload("c3", nq=301)
+    got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("kernel_launches")) == (1, 79, 1)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
+    wl = synth.workload("c5", nq=3000)
+    got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("stripe_team_warps"), ctx.stat("kernel_launches")) == (1, 311, 1, 1)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:500])
+    assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
+    wl = synth.workload("c3", nq=40)
+    ctx.search_batch([1.5, 2.6, 0.1, 0.2], True, wl.seq1, wl.queries)              # order needs the reference's double
+    assert ctx.stat("stripe_mode") == 0
+    ctx.search_batch(wl.weights, True, wl.seq1, wl.queries[:-1] + [wl.queries[-1][:499]])   # ragged
+    assert ctx.stat("stripe_mode") == 0
 
 
 def test_zero_copy_results_match_copied_results(psa, ctx, port, synth):

@@ -32,7 +32,7 @@ def main(argv):
         out_dir = argv[1]
         argv = argv[2:]
         os.makedirs(out_dir, exist_ok=True)
-    summary_path = os.path.join(out_dir, "r01_summary.json")
+    summary_path = os.path.join(out_dir, os.environ.get("PSA_ROUND", "r02") + "_summary.json")
     summary = json.load(open(summary_path)) if os.path.exists(summary_path) else {}
     for rep, workload in zip(argv[0::2], argv[1::2]):
         stem = os.path.splitext(os.path.basename(rep))[0]
