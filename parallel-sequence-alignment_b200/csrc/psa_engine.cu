@@ -326,7 +326,10 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     // Stripe mode: equal-length queries, exact integer order, all offsets, window fits shared memory -> one launch
     d.stripe = StripeGeom{};
     if (scan && uniform_len && last < 0 && ctx->table.exact && ctx->rank_planes <= 1 && ctx->opt_stripe_mode != 0 &&
-        ctx->opt_sliced_keys != 0 && stripe_keys_ok(ctx->table, ctx->uniform_len2) && (nq >= 2 || ctx->opt_stripe_mode == 1)) {
+        ctx->opt_sliced_keys != 0 && stripe_keys_ok(ctx->table, ctx->uniform_len2) &&
+        // auto: batches of queries long enough that the counting dominates (measured: at len2 = 64 the per-pass epilogue makes
+        // stripe mode no faster than batch mode's shared windows)
+        (ctx->opt_stripe_mode == 1 || (nq >= 2 && ctx->uniform_len2 >= 128))) {
         const bool rank_pass = ctx->rank_planes == 1 && !stripe_derives_rank(ctx->table, ctx->rank_planes, ctx->opt_derive_rank != 0);
         d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass, d.sm_count, ctx->opt_stripe_mode == 1);
         if (d.stripe.ok) { d.SG.fused_finish = false; d.SG.fused_combine = false; d.SG.pack_q = d.SG.pack_warps = 0; }

@@ -74,8 +74,11 @@ struct StripeGeom {
     int ro_stride = 0;   // words between the row-offset vectors of two queries of a task
     int blocks = 0;
     size_t smem = 0;
+    int threads = 0;     // block size
 };
-constexpr int kStripeThreads = 640;                 // 20 warps, one block per SM (<= 96 registers per thread)
+// threads of the one block per SM: 20 warps at <= 96 registers (28 warps at 72 registers measured no faster on short queries)
+__host__ __device__ constexpr int stripe_threads(int nb) { return nb <= 7 ? 640 : 640; }
+inline int stripe_threads_for_len2(int64_t len2) { return stripe_threads(len2 <= 127 ? 7 : 10); }
 constexpr int kStripeMaxQ = 32;                     // queries per task
 constexpr int kStripeMaxPasses = 64;                // passes per task
 constexpr size_t kStripeSmemMax = 224 * 1024;        // of the 227 KB a block may have (a little static shared memory on top)

@@ -217,7 +217,7 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
 // NB : counter planes (len2 < 2^NB), RANKPASS : a rank plane is read (K = 1 and the top rank is not derivable),
 // K : rank planes tracked (0 or 1), DR : top-rank bit derived from the class counts; keys are always bit-sliced
 template <int NB, int K, bool DR>
-__global__ void __launch_bounds__(kStripeThreads, 1)
+__global__ void __launch_bounds__(stripe_threads(NB), 1)
 k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const int key_planes,
          const int64_t key_bias)
 {
@@ -527,7 +527,8 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, i
     const double pass_c = double(steps / 32) * 560.0 + 700.0;
     double best_cost = 0, best_busy = 0;
     bool have = false;
-    const int warps_max = kStripeThreads / 32;
+    g.threads = stripe_threads_for_len2(len2);
+    const int warps_max = g.threads / 32;
     static const int dbg_q = std::getenv("PSA_STRIPE_Q") ? std::atoi(std::getenv("PSA_STRIPE_Q")) : 0;      // experiments only
     static const int dbg_t = std::getenv("PSA_STRIPE_T") ? std::atoi(std::getenv("PSA_STRIPE_T")) : 0;
     for (int Q = 1; Q <= kStripeMaxQ && Q <= nq; Q++) {
@@ -584,7 +585,7 @@ void launch_stripe_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtr
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripeSmemMax));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
-        kernel<<<SG.blocks, kStripeThreads, SG.smem, stream>>>(T, G, P, SG, key_planes, key_bias);
+        kernel<<<SG.blocks, SG.threads, SG.smem, stream>>>(T, G, P, SG, key_planes, key_bias);
     };
     if constexpr (K == 1) {
         if (derive) {

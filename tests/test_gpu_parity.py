@@ -489,21 +489,26 @@ def test_stripe_mode(ctx, port, planes, derive):
     assert used >= 40, used
 
 
-def test_stripe_mode_is_chosen_for_configs_3_and_5(ctx, port, synth):
-    """The default dispatch takes equal-length batches with exact small keys in stripe mode: config 3's shape as teams of
-    5 warps on 2 queries (79 lanes each), config 5's as one warp per query (311 lanes, 10 passes); a batch whose weights
-    need the re-score path or whose lengths differ keeps the linear-plane kernels."""
+def test_stripe_mode_dispatch(ctx, port, synth):
+    """The default dispatch takes equal-length batches of queries of 128+ symbols with exact small keys in stripe mode
+    (config 3: teams of 5 warps on 2 queries of 79 lanes each); short queries (config 5: one warp per query, 311 lanes, 10
+    passes -- when forced), batches whose weights need the re-score path and ragged batches keep the linear-plane kernels."""
     _set_engine(ctx, 0)
     wl = synth.workload("c3", nq=301)
     got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("kernel_launches")) == (1, 79, 1)
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
-    wl = synth.workload("c5", nq=3000)
+    wl = synth.workload("c5", nq=3000)                                    # short queries: batch mode unless stripe mode is forced
     got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    assert (ctx.stat("stripe_mode"), ctx.stat("batch_mode")) == (0, 1)
+    ctx.set_option("stripe_mode", 1)
+    forced = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("stripe_team_warps"), ctx.stat("kernel_launches")) == (1, 311, 1, 1)
+    ctx.set_option("stripe_mode", -1)
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:500])
     assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
+    assert [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in forced] == [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in got]
     wl = synth.workload("c3", nq=40)
     ctx.search_batch([1.5, 2.6, 0.1, 0.2], True, wl.seq1, wl.queries)              # order needs the reference's double
     assert ctx.stat("stripe_mode") == 0
