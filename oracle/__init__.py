@@ -156,6 +156,9 @@ class Ref:
         L.ref_divide_execute_tasks.restype = C.c_double
         L.ref_divide_execute_tasks.argtypes = [dp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
                                                C.c_int, ip, ip, cp]
+        if hasattr(L, "ref_np2"):
+            L.ref_np2.restype = C.c_double
+            L.ref_np2.argtypes = [dp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, ip, ip, cp, dp]
         L.ref_offset_score.restype = C.c_double
         L.ref_offset_score.argtypes = [dp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, ip, cp]
         L.ref_sign.restype = C.c_char
@@ -196,6 +199,15 @@ class Ref:
         sc = self.lib.ref_divide_execute_tasks(_w(weights), int(is_max), _b(seq1), _b(seq2), num_processes, pid,
                                                pct, nthreads, C.byref(o), C.byref(c), C.byref(ch))
         return self._res(sc, o, c, ch)
+
+    def np2(self, weights, is_max, seq1, seq2, pct=100, ndev=1, nthreads=4):
+        """Emulated `mpiexec -np 2` run of the reference (two host threads as the two ranks, divide_execute_tasks each,
+        MAXLOC/MINLOC merge); returns (Result, [score of rank 0, score of rank 1])."""
+        o, c, ch = C.c_int(), C.c_int(), C.c_char()
+        rs = (C.c_double * 2)()
+        sc = self.lib.ref_np2(_w(weights), int(is_max), _b(seq1), _b(seq2), pct, ndev, nthreads,
+                              C.byref(o), C.byref(c), C.byref(ch), rs)
+        return self._res(sc, o, c, ch), list(rs)
 
     def offset_score(self, weights, is_max, seq1, seq2, offset) -> Result:
         c, ch = C.c_int(), C.c_char()

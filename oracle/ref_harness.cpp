@@ -23,6 +23,8 @@
 #include <math.h>
 #include <omp.h>
 #include <mpi.h>
+#include <thread>
+#include <cuda_runtime_api.h>
 
 #include "def.h"
 #include "program_data.h"
@@ -132,6 +134,39 @@ double ref_divide_execute_tasks(const double* w, int is_max, const char* seq1, c
     double s = divide_execute_tasks(&d, num_processes, pid, &m);
     *out_offset = m.offset; *out_char_offset = m.char_offset; *out_ch = m.ch;
     return s;
+}
+
+/* EMULATION of the reference's "mpiexec -np 2" CUDA+OpenMP run (MPI is not installed in this image): two host threads
+   stand in for the two ranks.  Each selects its own GPU (rank % ndev, as two ranks on two one-GPU machines would each
+   have one) and calls the reference's own divide_execute_tasks(&data, 2, pid, &mutant) (cpu_funcs.c:123-218) with the
+   CUDA percentage at `pct`; the two (score, rank) pairs are then reduced the way MPI_MAXLOC / MPI_MINLOC do it
+   (cpu_funcs.c:64-77: better score wins, ties go to the lower rank) and the winner's Mutant is "sent" to rank 0
+   (cpu_funcs.c:82-94).  rank_scores[2] receives the per-rank scores.  Timing baseline only: the reference's GPU path
+   races across blocks. */
+double ref_np2(const double* w, int is_max, const char* seq1, const char* seq2, int pct, int ndev, int nthreads,
+               int* out_offset, int* out_char_offset, char* out_ch, double* rank_scores)
+{
+    ProgramData* d = new ProgramData[2];
+    Mutant m[2] = { { -1, -1, NOT_FOUND_CHAR }, { -1, -1, NOT_FOUND_CHAR } };
+    double s[2] = { NAN, NAN };
+    if (fill_problem(&d[0], w, is_max, seq1, seq2)) { delete[] d; return NAN; }
+    d[1] = d[0];
+    cuda_percentage = pct;
+    omp_set_num_threads(nthreads);
+    auto rank = [&](int pid) {
+        if (ndev > 0) cudaSetDevice(pid % ndev);
+        omp_set_num_threads(nthreads);
+        s[pid] = divide_execute_tasks(&d[pid], 2, pid, &m[pid]);
+    };
+    std::thread t1(rank, 1);
+    rank(0);
+    t1.join();
+    const int win = (is_max ? s[1] > s[0] : s[1] < s[0]) ? 1 : 0;     /* MAXLOC / MINLOC: ties -> lowest rank */
+    *out_offset = m[win].offset; *out_char_offset = m[win].char_offset; *out_ch = m[win].ch;
+    if (rank_scores) { rank_scores[0] = s[0]; rank_scores[1] = s[1]; }
+    const double best = s[win];
+    delete[] d;
+    return best;
 }
 
 /* One offset (cpu_funcs.c:257-300). Requires ref_fill_hash() first. */

@@ -182,3 +182,14 @@ def test_product_does_not_link_the_oracle(psa):
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "oracle/" not in text and "psa_oracle" not in text, f
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """bench.py --impl reference must run the reference only: it loads synth.py by file path, so the product package (whose
+    import maps libpsa_b200.so) never enters the process."""
+    code = ("import sys, bench; s = bench.load_synth(); wl = bench.make_workload(s, 'c3', 0, nq=4); "
+            "assert len(wl.queries) == 4 and len(wl.seq1) == 3000; "
+            "assert not any('parallel-sequence-alignment_b200' in m for m in sys.modules), [m for m in sys.modules if 'parallel' in m]; "
+            "maps = open('/proc/self/maps').read(); assert 'libpsa_b200' not in maps; print('ok')")
+    p = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-800:]

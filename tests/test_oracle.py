@@ -141,3 +141,17 @@ def test_vs_reference_capacity_block(port, ref, input_blocks):
     assert len(b["seq1"]) == ref.cap1 and len(b["seq2"]) == ref.cap2
     r = ref.search_omp(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"], 8)
     assert same_answer(port.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"], nthreads=4), r)
+
+
+def test_emulated_two_rank_run_of_the_reference(ref, input_blocks):
+    """oracle/ref_harness.cpp:ref_np2 -- two host threads standing in for `mpiexec -np 2` (divide_execute_tasks(&data, 2, pid)
+    each, MAXLOC/MINLOC merge).  With every offset on the CPU loops (percentage 0, no GPU needed) the merged answer must be the
+    single-rank answer; nothing in the reference pins the 2-rank result, so this is the emulation's own consistency check."""
+    import bench
+    for k in (1, 2, 3, 5, 8):
+        b = input_blocks[k]
+        with bench.silence_c_stdout():
+            res, per_rank = ref.np2(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"], pct=0, ndev=0, nthreads=1)       # 1 OpenMP thread per rank: the reference's fill_hash races with more (SURVEY D1)
+        e = b["expect"]
+        assert (res.offset, res.char_offset, res.ch, res.score) == (e["offset"], e["char_offset"], e["ch"], e["score"]), (k, res)
+        assert res.score in per_rank and len(per_rank) == 2

@@ -3,11 +3,41 @@
 prologue, unrolled loop bodies, epilogue ...) and print each run's share of executed instructions and of the
 warp-state samples, with its dominant stall reasons.
 
-    python tools/ncu_regions.py gpurun_out/c3p_source.csv.gz [min_share_pct]"""
+    python tools/ncu_regions.py gpurun_out/c3p_source.csv.gz [min_share_pct] [--json summary.json workload]
+
+With --json the hottest region (largest share of executed instructions: the unrolled 32-step counting group) is also
+recorded in the summary file under [workload][kernel]["inner_loop"]: its SASS instruction count split by issue pipe.
+bench.py derives the kernel's own integer-ALU bound from that record instead of from a constant."""
 import csv
 import gzip
 import io
+import json
+import os
 import sys
+
+ALU_PIPE = {"LOP3", "SHF", "IADD3", "VIADD", "ISETP", "SEL", "PRMT", "LEA", "IABS", "PLOP3", "VIMNMX", "IMNMX", "SGXT", "BMSK",
+            "R2P", "P2R", "FSEL", "FMNMX", "IADD", "MOV", "VABSDIFF", "LOP", "SHL", "SHR", "VOTE"}
+FMA_PIPE = {"IMAD", "FFMA", "FMUL", "FADD", "HFMA2", "HADD2", "HMUL2", "IDP"}
+LSU_PIPE = {"LDS", "STS", "LDG", "STG", "LD", "ST", "LDL", "STL", "ATOMS", "ATOMG", "RED", "LDSM", "LDC"}
+
+
+def clean_kernel_name(name):
+    name = name.split("(psa::")[0].split("(")[0] if name.startswith("void") is False else name
+    name = name.replace("void ", "").replace("psa::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
+    # drop the parameter list, keep the template arguments; C-style casts "(int)10" -> "10"
+    depth, out = 0, []
+    for ch in name:
+        if ch == "<":
+            depth += 1
+        if ch == "(" and depth == 0:
+            break
+        out.append(ch)
+        if ch == ">":
+            depth -= 1
+    name = "".join(out)
+    for cast in ("(int)", "(bool)"):
+        name = name.replace(cast, "")
+    return name.strip()
 
 
 def f(x):
@@ -19,6 +49,11 @@ def f(x):
 
 def main(argv):
     path = argv[0]
+    json_out = None
+    if "--json" in argv:
+        k = argv.index("--json")
+        json_out = (argv[k + 1], argv[k + 2])
+        argv = argv[:k] + argv[k + 3:]
     min_share = float(argv[1]) if len(argv) > 1 else 0.4
     fh = io.TextIOWrapper(gzip.open(path), newline="") if path.endswith(".gz") else open(path, newline="")
     rows = list(csv.reader(fh))
@@ -41,6 +76,24 @@ def main(argv):
                 runs.append(cur)
             cur = [k, k, v]
     runs.append(cur)
+    if json_out:
+        a, b, v = max(runs, key=lambda r: sum(f(x[ci]) for x in data[r[0]:r[1] + 1]))
+        pipes = {"alu": 0, "fma": 0, "lsu": 0, "other": 0}
+        ops = {}
+        for r in data[a:b + 1]:
+            t = r[cs].split()
+            op = (t[1] if t and t[0].startswith("@") and len(t) > 1 else t[0] if t else "?").split(".")[0]
+            ops[op] = ops.get(op, 0) + 1
+            pipes["alu" if op in ALU_PIPE else "fma" if op in FMA_PIPE else "lsu" if op in LSU_PIPE else "other"] += 1
+        rec = {"sass_first": a, "sass_last": b, "sass_instr": b - a + 1, "exec_per_instr": v,
+               "share_of_executed_pct": 100 * sum(f(x[ci]) for x in data[a:b + 1]) / tot_i,
+               "alu_pipe_instr": pipes["alu"], "fma_pipe_instr": pipes["fma"], "lsu_instr": pipes["lsu"], "other_instr": pipes["other"],
+               "ops": dict(sorted(ops.items(), key=lambda kv: -kv[1])[:8]), "steps_per_group": 32}
+        summary = json.load(open(json_out[0])) if os.path.exists(json_out[0]) else {}
+        kname = clean_kernel_name(rows[0][1] if len(rows[0]) > 1 else "?")
+        summary.setdefault(json_out[1], {}).setdefault(kname, {})["inner_loop"] = rec
+        summary[json_out[1]][kname]["executed_warp_instructions"] = tot_i
+        json.dump(summary, open(json_out[0], "w"), indent=1, sort_keys=True)
     # merge tiny neighbours into "other"
     other_i = other_s = 0.0
     for a, b, v in runs:

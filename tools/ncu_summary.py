@@ -53,7 +53,7 @@ def main(argv):
         tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
         name = rec.get("Kernel Name", stem).split("(")[0]
         name = name.replace("void ", "").replace("psa::", "").replace("<unnamed>::", "").replace("unnamed>::", "").strip()
-        summary.setdefault(workload, {})[name] = {
+        summary.setdefault(workload, {}).setdefault(name, {}).update({
             "capture": os.path.basename(rep),
             "dram_bytes_per_launch": dram,
             "duration_s_under_ncu": (num(rec.get("gpu__time_duration.sum", "0")) or 0) * tscale.get(unit.get("gpu__time_duration.sum", "ns"), 1e-9),
@@ -63,7 +63,10 @@ def main(argv):
             "smem_wavefronts_pct_of_peak": num(rec.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "")),
             "registers_per_thread": num(rec.get("launch__registers_per_thread", "")),
             "warp_instructions": num(rec.get("smsp__inst_executed.sum", "")),
-        }
+            "alu_pipe_pct_of_peak_active_max_sm": num(rec.get("sm__inst_executed_pipe_alu.max.pct_of_peak_sustained_active", "")),
+            "sm_cycles_active_avg": num(rec.get("sm__cycles_active.avg", "")),
+            "sm_cycles_elapsed_max": num(rec.get("sm__cycles_elapsed.max", "")),
+        })
     json.dump(summary, open(summary_path, "w"), indent=1, sort_keys=True)
     print(json.dumps(summary, indent=1))
 

@@ -5,12 +5,12 @@ set -u
 out=gpurun_out/profiles; mkdir -p $out
 [ -f profiles/r01_summary.json ] && cp profiles/r01_summary.json $out/
 for w in c3 c5 c4 c1; do
-  B="python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-others"
+  B="python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-others --no-strong"
   $B > gpurun_out/plain_$w.log 2>&1 || { echo "plain run of $w failed"; tail -3 gpurun_out/plain_$w.log; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/r01_${w}_launches.csv $B > gpurun_out/ncu_l$w.log 2>&1
 done
 cap() {   # workload, kernel regex, file stem
-  B="python bench.py --workload $1 --steps 3 --warmup 3 --no-cpu-baseline --no-others"
+  B="python bench.py --workload $1 --steps 3 --warmup 3 --no-cpu-baseline --no-others --no-strong"
   $B > /dev/null 2>&1 || { echo "plain run of $1 failed"; return; }
   ncu --set full --import-source on --clock-control none -k regex:$2 -s 3 -c 1 -f -o /tmp/$3 $B > gpurun_out/ncu_$3.log 2>&1
   python tools/ncu_summary.py --out $out /tmp/$3.ncu-rep $1 >> gpurun_out/sum.log 2>&1
