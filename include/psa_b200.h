@@ -241,6 +241,37 @@ int psa_run_files(psa_context* ctx, const char* input_path, const char* output_p
    by a newline, each exactly what the reference writes for that block alone.  *nblocks receives the count. */
 int psa_run_files_all(psa_context* ctx, const char* input_path, const char* output_path, int* nblocks);
 
+/* ---- widening ------------------------------------------------------------------------------------ */
+
+/* Query lists (8f-2).  The reference's input.txt carries exactly one Seq2 (cpu_funcs.c:360); the batched API wants many.
+   Two on-disk forms are read: FASTA (any line starting with '>' is a header; the lines up to the next header, white space
+   removed, are one query) and plain lists (no '>' anywhere: every white-space separated token is one query).  *seq2s
+   (concatenated queries, not NUL separated) and *q_off (nq + 1 byte offsets) are malloc()ed: release with psa_free. */
+int  psa_read_query_file(const char* path, char** seq2s, int64_t** q_off, int32_t* nq);
+void psa_free(void* p);
+
+/* input.txt supplies weights, Seq1 and the goal (its own Seq2 is ignored), `queries_path` the queries; one output stanza
+   per query, exactly what the reference writes for that query alone ("<mutant>\n<offset> <score %g>"), stanzas separated by a
+   newline.  The mutant strings are produced on the device (psa_search_batch_mutants). */
+int psa_run_query_file(psa_context* ctx, const char* input_path, const char* queries_path, const char* output_path, int32_t* nq);
+
+/* Reporting on the device (8f-3; in the reference only the winner's string is built, on the host: cpu_funcs.c:96-98).
+   psa_search_batch_mutants = psa_search_batch + the mutated copy of every query (Seq2 with its one substitution applied; a
+   query with no possible mutation is copied unchanged), written by a kernel in the layout of seq2s (out_mutants has
+   q_off[nq] bytes, query q at q_off[q]). */
+int psa_search_batch_mutants(psa_context* ctx, const double weights[4], int is_max,
+                             const char* seq1, int64_t len1, const char* seq2s, const int64_t* q_off, int32_t nq,
+                             psa_result* out, char* out_mutants);
+
+/* The k best offsets of ONE query over absolute offsets [first,last) under the reference order -- best score first, equal
+   scores by ascending offset (is_swapable, cuda_funcs.cu:290-307) -- selected on the device from the per-offset scores of
+   find_best_mutant_offset (cpu_funcs.c:257-300).  offsets[r], scores[r] and (if not NULL) char_offsets[r], letters[r]
+   describe rank r; *found = entries written (< k when fewer offsets have a mutation).  offsets[0] is the psa_search_range
+   answer.  Runs on the context's first GPU. */
+int psa_topk_offsets(psa_context* ctx, const double weights[4], int is_max,
+                     const char* seq1, int64_t len1, const char* seq2, int64_t len2, int64_t first, int64_t last,
+                     int32_t k, int32_t* offsets, double* scores, int32_t* char_offsets, char* letters, int32_t* found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,12 @@ def _sig():
     _lib.psa_write_output_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double]
     _lib.psa_run_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(_CResult)]
     _lib.psa_run_files_all.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    _lib.psa_read_query_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    _lib.psa_free.argtypes = [C.c_void_p]
+    _lib.psa_run_query_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
+    _lib.psa_search_batch_mutants.argtypes = batch + [C.POINTER(_CResult), C.c_void_p]
+    _lib.psa_topk_offsets.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64,
+                                      C.c_int32, C.POINTER(C.c_int32), dp, C.POINTER(C.c_int32), C.c_char_p, C.POINTER(C.c_int32)]
     # the six host primitives of cuda_funcs.h:44-61 (C spellings)
     _lib.psa_get_hashtable_sign.restype = C.c_char
     _lib.psa_get_hashtable_sign.argtypes = [C.c_char, C.c_char]
@@ -422,6 +428,58 @@ class Context:
         out = _CResult()
         self._check(_lib.psa_run_files(self._h, input_path.encode(), output_path.encode(), C.byref(out)))
         return _py(out)
+
+
+def read_query_file(path: str) -> List[bytes]:
+    """FASTA or one-query-per-token list -> queries (host only, no GPU needed)."""
+    p1, p2, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+    rc = _lib.psa_read_query_file(path.encode(), C.byref(p1), C.byref(p2), C.byref(n))
+    if rc:
+        raise PsaError(rc, path)
+    try:
+        offs = (C.c_int64 * (n.value + 1)).from_address(p2.value)
+        cat = C.string_at(p1.value, offs[n.value])
+        return [cat[offs[i]:offs[i + 1]] for i in range(n.value)]
+    finally:
+        _lib.psa_free(p1)
+        _lib.psa_free(p2)
+
+
+def _search_batch_mutants(self, weights, is_max: bool, seq1, queries):
+    """(results, mutant strings): psa_search_batch + every query with its one substitution applied, written on the device."""
+    b = Batch(seq1, queries)
+    out = (_CResult * max(b.nq, 1))()
+    buf = C.create_string_buffer(max(sum(b.lens), 1))
+    self._check(_lib.psa_search_batch_mutants(self._h, _w(weights), int(bool(is_max)), b.seq1_ptr, b.len1, b.seq2s_ptr, b.q_off_ptr,
+                                              b.nq, out, C.cast(buf, C.c_void_p)))
+    raw, cuts = buf.raw, [0]
+    for n in b.lens:
+        cuts.append(cuts[-1] + n)
+    return [_py(out[i]) for i in range(b.nq)], [raw[cuts[i]:cuts[i + 1]].decode("latin1") for i in range(b.nq)]
+
+
+def _topk_offsets(self, weights, is_max: bool, seq1, seq2, k: int, first: int = 0, last: Optional[int] = None):
+    """The k best offsets of one query in the reference order: list of (offset, score, char_offset, letter)."""
+    s1, s2 = _b(seq1), _b(seq2)
+    if last is None:
+        last = len(s1) - len(s2) + 1
+    offs, scores, coffs = (C.c_int32 * k)(), (C.c_double * k)(), (C.c_int32 * k)()
+    letters = C.create_string_buffer(k)
+    found = C.c_int32()
+    self._check(_lib.psa_topk_offsets(self._h, _w(weights), int(bool(is_max)), s1, len(s1), s2, len(s2), first, last, k,
+                                      offs, scores, coffs, letters, C.byref(found)))
+    return [(offs[r], scores[r], coffs[r], letters.raw[r:r + 1].decode("latin1")) for r in range(found.value)]
+
+
+def _run_query_file(self, input_path: str, queries_path: str, output_path: str) -> int:
+    n = C.c_int32()
+    self._check(_lib.psa_run_query_file(self._h, input_path.encode(), queries_path.encode(), output_path.encode(), C.byref(n)))
+    return n.value
+
+
+Context.search_batch_mutants = _search_batch_mutants
+Context.topk_offsets = _topk_offsets
+Context.run_query_file = _run_query_file
 
 
 def _run_files_all(self, input_path: str, output_path: str) -> int:

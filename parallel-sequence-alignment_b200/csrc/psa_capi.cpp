@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cctype>
 #include <cstddef>
@@ -217,6 +218,94 @@ int psa_run_files(psa_context* ctx, const char* input_path, const char* output_p
         if (out) *out = r;
     }
     std::free(seq1); std::free(seq2);
+    return rc;
+}
+
+void psa_free(void* p) { std::free(p); }
+
+int psa_read_query_file(const char* path, char** seq2s, int64_t** q_off, int32_t* nq)
+{
+    if (!path || !seq2s || !q_off || !nq) return PSA_ERR_ARG;
+    *seq2s = nullptr; *q_off = nullptr; *nq = 0;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return PSA_ERR_IO;
+    std::string text;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    // FASTA if any line starts with '>': header lines end the record before them; otherwise every token is a query
+    bool fasta = false;
+    for (size_t i = 0; i < text.size(); i++)
+        if (text[i] == '>' && (i == 0 || text[i - 1] == '\n')) { fasta = true; break; }
+    std::string cat;
+    std::vector<int64_t> offs(1, 0);
+    auto close_record = [&]() { if ((int64_t)cat.size() > offs.back()) offs.push_back((int64_t)cat.size()); };
+    size_t i = 0;
+    while (i < text.size()) {
+        size_t e = text.find('\n', i);
+        if (e == std::string::npos) e = text.size();
+        if (fasta && text[i] == '>') close_record();
+        else if (fasta && text[i] == ';') {}                      // old-style FASTA comment line
+        else
+            for (size_t k = i; k < e; k++) {
+                const unsigned char c = (unsigned char)text[k];
+                if (std::isspace(c)) { if (!fasta) close_record(); }
+                else cat.push_back((char)c);
+            }
+        if (!fasta) close_record();
+        i = e + 1;
+    }
+    close_record();
+    const size_t n = offs.size() - 1;
+    if (n > 0x7FFFFFFFu) return PSA_ERR_ARG;
+    *seq2s = (char*)std::malloc(cat.size() + 1);
+    *q_off = (int64_t*)std::malloc(sizeof(int64_t) * (n + 1));
+    if (!*seq2s || !*q_off) { std::free(*seq2s); std::free(*q_off); *seq2s = nullptr; *q_off = nullptr; return PSA_ERR_NOMEM; }
+    std::memcpy(*seq2s, cat.data(), cat.size());
+    (*seq2s)[cat.size()] = '\0';
+    std::memcpy(*q_off, offs.data(), sizeof(int64_t) * (n + 1));
+    *nq = (int32_t)n;
+    return PSA_OK;
+}
+
+int psa_run_query_file(psa_context* ctx, const char* input_path, const char* queries_path, const char* output_path, int32_t* nq_out)
+{
+    if (!ctx || !input_path || !queries_path || !output_path) return PSA_ERR_ARG;
+    if (nq_out) *nq_out = 0;
+    double w[4];
+    int is_max = 0;
+    char *seq1 = nullptr, *seq2 = nullptr, *qs = nullptr;
+    int64_t* q_off = nullptr;
+    int32_t nq = 0;
+    int rc = psa_read_input_file(input_path, w, &is_max, &seq1, &seq2);
+    if (rc == PSA_OK) rc = psa_read_query_file(queries_path, &qs, &q_off, &nq);
+    if (rc == PSA_OK && nq == 0) rc = PSA_ERR_IO;
+    std::vector<psa_result> res((size_t)std::max(nq, 1));
+    std::string mutants;
+    if (rc == PSA_OK) {
+        mutants.resize((size_t)q_off[nq]);
+        rc = psa_search_batch_mutants(ctx, w, is_max, seq1, (int64_t)std::strlen(seq1), qs, q_off, nq, res.data(), &mutants[0]);
+    }
+    if (rc == PSA_OK) {
+        std::string text;
+        for (int32_t q = 0; q < nq; q++) {
+            char tail[96];
+            std::snprintf(tail, sizeof(tail), "\n%d %g", res[q].mutant.offset, res[q].score);     // cpu_funcs.c:377
+            if (q) text += "\n";
+            text.append(mutants, (size_t)q_off[q], (size_t)(q_off[q + 1] - q_off[q]));
+            text += tail;
+        }
+        FILE* o = std::fopen(output_path, "w");
+        if (!o) rc = PSA_ERR_IO;
+        else {
+            bool wrote = std::fwrite(text.data(), 1, text.size(), o) == text.size();
+            wrote = (std::fclose(o) == 0) && wrote;
+            if (!wrote) rc = PSA_ERR_IO;
+        }
+    }
+    if (rc == PSA_OK && nq_out) *nq_out = nq;
+    std::free(seq1); std::free(seq2); psa_free(qs); psa_free(q_off);
     return rc;
 }
 

@@ -50,7 +50,7 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants;
     SliceGeom SG{};
     StripeGeom stripe{};       // ok != 0: this shard runs in stripe mode (one launch: window + scan + finish)
     PinBuf h_qoff, h_tile_start, h_out;
@@ -175,7 +175,7 @@ void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
     for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
-                       &d.cls_planes, &d.rank_planes })
+                       &d.cls_planes, &d.rank_planes, &d.mutants })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
@@ -757,11 +757,23 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
     if (!weights || !seq1 || !seq2s || !q_off || nq < 0) return fail(ctx, PSA_ERR_ARG, "null argument or nq < 0");
     if (len1 < 1 || len1 > 0x7FFF0000ll) return fail(ctx, PSA_ERR_ARG, "len1 out of range");
     int64_t max_len2 = 0, min_len2 = INT64_MAX;
-    for (int q = 0; q < nq; q++) {
-        const int64_t len2 = q_off[q + 1] - q_off[q];
-        if (len2 < 1 || len2 > len1) return fail(ctx, PSA_ERR_ARG, "query %d: len2=%lld must be in [1, len1]", q, (long long)len2);
-        max_len2 = std::max(max_len2, len2);
-        min_len2 = std::min(min_len2, len2);
+    {
+        // equal-length batches (the common large case: config 5 has 65 536 queries) are recognised by a branch-free pass the
+        // compiler vectorises; only ragged batches pay for the min / max walk
+        const int64_t len0 = nq > 0 ? q_off[1] - q_off[0] : 0;
+        int64_t differs = 0;
+        for (int q = 0; q < nq; q++) differs |= (q_off[q + 1] - q_off[q]) ^ len0;
+        if (nq > 0 && differs == 0) {
+            if (len0 < 1 || len0 > len1) return fail(ctx, PSA_ERR_ARG, "query 0: len2=%lld must be in [1, len1]", (long long)len0);
+            max_len2 = min_len2 = len0;
+        } else {
+            for (int q = 0; q < nq; q++) {
+                const int64_t len2 = q_off[q + 1] - q_off[q];
+                if (len2 < 1 || len2 > len1) return fail(ctx, PSA_ERR_ARG, "query %d: len2=%lld must be in [1, len1]", q, (long long)len2);
+                max_len2 = std::max(max_len2, len2);
+                min_len2 = std::min(min_len2, len2);
+            }
+        }
     }
     ctx->uniform_len2 = nq > 0 && min_len2 == max_len2 ? max_len2 : 0;
     if (max_len2 > kExactMaxLen2) return fail(ctx, PSA_ERR_ARG, "len2 > %lld is not supported", (long long)kExactMaxLen2);
@@ -821,7 +833,13 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
 
     const int64_t granule = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
     ctx->plan.assign(ndev, psa_shard{ 0, 0, -1, -1 });
-    if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, ctx->plan.data())))
+    if (nq > 1 && ctx->uniform_len2 > 0) {
+        // lengths were validated above and are all equal: the balanced split is arithmetic (no second pass over q_off)
+        for (int g = 0; g < ndev; g++) {
+            ctx->plan[g].q_begin = int32_t(int64_t(nq) * g / ndev);
+            ctx->plan[g].q_end = int32_t(int64_t(nq) * (g + 1) / ndev);
+        }
+    } else if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, ctx->plan.data())))
         return fail(ctx, rc, "cannot partition the batch");
     int used = 0;
     for (int g = 0; g < ndev; g++) used += ctx->plan[g].q_begin != ctx->plan[g].q_end;
@@ -1052,6 +1070,91 @@ int psa_offset_scores(psa_context* ctx, const double weights[4], int is_max, con
     PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
     if (bad_symbol_seen(d)) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
     return PSA_OK;
+}
+
+int psa_topk_offsets(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1, const char* seq2,
+                     int64_t len2, int64_t first, int64_t last, int32_t k, int32_t* offsets, double* scores, int32_t* char_offsets,
+                     char* letters, int32_t* found)
+{
+    if (!ctx) return PSA_ERR_ARG;
+    if (!weights || !seq1 || !seq2 || !offsets || !scores || !found || k < 1) return fail(ctx, PSA_ERR_ARG, "null argument or k < 1");
+    if (len2 < 1 || len2 > len1 || len1 > 0x7FFF0000ll || len2 > kExactMaxLen2 || first < 0 || first >= last ||
+        last > offsets_of(len1, len2))
+        return fail(ctx, PSA_ERR_ARG, "lengths or offset range invalid");
+    *found = 0;
+    ctx->prepared = ctx->ran = false;
+    DeviceTable T;
+    int rc = build_tables(weights, is_max, len2, nullptr, &T);
+    if (rc) return fail(ctx, rc, "%s", psa_strerror(rc));
+    ctx->table_valid = false;                    // the cached table belongs to the batch entry points
+    DeviceState& d = ctx->devs[0];
+    PSA_CUDA(ctx, cudaSetDevice(d.dev));
+    const int64_t n = last - first;
+    const int kk = int(std::min<int64_t>(k, n));
+    if ((rc = ensure_dev(ctx, d.seq1, (size_t)len1 + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.seq2s, (size_t)len2 + 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.out, 64))) return rc;
+    if ((rc = ensure_dev(ctx, d.partial, (size_t)n * 13 + 64))) return rc;         // scores | char offsets | letters
+    if ((rc = ensure_dev(ctx, d.tiles, sizeof(TopkRec) * (size_t)kk + 64))) return rc;
+    if ((rc = ensure_pin(ctx, d.h_out, sizeof(TopkRec) * (size_t)kk + 64))) return rc;
+    double* d_scores = (double*)d.partial.p;
+    int32_t* d_coff = (int32_t*)(d_scores + n);
+    uint8_t* d_let = (uint8_t*)(d_coff + n);
+    TopkRec* d_top = (TopkRec*)d.tiles.p;
+    int32_t* d_found = (int32_t*)((char*)d.tiles.p + sizeof(TopkRec) * (size_t)kk);
+    BatchGeom G{};
+    G.len1 = len1; G.first = first; G.last = last; G.nq = 1; G.uniform_len2 = (int32_t)len2;
+    BatchPtrs P{};
+    P.seq1 = (const uint8_t*)d.seq1.p; P.seq2s = (const uint8_t*)d.seq2s.p;
+    P.cand_count = (int32_t*)d.out.p; P.err_flag = d.h_err; P.run_tag = next_run_tag(d);
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2, (size_t)len2, cudaMemcpyHostToDevice, d.stream));
+    launch_offset_profile(T, G, P, d_scores, d_coff, d_let, d.stream);
+    launch_topk(T.is_max, first, n, kk, d_scores, d_coff, d_let, d_top, d_found, d.stream);
+    PSA_CUDA(ctx, cudaGetLastError());
+    PSA_CUDA(ctx, cudaMemcpyAsync(d.h_out.p, d_top, sizeof(TopkRec) * (size_t)kk + sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
+    PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    if (bad_symbol_seen(d)) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
+    const TopkRec* h = (const TopkRec*)d.h_out.p;
+    const int32_t nf = *(const int32_t*)((const char*)d.h_out.p + sizeof(TopkRec) * (size_t)kk);
+    for (int r = 0; r < nf; r++) {
+        offsets[r] = h[r].offset; scores[r] = h[r].score;
+        if (char_offsets) char_offsets[r] = h[r].char_offset;
+        if (letters) letters[r] = (char)h[r].letter;
+    }
+    *found = nf;
+    return PSA_OK;
+}
+
+int psa_search_batch_mutants(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,
+                             const char* seq2s, const int64_t* q_off, int32_t nq, psa_result* out, char* out_mutants)
+{
+    if (!ctx) return PSA_ERR_ARG;
+    if (!out_mutants && nq > 0) return fail(ctx, PSA_ERR_ARG, "null mutant buffer");
+    // the records have to stay on the device for the emission kernel: no stores into host memory for this call
+    const int saved_zc = ctx->opt_zero_copy;
+    ctx->opt_zero_copy = 0;
+    int rc = psa_search_batch(ctx, weights, is_max, seq1, len1, seq2s, q_off, nq, out);
+    ctx->opt_zero_copy = saved_zc;
+    if (rc || nq == 0) return rc;
+    if (nq == 1) {
+        // one query (possibly split by offset range over the GPUs and merged on the host): one poke, like cpu_funcs.c:96-98
+        std::memcpy(out_mutants, seq2s + q_off[0], (size_t)(q_off[1] - q_off[0]));
+        if (out[0].mutant.char_offset >= 0 && out[0].mutant.ch) out_mutants[out[0].mutant.char_offset] = out[0].mutant.ch;
+        return PSA_OK;
+    }
+    return for_each_device(ctx, [ctx, q_off, out_mutants](DeviceState& d) {
+        if (!d.active) return (int)PSA_OK;
+        PSA_CUDA(ctx, cudaSetDevice(d.dev));
+        const int64_t byte0 = q_off[d.q_begin], nbytes = q_off[d.q_end] - byte0;
+        int r = ensure_dev(ctx, d.mutants, (size_t)nbytes + 64);
+        if (r) return r;
+        launch_emit_mutants(d.G, d.P, (const QueryRec*)d.out.p, nbytes, (uint8_t*)d.mutants.p, d.sm_count, d.stream);
+        PSA_CUDA(ctx, cudaGetLastError());
+        PSA_CUDA(ctx, cudaMemcpyAsync(out_mutants + byte0, d.mutants.p, (size_t)nbytes, cudaMemcpyDeviceToHost, d.stream));
+        PSA_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        return (int)PSA_OK;
+    });
 }
 
 void* psa_alloc_pinned(size_t bytes)

@@ -16,6 +16,8 @@
 #include "psa_device.cuh"
 #include "psa_finish.cuh"
 
+#include <algorithm>
+
 namespace psa {
 
 namespace {
@@ -209,6 +211,69 @@ k_offset_profile(const __grid_constant__ DeviceTable T, const BatchGeom G, const
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Top-k offsets of one query (reporting) from the per-offset profile above: one block repeats k times "the
+// best offset that comes after the previous pick in the reference order" (score best first, equal scores by ascending
+// offset; is_swapable, cuda_funcs.cu:290-307).  k passes over n scores in L2: a reporting path, not a hot one.
+// -------------------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 1024;
+__global__ void __launch_bounds__(kTopkThreads)
+k_topk(const int is_max, const int64_t first, const int64_t n, const int k, const double* __restrict__ scores,
+       const int32_t* __restrict__ char_offsets, const uint8_t* __restrict__ letters, TopkRec* __restrict__ out, int32_t* __restrict__ found)
+{
+    __shared__ Cand s_part[kTopkThreads / 32];
+    Cand prev{ INT64_MAX, -1 };                                     // nothing picked yet: everything comes after it
+    int r = 0;
+    for (; r < k; r++) {
+        Cand mine{ kKeyNone, 0x7FFFFFFF };
+        for (int64_t i = threadIdx.x; i < n; i += kTopkThreads) {
+            if (letters[i] == 0) continue;                          // no mutation possible at this offset
+            const double sc = scores[i];
+            const int64_t key = sortable_from_double(is_max ? sc : -sc);
+            const int32_t off = int32_t(first + i);
+            const bool after_prev = key < prev.key || (key == prev.key && off > prev.off);
+            if (after_prev && better(key, off, mine.key, mine.off)) { mine.key = key; mine.off = off; }
+        }
+        const Cand win = block_best<kTopkThreads>(mine, s_part);
+        if (win.key == kKeyNone) break;
+        if (threadIdx.x == 0) {
+            const int64_t i = int64_t(win.off) - first;
+            TopkRec rec;
+            rec.score = scores[i]; rec.offset = win.off; rec.char_offset = char_offsets[i]; rec.letter = letters[i]; rec.pad = 0;
+            out[r] = rec;
+        }
+        prev = win;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *found = r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Mutant strings of a batch (reporting; the reference builds the winner's string on the host, cpu_funcs.c:96-98):
+// a copy of every query with its one substitution applied.  Thread per byte of the concatenated queries.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_emit_mutants(const BatchGeom G, const BatchPtrs P, const QueryRec* __restrict__ recs, const int64_t nbytes, uint8_t* __restrict__ out)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nbytes; e += int64_t(gridDim.x) * blockDim.x) {
+        int q;
+        int64_t qbeg;
+        if (G.uniform_len2 > 0) { q = int(e / G.uniform_len2); qbeg = int64_t(q) * G.uniform_len2; }
+        else {
+            int lo = 0, hi = G.nq;                                  // qoff[lo] <= e < qoff[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (P.qoff[mid] <= e) lo = mid; else hi = mid;
+            }
+            q = lo; qbeg = P.qoff[lo];
+        }
+        const QueryRec& r = recs[q];
+        uint8_t c = P.seq2s[e];
+        if (r.char_offset >= 0 && e - qbeg == r.char_offset && (r.ch & 0xFF) != 0) c = uint8_t(r.ch & 0xFF);
+        out[e] = c;
+    }
+}
+
 // (block per query: min blocks = 1, so ptxas may spend registers on keeping the re-score loop's loads well ahead of its add chain)
 template <int WPQ>
 __global__ void __launch_bounds__(kFinishThreads, WPQ == 1 ? 4 : 1)
@@ -233,6 +298,20 @@ void launch_offset_profile(const DeviceTable& T, const BatchGeom& G, const Batch
     if (n < 1) return;
     k_offset_profile<<<(unsigned)((n + kExactThreads - 1) / kExactThreads), kExactThreads, 0, stream>>>(T, G, P, scores, char_offsets,
                                                                                                         letters);
+}
+
+void launch_topk(int is_max, int64_t first, int64_t n, int k, const double* scores, const int32_t* char_offsets, const uint8_t* letters,
+                 TopkRec* out, int32_t* found, cudaStream_t stream)
+{
+    k_topk<<<1, kTopkThreads, 0, stream>>>(is_max, first, n, k, scores, char_offsets, letters, out, found);
+}
+
+void launch_emit_mutants(const BatchGeom& G, const BatchPtrs& P, const QueryRec* recs, int64_t nbytes, uint8_t* out, int sm_count,
+                         cudaStream_t stream)
+{
+    if (nbytes < 1) return;
+    const int64_t blocks = std::min<int64_t>((nbytes + 255) / 256, int64_t(sm_count) * 8);
+    k_emit_mutants<<<(unsigned)blocks, 256, 0, stream>>>(G, P, recs, nbytes, out);
 }
 
 void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, bool scan_records, cudaStream_t stream)

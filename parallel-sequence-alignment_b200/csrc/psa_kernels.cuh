@@ -100,6 +100,18 @@ void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P,
 // per-offset scores / mutated position / letter of one query over [G.first, G.last)
 void launch_offset_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, double* scores, int32_t* char_offsets,
                            uint8_t* letters, cudaStream_t stream);
+// top-k offsets of one query from its per-offset profile (one block, k selection passes), and the mutated copies of a batch's queries
+struct TopkRec {
+    double  score;
+    int32_t offset;
+    int32_t char_offset;
+    int32_t letter;
+    int32_t pad;
+};
+void launch_topk(int is_max, int64_t first, int64_t n, int k, const double* scores, const int32_t* char_offsets, const uint8_t* letters,
+                 TopkRec* out, int32_t* found, cudaStream_t stream);
+void launch_emit_mutants(const BatchGeom& G, const BatchPtrs& P, const QueryRec* recs, int64_t nbytes, uint8_t* out, int sm_count,
+                         cudaStream_t stream);
 // bit-plane profile of Seq1 for the scan engine
 void launch_profile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, int sm_count,
                     cudaStream_t stream);

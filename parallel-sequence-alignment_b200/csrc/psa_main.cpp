@@ -3,8 +3,10 @@
 // the same three stdout lines.  argv[1] keeps the reference's meaning (CUDA percentage, -100 =
 // sequential CPU) but is only echoed: there is no CPU path here, every offset runs on the GPU.
 //
-//   psa_b200_cli [cuda_percentage] [--gpus N] [--input PATH] [--output PATH] [--all-blocks]
+//   psa_b200_cli [cuda_percentage] [--gpus N] [--input PATH] [--output PATH] [--all-blocks] [--queries FILE]
 // --all-blocks: consume every problem block stacked in the input file (the reference reads only the first)
+// --queries FILE: weights, Seq1 and goal from the input file, the queries from FILE (FASTA, or one query per token);
+//                 one output stanza per query
 #include "psa_b200.h"
 
 #include <chrono>
@@ -19,11 +21,13 @@ int main(int argc, char** argv)
     int gpus = 1;
     int percentage = 100;
     bool all_blocks = false;
+    const char* queries = nullptr;
     for (int i = 1; i < argc; i++) {
         if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--input") && i + 1 < argc) in = argv[++i];
         else if (!std::strcmp(argv[i], "--output") && i + 1 < argc) out = argv[++i];
         else if (!std::strcmp(argv[i], "--all-blocks")) all_blocks = true;
+        else if (!std::strcmp(argv[i], "--queries") && i + 1 < argc) queries = argv[++i];
         else percentage = std::atoi(argv[i]);
     }
     (void)percentage;
@@ -38,7 +42,8 @@ int main(int argc, char** argv)
     auto t0 = std::chrono::steady_clock::now();
     psa_result r;
     int blocks = 1;
-    rc = all_blocks ? psa_run_files_all(ctx, in, out, &blocks) : psa_run_files(ctx, in, out, &r);
+    int32_t nq = 0;
+    rc = queries ? psa_run_query_file(ctx, in, queries, out, &nq) : all_blocks ? psa_run_files_all(ctx, in, out, &blocks) : psa_run_files(ctx, in, out, &r);
     auto t1 = std::chrono::steady_clock::now();
     if (rc) {
         if (rc == PSA_ERR_IO) std::printf("Error reading input file `%s` or writing `%s`\n", in, out);   // cpu_funcs.c:37,43,103

@@ -193,3 +193,17 @@ def test_reference_arm_does_not_load_the_product_library():
             "maps = open('/proc/self/maps').read(); assert 'libpsa_b200' not in maps; print('ok')")
     p = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-800:]
+
+
+def test_query_file_reader(psa, tmp_path):
+    """psa_read_query_file (host only): FASTA records and plain token lists."""
+    f = tmp_path / "q.fa"
+    f.write_text(">sp|P1|first query\nHELLO\nWORLD\n\n>second\nACDEFGHIK\n;comment\n>empty\n>third  \n  KK-LL \n")
+    assert psa.read_query_file(str(f)) == [b"HELLOWORLD", b"ACDEFGHIK", b"KK-LL"]
+    f.write_text("HELLO WORLD\nACDEFGHIK\n\n\tKK-LL")
+    assert psa.read_query_file(str(f)) == [b"HELLO", b"WORLD", b"ACDEFGHIK", b"KK-LL"]
+    f.write_text("")
+    assert psa.read_query_file(str(f)) == []
+    with pytest.raises(psa.PsaError) as e:
+        psa.read_query_file(str(tmp_path / "missing.fa"))
+    assert e.value.status == psa.PSA_ERR_IO

@@ -617,3 +617,62 @@ def test_reference_program_links_with_no_reference_cuda_file(tmp_path, input_blo
             p = subprocess.run([exe] + argv, cwd=d, capture_output=True, text=True, timeout=300)
             assert p.returncode == 0, (k, argv, p.stderr[-500:])
             assert (d / "output.txt").read_text() == "%s\n%d %s" % (mut, e["offset"], e["score_g"]), (k, argv)
+
+
+def test_topk_offsets(ctx, port, synth):
+    """psa_topk_offsets: the k best offsets in the reference order (best score first, ties by ascending offset), selected on the
+    device; rank 0 is the search answer."""
+    s1, s2 = synth.letters(601, 6000), synth.letters(602, 210)
+    core = synth.letters(603, 150)
+    tied = synth.letters(604, 700) + core + synth.letters(605, 900) + core + synth.letters(606, 400) + core
+    for seq1, seq2 in ((s1, s2), (tied, core)):
+        for w in ([1, 3, 4, 2], [1, 1, 1, 1], [1.5, 2.6, 0.1, 0.2]):
+            for is_max in (True, False):
+                sc = port.scores(w, is_max, seq1, seq2)
+                order = sorted(range(len(sc)), key=lambda n: (-sc[n] if is_max else sc[n], n))
+                for k, (f, l) in ((1, (0, len(sc))), (17, (0, len(sc))), (40, (100, 131)), (5, (len(sc) - 3, len(sc)))):
+                    got = ctx.topk_offsets(w, is_max, seq1, seq2, k, f, l)
+                    exp = [n for n in order if f <= n < l][:k]
+                    assert [g[0] for g in got] == exp, (w, is_max, k, f, l)
+                    assert [g[1] for g in got] == [sc[n] for n in exp]
+                    o = port.offset_naive(w, is_max, seq1, seq2, got[0][0])
+                    assert (got[0][2], got[0][3]) == (o.char_offset, o.ch)
+                best = ctx.search(w, is_max, seq1, seq2)
+                top = ctx.topk_offsets(w, is_max, seq1, seq2, 3)
+                assert (top[0][0], top[0][1], top[0][2], top[0][3]) == (best.offset, best.score, best.char_offset, best.ch)
+    _set_engine(ctx, 0)
+
+
+def test_mutant_strings_on_the_device(psa, ctx, port, synth):
+    """psa_search_batch_mutants: every query with its one substitution applied, written by a kernel (equal-length and ragged
+    batches, one query, several device slots)."""
+    s1 = synth.letters(611, 4000)
+    eq = [synth.letters(620 + k, 300) for k in range(70)]
+    ragged = [synth.letters(700 + k, 5 + 37 * k) for k in range(40)]
+    for qs in (eq, ragged, [eq[0]]):
+        for w, is_max in (([1, 3, 4, 2], True), ([2, 1.5, 1.1, 1.3], False)):
+            res, muts = ctx.search_batch_mutants(w, is_max, s1, qs)
+            exp = port.search_batch(w, is_max, s1, qs)
+            for q, r, m, e in zip(qs, res, muts, exp):
+                assert same_answer(r, e)
+                assert m == e.mutant(q.decode()) and sum(a != b for a, b in zip(m, q.decode())) <= 1
+    with psa.Context(devices=[0, 0, 0]) as c:
+        res, muts = c.search_batch_mutants([1, 3, 4, 2], False, s1, ragged)
+        exp = port.search_batch([1, 3, 4, 2], False, s1, ragged)
+        assert [m for m in muts] == [e.mutant(q.decode()) for q, e in zip(ragged, exp)]
+
+
+def test_query_file_run_and_cli(psa, ctx, port, tmp_path, input_blocks):
+    """weights, Seq1 and goal from an input.txt, the queries from a FASTA file; one reference-format stanza per query."""
+    import subprocess
+    b = input_blocks[5]
+    (tmp_path / "input.txt").write_text(" ".join(b["weights_text"]) + "\n" + b["seq1"] + "\n" + b["seq2"] + "\n" + b["goal"] + "\n")
+    n1 = len(b["seq1"])
+    qs = [b["seq1"][3:3 + n] for n in (5, 9, 17)] + [b["seq2"], "ACDEFGHIKLMNPQRSTVWY"[: min(20, n1)]]
+    (tmp_path / "q.fa").write_text("".join(f">q{k}\n{q[:7]}\n{q[7:]}\n" for k, q in enumerate(qs)))
+    assert ctx.run_query_file(str(tmp_path / "input.txt"), str(tmp_path / "q.fa"), str(tmp_path / "out.txt")) == len(qs)
+    exp = port.search_batch(b["weights"], b["goal"] == "maximum", b["seq1"], qs)
+    want = "\n".join("%s\n%d %g" % (e.mutant(q), e.offset, e.score) for q, e in zip(qs, exp))
+    assert (tmp_path / "out.txt").read_text() == want
+    p = subprocess.run([psa.CLI_PATH, "--queries", "q.fa"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and (tmp_path / "output.txt").read_text() == want, p.stderr
