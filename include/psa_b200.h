@@ -146,8 +146,8 @@ int psa_plan_shards(int64_t len1, const int64_t* q_off, int32_t nq, int nshards,
 int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* queries_per_block, int* warps);
 
 /* The launch shape of stripe mode (one launch per batch) for `nq` queries of `len2` symbols against
-   `len1` on a GPU with `sm_count` SMs; rank_pass = 1 when a rank bit plane has to be read (the top rank is not derivable
-   from the sign classes).  shape[] = { applies (0/1), lanes per query S = ceil(offsets / 32), queries per task, warp
+   `len1` on a GPU with `sm_count` SMs; rank_pass = number of rank bit planes the window carries (0 when the top rank follows
+   from the sign classes, else 1 or 2).  shape[] = { applies (0/1), lanes per query S = ceil(offsets / 32), queries per task, warp
    passes per task, warps per team, teams per block, blocks, dynamic shared memory in bytes }.  Pure host arithmetic. */
 int psa_plan_stripes(int64_t len1, int64_t len2, int32_t nq, int rank_pass, int sm_count, int shape[8]);
 

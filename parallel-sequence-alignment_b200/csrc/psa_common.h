@@ -36,6 +36,20 @@ struct DeviceTable {
                                       // -1: it is not (then the scan reads it from a rank bit plane)
 };
 
+// The constants of the bit-sliced key build (SlicedKeys, psa_scan_core.cuh) for one (table, query length, plane count),
+// resolved on the host once per launch so that the kernel does no 64-bit arithmetic on table fields per pass:
+//   key' = c0 + ka N(b0) + kb N(b1) + kc N(b0&b1) + dv[first tracked plane met, else the floor]     (all >= 0, < 2^planes)
+struct SlicedPlan {
+    int32_t  ka, kb, kc;       // multipliers of the three vertical counters, |k| < 32
+    uint32_t c0;               // bias + len2 * k('*') + the smallest rank term
+    uint32_t dv[4];            // rank term of tracked plane k, above the smallest one (< 256)
+    uint32_t dv_floor;         // rank term of an offset that met no tracked plane
+    int32_t  floor_none;       // nothing below the tracked planes but "no substitute at all"
+    int32_t  floor_exact;      // an offset that met no tracked plane still has an exactly known rank
+    int64_t  bias;             // key = key' - bias
+    int64_t  kfl;              // key units of the floor rank's difference
+};
+
 constexpr int64_t kKeyNone = INT64_MIN;       // key of an offset with no possible mutation / no data
 
 // One record per (query, tile of offsets), written by the scan / exact kernels.

@@ -327,11 +327,18 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.stripe = StripeGeom{};
     if (scan && uniform_len && last < 0 && ctx->table.exact && ctx->rank_planes <= 1 && ctx->opt_stripe_mode != 0 &&
         ctx->opt_sliced_keys != 0 && stripe_keys_ok(ctx->table, ctx->uniform_len2) &&
-        // auto: batches of queries long enough that the counting dominates (measured: at len2 = 64 the per-pass epilogue makes
-        // stripe mode no faster than batch mode's shared windows)
-        (ctx->opt_stripe_mode == 1 || (nq >= 2 && ctx->uniform_len2 >= 128))) {
+        (ctx->opt_stripe_mode == 1 || nq >= 2)) {
+        // rank planes the window carries: none when the top rank follows from the class counts; else two (top and second rank,
+        // interleaved at the class pitch: as cheap to read as one, and a short query's winner often has only the second) when
+        // the table has a second rank to track and the window still fits, else one
         const bool rank_pass = ctx->rank_planes == 1 && !stripe_derives_rank(ctx->table, ctx->rank_planes, ctx->opt_derive_rank != 0);
-        d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass, d.sm_count, ctx->opt_stripe_mode == 1);
+        const int avail = ctx->table.nranks - (ctx->table.has_none ? 0 : 1);
+        const bool force = ctx->opt_stripe_mode == 1;
+        if (rank_pass && avail >= 2) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, 2, d.sm_count, force);
+        if (!d.stripe.ok) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass ? 1 : 0, d.sm_count, force);
+        // auto: short queries only in the one-warp-per-task shape (running best in bit planes: config 5 2.02 -> 1.39 ms); with
+        // several warps per task their per-pass epilogue makes stripe mode no faster than batch mode's shared windows
+        if (d.stripe.ok && !force && ctx->uniform_len2 < 128 && d.stripe.T != 1) d.stripe = StripeGeom{};
         if (d.stripe.ok) { d.SG.fused_finish = false; d.SG.fused_combine = false; d.SG.pack_q = d.SG.pack_warps = 0; }
     }
 
@@ -649,7 +656,7 @@ int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* que
 int psa_plan_stripes(int64_t len1, int64_t len2, int32_t nq, int rank_pass, int sm_count, int shape[8])
 {
     if (!shape || len1 < 1 || len2 < 1 || len2 > len1 || nq < 0 || sm_count < 1) return PSA_ERR_ARG;
-    const StripeGeom g = stripe_plan(len1, len2, nq, rank_pass != 0, sm_count);
+    const StripeGeom g = stripe_plan(len1, len2, nq, rank_pass < 0 ? 0 : rank_pass > 2 ? 2 : rank_pass, sm_count);
     const int v[8] = { g.ok, g.S, g.Q, g.passes, g.T, g.teams, g.blocks, int(g.smem) };
     for (int k = 0; k < 8; k++) shape[k] = v[k];
     return PSA_OK;

@@ -5,6 +5,13 @@
 #include "psa_device.cuh"
 
 namespace psa {
+#if defined(PSA_FINISH_TRACE)
+// debug build only (make EXTRA=-DPSA_FINISH_TRACE): SM clock at the phase boundaries of the finish step, thread 0 of block 0
+__device__ long long g_finish_trace[16];
+#define FIN_MARK(k) do { if (threadIdx.x == 0 && block_index == 0) g_finish_trace[k] = clock64(); } while (0)
+#else
+#define FIN_MARK(k) ((void)0)
+#endif
 namespace {
 
 // -------------------------------------------------------------------------------------------------
@@ -30,10 +37,23 @@ constexpr int kFinishList = 32;       // candidate tiles remembered per query be
 // The body is a device function so that k_combine's last block can run it too (slice mode on a small grid: one launch
 // fewer per single query).  `block_index` stands for blockIdx.x of a k_finish launch; WAIT: the caller has not yet waited
 // for the kernels before it.
-template <int WPQ, bool WAIT>
+// COOP (block per query, k_finish<8> only): when a query has only a few candidate words, each is re-scored by the whole
+// block instead of by one warp.  Warps 1..7 take turns producing the 32 lanes' addends, 32 steps per slot of an 8-slot ring
+// in dynamic shared memory (symbol staging, pair index, weight lookup: ~1300 cycles per slot for a lone warp, which is what
+// made a one-warp re-score run at 41 cycles per step); warp 0 only loads its addends and runs the chain of dependent double
+// adds -- the one part whose order is the reference's (cpu_funcs.c:278) and has to be serial -- at the pace of the FP64 pipe.
+constexpr int kFinishRingSteps = 32;
+constexpr int kFinishRingSlots = 8;
+constexpr int kFinishCoopMaxWords = 4;                                   // more candidate words than this: one warp per word, side by side
+constexpr size_t kFinishRingBytes = size_t(kFinishRingSlots) * kFinishRingSteps * 32 * sizeof(double);
+constexpr size_t kFinishRankBytes = size_t(kFinishWarps) * 32 * sizeof(uint32_t);
+constexpr size_t kFinishDynBytes = kFinishRingBytes + kFinishRankBytes + 2 * kFinishRingSlots * sizeof(uint64_t);
+
+template <int WPQ, bool WAIT, bool COOP = false>
 __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, const int scan_records,
                                             const int block_index)
 {
+    extern __shared__ __align__(16) unsigned char fin_dyn[];            // COOP only: ring | best ranks per producer | full[8], empty[8]
     constexpr int kGroup = WPQ * 32;                                    // threads working on one query
     __shared__ Cand s_part[kFinishWarps];
     __shared__ unsigned long long s_pos;
@@ -46,7 +66,9 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
     __shared__ uint8_t s_win[kFinishWarps][kFinishChunk + 32];          // Seq1 symbols under the 32 offsets
     __shared__ double s_wtab[kSymbols * kRowPad];                       // pair weight by (Seq2 symbol * kRowPad + Seq1 symbol)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    FIN_MARK(0);
     if (tid < 4) s_w[tid] = T.wcls[tid];
+    if (COOP && tid < 2 * kFinishRingSlots) mbar_init(reinterpret_cast<uint64_t*>(fin_dyn + kFinishRingBytes + kFinishRankBytes) + tid, 1);
     if (tid == 0) s_pos = 0ull;
     if (tid < 4) s_cnt[tid] = 0;
     if (WAIT) pdl_wait();                                               // tile records come from the kernels before us
@@ -55,6 +77,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
     if (!T.exact)
         for (int k = tid; k < kSymbols * kRowPad; k += kFinishThreads) s_wtab[k] = T.wcls[P.code_table[k] & 3u];
     __syncthreads();
+    FIN_MARK(1);
     const int q = WPQ == 1 ? block_index * kFinishWarps + warp : block_index;
     if (q >= G.nq) return;
     const int gtid = WPQ == 1 ? lane : tid;                             // index within the query's thread group
@@ -88,10 +111,11 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
     Cand win = WPQ == 1 ? warp_best(mine) : block_best<kFinishThreads>(mine, s_part);
 
     if (!T.exact && scan_records) {
+    FIN_MARK(2);
         const int64_t threshold = win.key == kKeyNone ? kKeyNone : win.key - T.key_slack;   // |key| < 2^61: no wrap
         const int tile_words = G.tile >> 5;
         Cand mine2{ kKeyNone, 0x7FFFFFFF };
-        int words = 0;
+        int words = 0, cand_seq = 0;
         // candidate tiles, found in parallel (a query can have thousands of tiles and one or two candidates)
         int* my_list = s_list[WPQ == 1 ? warp : 0];
         int* my_count = &s_nlist[WPQ == 1 ? warp : 0];
@@ -113,9 +137,25 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
             }
         }
         if (WPQ == 1) __syncwarp(); else __syncthreads();
+        FIN_MARK(3);
         const int nlist = *my_count;
         const bool listed = nlist <= kFinishList;               // else: walk every tile (correct, just slower)
         const int ntry = listed ? nlist : (t1 - t0);
+        FIN_MARK(4);
+        // COOP: how many candidate words are there?  (every warp counts the same sequence; a handful of tiles at most)
+        bool coop = false;
+        int coop_blk = 0;                                               // ring blocks so far (the same on every warp)
+        if (COOP && listed) {
+            int total_words = 0;
+            for (int k = 0; k < nlist; k++) {
+                const int64_t* lk = P.lane_keys + int64_t(my_list[k]) * tile_words;
+                for (int w0 = 0; w0 < tile_words; w0 += 32) {
+                    const int64_t kk = (w0 + lane) < tile_words ? __ldcg(lk + w0 + lane) : kKeyNone;
+                    total_words += __popc(__ballot_sync(0xFFFFFFFFu, kk != kKeyNone && kk >= threshold));
+                }
+            }
+            coop = total_words >= 1 && total_words <= kFinishCoopMaxWords;
+        }
         for (int k = 0; k < ntry; k++) {
             const int t = listed ? my_list[k] : t0 + k;
             if (!listed) {
@@ -132,12 +172,36 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                 while (cand) {
                     const int w = w0 + __ffs(int(cand)) - 1;
                     cand &= cand - 1u;
-                    if (WPQ > 1 && (w % WPQ) != gwarp) continue;       // candidate words go round the warps of the block
-                    words++;
+                    // candidate words go round the warps of the block in the order they are met (every warp walks the same
+                    // sequence), so that k <= WPQ words are always re-scored side by side -- by word index two candidates of
+                    // different tiles could land on the same warp and double the longest chain
+                    if (!(COOP && coop) && WPQ > 1 && (cand_seq++ % WPQ) != gwarp) continue;
                     const int64_t n0 = tb + 32 * w;                    // the word's first offset; this lane owns n0 + lane
                     const int64_t n = n0 + lane;
                     double total = 0.0;
                     uint32_t best_rank = 0;
+                    if (COOP && coop) __syncthreads();                 // the previous word is done with the ring and the rank slots
+                    if (COOP && coop && gwarp == 0) {
+                        // ---- consumer: addends from the ring, adds in step order --------------------------------------
+                        const double* ring = reinterpret_cast<const double*>(fin_dyn);
+                        uint64_t* bars = reinterpret_cast<uint64_t*>(fin_dyn + kFinishRingBytes + kFinishRankBytes);      // full[8], empty[8]
+                        int nblk = 0;
+                        for (int c0 = 0; c0 < len2; c0 += kFinishChunk)
+                            nblk += (((len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk) + kFinishRingSteps - 1) / kFinishRingSteps;
+                        for (int kb = 0; kb < nblk; kb++) {
+                            const int slot = coop_blk % kFinishRingSlots, use = coop_blk / kFinishRingSlots;
+                            mbar_wait(bars + slot, uint32_t(use) & 1u);                  // produced?
+                            const double* src = ring + size_t(slot) * kFinishRingSteps * 32 + lane;
+                            double a[kFinishRingSteps];
+#pragma unroll
+                            for (int u = 0; u < kFinishRingSteps; u++) a[u] = src[u * 32];
+#pragma unroll
+                            for (int u = 0; u < kFinishRingSteps; u++) total += a[u];
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bars + kFinishRingSlots + slot);  // consumed
+                            coop_blk++;
+                        }
+                    } else
                     for (int c0 = 0; c0 < len2; c0 += kFinishChunk) {
                         const int cl = (len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk;
                         __syncwarp();
@@ -184,6 +248,44 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                         // at a time: all symbol loads, then all weight loads (one table indexed by the symbol pair), then
                         // the 32 adds.  (A hand-pipelined version with the next block's loads between the adds was slower:
                         // ptxas places the address adds right behind their loads and a lone warp stalls on each.)
+                        if (COOP && coop) {
+                            // ---- producers (warps 1..7): every seventh ring block each -------------------------------------
+                            double* ring = reinterpret_cast<double*>(fin_dyn);
+                            uint64_t* bars = reinterpret_cast<uint64_t*>(fin_dyn + kFinishRingBytes + kFinishRankBytes);
+                            for (int i0 = 0; i0 < cl; i0 += kFinishRingSteps, coop_blk++) {
+                                if (coop_blk % (kFinishWarps - 1) != gwarp - 1) continue;
+                                const int slot = coop_blk % kFinishRingSlots, use = coop_blk / kFinishRingSlots;
+                                if (use >= 1) mbar_wait(bars + kFinishRingSlots + slot, uint32_t(use - 1) & 1u);    // the slot's previous content is consumed
+                                double* dst = ring + size_t(slot) * kFinishRingSteps * 32 + lane;
+                                if (i0 + kFinishRingSteps <= cl) {
+                                    uint32_t idx[kFinishRingSteps];
+                                    double w32[kFinishRingSteps];
+#pragma unroll
+                                    for (int u = 0; u < kFinishRingSteps; u++) idx[u] = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+#pragma unroll
+                                    for (int u = 0; u < kFinishRingSteps; u++) {
+                                        w32[u] = s_wtab[idx[u]];
+                                        best_rank = max(best_rank, uint32_t(s_code[idx[u]]) >> 2);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < kFinishRingSteps; u++) dst[u * 32] = w32[u];
+                                } else {
+                                    for (int u = 0; u < kFinishRingSteps; u++) {
+                                        double wgt = 0.0;                             // steps past the end add +0.0: exact
+                                        if (i0 + u < cl) {
+                                            const uint32_t idx = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+                                            wgt = s_wtab[idx];
+                                            best_rank = max(best_rank, uint32_t(s_code[idx]) >> 2);
+                                        }
+                                        dst[u * 32] = wgt;
+                                    }
+                                }
+                                __threadfence_block();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bars + slot);              // produced
+                            }
+                            continue;
+                        }
                         for (int i0 = 0; i0 < cl; i0 += 32) {
                             if (i0 + 32 <= cl) {
                                 uint32_t idx[32];
@@ -206,6 +308,16 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                             }
                         }
                     }
+                    if (COOP && coop) {
+                        // the producers' best ranks meet in shared memory; warp 0 owns the word's result
+                        uint32_t* rank_x = reinterpret_cast<uint32_t*>(fin_dyn + kFinishRingBytes);
+                        if (gwarp > 0) rank_x[gwarp * 32 + lane] = best_rank;
+                        __syncthreads();
+                        if (gwarp > 0) continue;
+#pragma unroll
+                        for (int g = 1; g < kFinishWarps; g++) best_rank = max(best_rank, rank_x[g * 32 + lane]);
+                    }
+                    words++;
                     if (best_rank && n >= first && n < last) {
                         const double score = total + T.wdiff[best_rank];                   // cpu_funcs.c:299
                         const int64_t key = sortable_from_double(T.is_max ? score : -score);
@@ -214,6 +326,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                 }
             }
         }
+        FIN_MARK(5);
         if (lane == 0 && words) atomicAdd(P.cand_count, words);
         win = WPQ == 1 ? warp_best(mine2) : block_best<kFinishThreads>(mine2, s_part);
     }
@@ -228,6 +341,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
     }
 
     PSA_CHECK(win.off >= first && win.off < last && int64_t(win.off) + len2 <= G.len1);
+    FIN_MARK(6);
     const uint8_t* a = P.seq1 + win.off;
     int cnt[4] = { 0, 0, 0, 0 };
     unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
@@ -254,6 +368,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
             for (int c = 0; c < 4; c++) atomicAdd(&s_cnt[c], cnt[c]);
         }
         __syncthreads();
+    FIN_MARK(7);
         pos = s_pos;
 #pragma unroll
         for (int c = 0; c < 4; c++) cnt[c] = s_cnt[c];

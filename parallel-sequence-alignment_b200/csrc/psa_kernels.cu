@@ -279,10 +279,14 @@ template <int WPQ>
 __global__ void __launch_bounds__(kFinishThreads, WPQ == 1 ? 4 : 1)
 k_finish(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const int scan_records)
 {
-    finish_body<WPQ, true>(T, G, P, scan_records, int(blockIdx.x));
+    finish_body<WPQ, true, WPQ == kFinishWarps>(T, G, P, scan_records, int(blockIdx.x));
 }
 
 } // namespace
+
+#if defined(PSA_FINISH_TRACE)
+extern "C" int psa_debug_finish_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_finish_trace, sizeof(long long) * 16); }
+#endif
 
 void launch_exact_tiles(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, cudaStream_t stream)
 {
@@ -318,7 +322,16 @@ void launch_finish(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P,
 {
     if (G.nq < 1) return;
     if (G.nq >= 256) launch_dependent(k_finish<1>, dim3((G.nq + kFinishWarps - 1) / kFinishWarps), dim3(kFinishThreads), 0, stream, T, G, P, scan_records ? 1 : 0);
-    else launch_dependent(k_finish<kFinishWarps>, dim3(G.nq), dim3(kFinishThreads), 0, stream, T, G, P, scan_records ? 1 : 0);
+    else {
+        static bool done[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(dev >= 0 && dev < 64 && done[dev])) {
+            cudaFuncSetAttribute(k_finish<kFinishWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFinishDynBytes));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+        launch_dependent(k_finish<kFinishWarps>, dim3(G.nq), dim3(kFinishThreads), kFinishDynBytes, stream, T, G, P, scan_records ? 1 : 0);
+    }
 }
 
 } // namespace psa

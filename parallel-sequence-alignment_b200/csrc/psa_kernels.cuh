@@ -75,6 +75,7 @@ struct StripeGeom {
     int blocks = 0;
     size_t smem = 0;
     int threads = 0;     // block size
+    int rank_planes_read = 0;   // rank bit planes in the window: 0 (none tracked, or the top rank is derived), 1 (uint32), 2 (uint2)
 };
 // threads of the one block per SM: 20 warps at <= 96 registers (28 warps at 72 registers measured no faster on short queries)
 __host__ __device__ constexpr int stripe_threads(int nb) { return nb <= 7 ? 640 : 640; }
@@ -82,7 +83,7 @@ inline int stripe_threads_for_len2(int64_t len2) { return stripe_threads(len2 <=
 constexpr int kStripeMaxQ = 32;                     // queries per task
 constexpr int kStripeMaxPasses = 64;                // passes per task
 constexpr size_t kStripeSmemMax = 224 * 1024;        // of the 227 KB a block may have (a little static shared memory on top)
-StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, int sm_count, bool force = false);
+StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, int rank_planes_read, int sm_count, bool force = false);
 // does the scan take the top-rank bit from the class counts (no rank plane read) for this table / plane count?
 bool stripe_derives_rank(const DeviceTable& T, int rank_planes, bool allow_derive);
 bool stripe_keys_ok(const DeviceTable& T, int64_t len2);     // the bit-sliced key epilogue applies (required by stripe mode)

@@ -347,6 +347,46 @@ struct SlicedKeys {
         nokey = floor_none ? ~seen : 0u;
     }
 
+    // the same from constants the host resolved (SlicedPlan): nothing but bit-plane operations here
+    template <int NUP>
+    __device__ __forceinline__ void build(const SlicedPlan& S, const VCounter<NUP>& A, const VCounter<NUP>& B, const VCounter<NUP>& C,
+                                          const uint32_t (&racc)[K > 0 ? K : 1])
+    {
+        bias = S.bias;
+        kfl = S.kfl;
+#pragma unroll
+        for (int j = 0; j < P; j++) acc[j] = ((S.c0 >> j) & 1u) ? 0xFFFFFFFFu : 0u;
+        uint32_t x[NB];
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = A.plane(k);
+        sliced_add_scaled<NB, P>(acc, x, S.ka);
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = B.plane(k);
+        sliced_add_scaled<NB, P>(acc, x, S.kb);
+#pragma unroll
+        for (int k = 0; k < NB; k++) x[k] = C.plane(k);
+        sliced_add_scaled<NB, P>(acc, x, S.kc);
+        uint32_t seen = 0, dpl[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) dpl[j] = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t sel = racc[k] & ~seen;
+            seen |= racc[k];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((S.dv[k] >> j) & 1u) dpl[j] |= sel;
+        }
+        if (!S.floor_none) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((S.dv_floor >> j) & 1u) dpl[j] |= ~seen;
+        }
+        sliced_add_scaled<8, P>(acc, dpl, 1);
+        rmask = S.floor_exact ? 0xFFFFFFFFu : seen;
+        nokey = S.floor_none ? ~seen : 0u;
+    }
+
     __device__ __forceinline__ uint32_t scan(uint32_t mask, int64_t ln0, Cand& res, Cand& ub, int stride = 1) const
     {
         uint32_t v;

@@ -85,6 +85,22 @@ __device__ __forceinline__ void stripe_rank_group(uint32_t& racc, const char* pr
 // bytes of the Seq1 symbol area: the window build gathers positions up to (Wn - 1) + 31 S (rounded up to whole 16-byte stores)
 __host__ __device__ inline int stripe_seq1_span(const StripeGeom& g) { return (g.Wn + 31 * g.S + 16 + 15) & ~15; }
 
+// Two rank planes ("best rank here is the top / the second rank") interleaved as uint2 at the class window's 8-byte pitch:
+//   pr : s_rnk + l * 8;  ro : the class pass's byte offsets (row * Wn * 8 + step * 8)
+__device__ __forceinline__ void stripe_rank_group2(uint32_t (&racc)[2], const char* pr, const uint32_t* ro)
+{
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint2 a = *reinterpret_cast<const uint2*>(pr + o4.x), b = *reinterpret_cast<const uint2*>(pr + o4.y);
+        const uint2 c = *reinterpret_cast<const uint2*>(pr + o4.z), d = *reinterpret_cast<const uint2*>(pr + o4.w);
+        racc[0] |= a.x | b.x;
+        racc[0] |= c.x | d.x;
+        racc[1] |= a.y | b.y;
+        racc[1] |= c.y | d.y;
+    }
+}
+
 __device__ __forceinline__ void team_sync(int team, int team_threads)
 {
     if (team_threads == 32) __syncwarp();
@@ -214,27 +230,103 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
     }
 }
 
+// One pass over the alignment of query q at offset `off` by one warp: sign counts and the best (rank, lowest i), the same on
+// every lane.  Seq1 symbols and the pair table come from shared memory; the query is read from global memory in rounds of 8
+// loads per lane.
+__device__ __forceinline__ void stripe_walk(const BatchPtrs& P, const uint8_t* s_seq1, const uint8_t* s_code, int64_t qbeg, int len2, int off,
+                                            int (&cnt)[4], int& rank, int& first_i)
+{
+    const int lane = threadIdx.x & 31;
+    const uint8_t* a = s_seq1 + off;
+    const uint8_t* b = P.seq2s + qbeg;
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+    unsigned long long pos = 0ull;        // (rank << 32) | ~i  -> max = best rank, then lowest i
+    for (int base = lane; base < len2; base += 8 * 32) {
+        uint8_t vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) vb[u] = (base + u * 32) < len2 ? b[base + u * 32] : uint8_t('A');
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = base + u * 32;
+            if (i < len2) {
+                uint32_t c1 = a[i], c2 = symbol_of(vb[u]);
+                if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }                           // a bad symbol: the batch is rejected anyway
+                const uint32_t code = s_code[c2 * kRowPad + c1];
+                cnt[code & 3u]++;
+                const unsigned long long pp = (uint64_t(code >> 2) << 32) | uint32_t(~uint32_t(i));
+                pos = pp > pos ? pp : pos;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pos, d);
+        pos = o > pos ? o : pos;
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
+    }
+    rank = int(pos >> 32);
+    first_i = int(~uint32_t(pos));
+}
+
+// the record of a query at which no offset has a possible mutation (what the reference returns then: cuda_funcs.cu:143-145)
+__device__ __forceinline__ void stripe_emit_none(const DeviceTable& T, const BatchPtrs& P, int q)
+{
+    if ((threadIdx.x & 31) != 0) return;
+    QueryRec out;
+    out.score = T.is_max ? -INFINITY : INFINITY;
+    out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
+    out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
+    P.out[q] = out;
+}
+
+// the result record from a finished walk (lane 0 writes)
+__device__ __forceinline__ void stripe_emit(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_seq1, int q, int64_t qbeg, int off,
+                                            const int (&cnt)[4], int rank, int first_i)
+{
+    if ((threadIdx.x & 31) != 0) return;
+    QueryRec out;
+    uint32_t c1 = s_seq1[off + first_i], c2 = symbol_of(P.seq2s[qbeg + first_i]);
+    if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+    out.offset = off;
+    out.char_offset = first_i;
+    out.ch = T.sub[c2][c1];
+    out.rank = rank;
+    double sc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        out.counts[c] = cnt[c];
+        sc = __dadd_rn(sc, __dmul_rn(double(cnt[c]), T.wcls[c]));              // exact (psa_table.cpp), same as k_finish
+    }
+    out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
+    if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
+    P.out[q] = out;
+}
+
 // NB : counter planes (len2 < 2^NB), RANKPASS : a rank plane is read (K = 1 and the top rank is not derivable),
-// K : rank planes tracked (0 or 1), DR : top-rank bit derived from the class counts; keys are always bit-sliced
-template <int NB, int K, bool DR>
+// K : rank planes tracked (0 or 1), DR : top-rank bit derived from the class counts; keys are always bit-sliced;
+// SEQ : teams of one warp (T == 1) -- the warp owns all passes of its task and keeps its running best in bit planes
+template <int NB, int K, bool DR, bool SEQ>
 __global__ void __launch_bounds__(stripe_threads(NB), 1)
-k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const int key_planes,
-         const int64_t key_bias)
+k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const StripeGeom SG,
+         const __grid_constant__ SlicedPlan SP)
 {
     constexpr int NUP = NB - 5;
-    constexpr bool kRankPass = K > 0 && !DR;
+    constexpr bool kRankPass = K > 0 && !DR;                        // rank planes are read (not derived from the class counts)
+    constexpr bool kRank2 = kRankPass && K == 2;                    // two planes as uint2 at the class pitch (no second offset vector)
+    constexpr bool kRor = kRankPass && !kRank2;                     // one plane at a 4-byte pitch: its own offset vector
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wn = SG.Wn, S = SG.S, steps = SG.steps;
     unsigned char* s_cls = smem;                                                            // uint2 [28][Wn]
     unsigned char* s_rnk = s_cls + size_t(kPlaneRows) * Wn * 8;                             // uint32 [28][Wn]
-    unsigned char* s_seq1 = s_rnk + (kRankPass ? size_t(kPlaneRows) * Wn * 4 : 0);          // symbols of Seq1
+    unsigned char* s_seq1 = s_rnk + (kRankPass ? size_t(kPlaneRows) * Wn * (kRank2 ? 8 : 4) : 0);   // symbols of Seq1
     const int seq1_span = stripe_seq1_span(SG);                                             // every position the build gathers
     uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_seq1 + seq1_span);
     const int ro_team = SG.Q * SG.ro_stride;                                                // words per team (class offsets)
     uint32_t* s_ror_all = s_ro_all + size_t(SG.teams) * ro_team;                            // rank offsets (kRankPass)
-    StripeSlot* s_slot_all = reinterpret_cast<StripeSlot*>(s_ror_all + (kRankPass ? size_t(SG.teams) * ro_team : 0));
+    StripeSlot* s_slot_all = reinterpret_cast<StripeSlot*>(s_ror_all + (kRor ? size_t(SG.teams) * ro_team : 0));
     const int slots_team = SG.T * SG.Q;                                                     // [warp of the team][query of the task]
-    __shared__ uint32_t s_col[3][32];
+    __shared__ uint32_t s_col[4][32];
     __shared__ __align__(16) uint8_t s_code[kSymbols * kRowPad];                            // the pair table, for the finish step
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
@@ -256,32 +348,37 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     const int task_stride = SG.teams * int(gridDim.x);
     const int first_task = team * int(gridDim.x) + int(blockIdx.x);
 
-    // Per-step row offsets of a task's queries (needs nothing but the queries): a warp of the team takes whole queries, its
-    // lanes stride the steps; the byte loads of a query are issued together, padding steps read the all-zero row.
+    // Per-step row offsets of a task's queries (needs nothing but the queries).  The team's threads stride the flattened
+    // (query, step) space; a thread's byte loads -- up to 8 per round -- are all issued before the first is used, so a round
+    // costs one trip to L2 / HBM, and padding steps read the all-zero row.
     auto build_row_offsets = [&](int task) {
         const int q0 = task * SG.Q;
         const int nqt = (G.nq - q0) < SG.Q ? (G.nq - q0) : SG.Q;
+        const uint8_t* src = P.seq2s + int64_t(q0) * len2;
+        const int total = nqt * steps;
         bool bad = false;
-        for (int jj = tw; jj < nqt; jj += SG.T) {
-            const uint8_t* src = P.seq2s + int64_t(q0 + jj) * len2;
-            uint32_t* ro = s_ro + jj * SG.ro_stride;
-            uint32_t* ror = s_ror + jj * SG.ro_stride;
-            for (int base = lane; base < steps; base += 8 * 32) {
-                uint8_t v[8];
+        int jj = 0, st = tw * 32 + lane;                            // element tt of the flattened space, kept as (query, step)
+        while (st >= steps) { st -= steps; jj++; }
+        for (int base = tw * 32 + lane; base < total; base += 8 * team_threads) {
+            uint8_t v[8];
+            int qj[8], qs[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (base + u * 32) < len2 ? src[base + u * 32] : uint8_t('A');
+            for (int u = 0; u < 8; u++) {
+                qj[u] = jj; qs[u] = st;
+                v[u] = (base + u * team_threads < total && st < len2) ? src[jj * len2 + st] : uint8_t('A');
+                st += team_threads;
+                while (st >= steps) { st -= steps; jj++; }
+            }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int st = base + u * 32;
-                    if (st < steps) {
-                        uint32_t row = kZeroRow;
-                        if (st < len2) {
-                            row = symbol_of(v[u]);
-                            if (row == 0xFFu) { bad = true; row = 0; }
-                        }
-                        ro[st] = (row * uint32_t(Wn) + uint32_t(st)) * 8u;
-                        if (kRankPass) ror[st] = (row * uint32_t(Wn) + uint32_t(st)) * 4u;
+            for (int u = 0; u < 8; u++) {
+                if (base + u * team_threads < total) {
+                    uint32_t row = kZeroRow;
+                    if (qs[u] < len2) {
+                        row = symbol_of(v[u]);
+                        if (row == 0xFFu) { bad = true; row = 0; }
                     }
+                    s_ro[qj[u] * SG.ro_stride + qs[u]] = (row * uint32_t(Wn) + uint32_t(qs[u])) * 8u;
+                    if (kRor) s_ror[qj[u] * SG.ro_stride + qs[u]] = (row * uint32_t(Wn) + uint32_t(qs[u])) * 4u;
                 }
             }
         }
@@ -296,7 +393,7 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     if (team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
 
     // ---- the striped window, built once per block ------------------------------------------------------
-    for (int k = tid; k < 3 * 32; k += nthreads) s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
+    for (int k = tid; k < 4 * 32; k += nthreads) s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
     for (int k = tid; k < kSymbols * kRowPad / 4; k += nthreads)
         reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(&T.code[0][0])[k];
     {
@@ -333,7 +430,7 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     // p + (t + k) S), so each follows from its predecessor by a one-bit shift that takes in ONE new position per row --
     // 2 ALU instructions per row instead of another transpose (the window has S + steps words, only S distinct columns).
     {
-        constexpr int nkinds = kRankPass ? 3 : 2;
+        constexpr int nkinds = kRankPass ? 2 + K : 2;
         for (int task = tid; task < S * nkinds; task += nthreads) {
             const int kind = task / S, p = task - kind * S;
             const uint32_t* col = s_col[kind];
@@ -341,8 +438,8 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
 #pragma unroll
             for (int t = 0; t < 32; t++) m[t] = col[s_seq1[p + t * S]];
             transpose32(m);
-            uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk);
-            const int wstep = kind < 2 ? 2 : 1;                                             // words between neighbours of a row
+            uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk) + (kRank2 ? kind - 2 : 0);
+            const int wstep = (kind < 2 || kRank2) ? 2 : 1;                                 // words between neighbours of a row
             for (int k = 0;; k++) {
                 const int word = p + k * S;
                 if (word >= Wn) break;
@@ -372,6 +469,151 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
         StripeSlot* my_slot = s_slot + tw * SG.Q;
         if (lane < nqt) my_slot[lane] = StripeSlot{ kKeyNone, 0x7FFFFFFF, 0u, 0u, 0u, 0u, 0u };
         __syncwarp();
+        if constexpr (SEQ) {
+            // ---- one warp owns the task: running best in bit planes ---------------------------------------------------
+            // Per bit position (= per stripe of the lane) the best key seen over the warp's passes of the lane's current query
+            // stays in the vertical domain: a pass costs the key build plus one bit-sliced compare-select (~70 LOP3) instead of
+            // arg-max + warp reduction + settling + slot traffic.  Unresolved offsets take part with their upper bounds and a
+            // flag; only when a query's overall winner is such a bound AND the bound turns out not to be tight is the query
+            // searched again the exact way (a few per cent of short-query batches).
+            constexpr int PK = SlicedKeys<NB, K>::P;
+            constexpr int kPassPlanes = 6;                          // kStripeMaxPasses = 64
+            const int64_t kfloor = SP.kfl;
+            uint32_t best[PK], bpass[kPassPlanes], bres = 0u, bvalid = 0u;
+#pragma unroll
+            for (int k = 0; k < PK; k++) best[k] = 0u;
+#pragma unroll
+            for (int k = 0; k < kPassPlanes; k++) bpass[k] = 0u;
+            int lq = -1;                                            // query whose candidates this lane's planes hold
+
+            // lanes whose planes belong to a query other than `jnext` hand their best candidate to that query's slot
+            auto flush = [&](int jnext) {
+                const bool go = lq >= 0 && lq != jnext;
+                if (!__any_sync(0xFFFFFFFFu, go)) return;
+                uint32_t v = 0;
+                int bb = 0;
+                const bool have = sliced_argmax<PK>(best, go ? bvalid : 0u, v, bb);
+                int pw = 0;
+#pragma unroll
+                for (int k = 0; k < kPassPlanes; k++) pw |= int((bpass[k] >> bb) & 1u) << k;
+                const Cand c = have ? Cand{ int64_t(v) - SP.bias, int32_t(pw * 32 + lane - lq * S + bb * S) } : none;
+                const uint32_t cres = have ? (bres >> bb) & 1u : 0u;
+                uint32_t todo = __ballot_sync(0xFFFFFFFFu, go);
+                while (todo) {                                      // one old query at a time (warp-uniform)
+                    const int jj = __shfl_sync(0xFFFFFFFFu, lq, __ffs(int(todo)) - 1);
+                    const bool in = go && lq == jj;
+                    const Cand wb = warp_best(in ? c : none);
+                    const uint32_t own = __ballot_sync(0xFFFFFFFFu, in && wb.key != kKeyNone && c.key == wb.key && c.off == wb.off);
+                    const uint32_t wres = own ? __shfl_sync(0xFFFFFFFFu, cres, __ffs(int(own)) - 1) : 0u;
+                    PSA_CHECK(jj >= 0 && jj < nqt);
+                    if (lane == 0 && wb.key != kKeyNone && better(wb.key, wb.off, my_slot[jj].key, my_slot[jj].off))
+                        my_slot[jj] = StripeSlot{ wb.key, wb.off, 0u, wres, 0u, 0u, 0u };   // .na: 1 = the key is exact (resolved offset)
+                    __syncwarp();
+                    todo &= ~__ballot_sync(0xFFFFFFFFu, in);
+                }
+                if (go) { bvalid = 0u; bres = 0u; lq = -1; }
+            };
+
+            // counters of one pass (shared by the running-best loop and the exact re-search)
+            auto count_pass = [&](int jc, int lc, uint32_t vmask, VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, uint32_t (&racc)[K > 0 ? K : 1]) {
+                const uint32_t* ro = s_ro + jc * SG.ro_stride;
+#pragma unroll
+                for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0u;
+                racc[0] = ~vmask;
+                if constexpr (kRank2) {
+                    const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(lc) * 8;
+                    for (int g = 0; g < groups; g++) {
+                        stripe_rank_group2(racc, pr, ro + g * 32);
+                        if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+                    }
+                } else if constexpr (kRankPass) {
+                    const uint32_t* ror = s_ror + jc * SG.ro_stride;
+                    const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(lc) * 4;
+                    for (int g = 0; g < groups; g++) {
+                        stripe_rank_group(racc[0], pr, ror + g * 32);
+                        if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+                    }
+                }
+                A.clear(); B.clear(); C.clear();
+                const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(lc) * 8;
+                for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+                if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
+            };
+
+            int j = 0, l = lane;
+            while (l >= S) { l -= S; j++; }
+            for (int p = 0; p < passes; p++) {
+                const bool lane_on = p * 32 + lane < lanes_task;
+                flush(lane_on ? j : -2);
+                if (lane_on) lq = j;
+                const int jc = lane_on ? j : 0, lc = lane_on ? l : 0;   // idle lanes shadow lane 0 (addresses stay valid)
+                const uint32_t vmask = lane_on ? stripe_valid_mask(lc, S, noff) : 0u;
+                VCounter<NUP> A, B, C;
+                uint32_t racc[K > 0 ? K : 1];
+                count_pass(jc, lc, vmask, A, B, C, racc);
+                SlicedKeys<NB, K> keys;
+                keys.build(SP, A, B, C, racc);
+                const uint32_t valid = vmask & ~keys.nokey;
+                // new > old, MSB first; a position without an old candidate takes the new one
+                uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = PK - 1; k >= 0; k--) {
+                    gt |= eq & keys.acc[k] & ~best[k];
+                    eq &= ~(keys.acc[k] ^ best[k]);
+                }
+                gt = ((gt & bvalid) | ~bvalid) & valid;
+#pragma unroll
+                for (int k = 0; k < PK; k++) best[k] = (gt & keys.acc[k]) | (~gt & best[k]);
+                bres = (gt & keys.rmask) | (~gt & bres);
+#pragma unroll
+                for (int k = 0; k < kPassPlanes; k++) bpass[k] = ((p >> k) & 1) ? (bpass[k] | gt) : (bpass[k] & ~gt);
+                bvalid |= valid;
+                l += 32;
+                while (l >= S) { l -= S; j++; }
+            }
+            flush(-2);
+            // ---- finish the task's queries ---------------------------------------------------------------------------
+            for (int jj = 0; jj < nqt; jj++) {
+                const StripeSlot r = my_slot[jj];
+                const int q = q0 + jj;
+                const int64_t qbeg = int64_t(q) * len2;
+                if (r.key == kKeyNone) { stripe_emit_none(T, P, q); continue; }
+                int cnt[4], rank, first_i, off = r.off;
+                stripe_walk(P, s_seq1, s_code, qbeg, len2, off, cnt, rank, first_i);
+                if (!r.na && (rank <= 0 || T.kdiff[rank] != kfloor)) {
+                    // The winner is an unresolved offset and its bound was not tight: its true key is lower, and candidates the
+                    // planes dropped in its favour may beat it.  Search this one query again the exact way (per pass: resolved
+                    // arg-max, then settle every unresolved offset that could still win -- what the linear kernels do).
+                    Cand lb = none;
+                    const int plo = (jj * S) >> 5, phi = ((jj + 1) * S - 1) >> 5;
+                    for (int p = plo; p <= phi; p++) {
+                        const int f = p * 32 + lane;
+                        const bool on = f < lanes_task && f >= jj * S && f < (jj + 1) * S;
+                        const int lc = on ? f - jj * S : 0;
+                        const uint32_t vmask = on ? stripe_valid_mask(lc, S, noff) : 0u;
+                        VCounter<NUP> A, B, C;
+                        uint32_t racc[K > 0 ? K : 1];
+                        count_pass(jj, lc, vmask, A, B, C, racc);
+                        SlicedKeys<NB, K> keys;
+                        keys.build(SP, A, B, C, racc);
+                        Cand mine = none, ub = none;
+                        const uint32_t umask = keys.scan(vmask, lc, mine, ub, S);
+                        if (on && better(mine.key, mine.off, lb.key, lb.off)) lb = mine;
+                        const Cand wb = settle_unresolved(T, P, keys, on ? lb : none, on ? ub : none, on ? umask : 0u, lc, qbeg, len2, S);
+                        if (on && wb.key != kKeyNone && wb.off % S == lc && better(wb.key, wb.off, lb.key, lb.off)) lb = wb;
+                    }
+                    const Cand fin = warp_best(lb);
+                    if (fin.key == kKeyNone) { stripe_emit_none(T, P, q); continue; }
+                    off = fin.off;
+                    stripe_walk(P, s_seq1, s_code, qbeg, len2, off, cnt, rank, first_i);
+                }
+                stripe_emit(T, P, s_seq1, q, qbeg, off, cnt, rank, first_i);
+            }
+            __syncwarp();                                           // this task's row offsets and slots are consumed
+            if (task + task_stride < SG.ntasks) build_row_offsets(task + task_stride);
+            __syncwarp();
+            continue;
+        }
         // Lane-local running best of the lane's current query, carried across this warp's passes: (key, offset), the pass
         // that produced it, and a warp-uniform floor -- the best RESOLVED key seen so far in the query, as the biased 32-bit
         // value of the bit-sliced keys -- under which nothing needs a second look.
@@ -385,8 +627,16 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
             const uint32_t vmask = lane_on ? stripe_valid_mask(l, S, noff) : 0u;
             const uint32_t* ro = s_ro + j * SG.ro_stride;
             uint32_t racc[K > 0 ? K : 1];
+#pragma unroll
+            for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0u;
             racc[0] = ~vmask;                                       // offsets outside the range count as saturated
-            if (kRankPass) {
+            if constexpr (kRank2) {
+                const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 8;
+                for (int g = 0; g < groups; g++) {
+                    stripe_rank_group2(racc, pr, ro + g * 32);
+                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
+                }
+            } else if constexpr (kRankPass) {
                 const uint32_t* ror = s_ror + j * SG.ro_stride;
                 const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 4;
                 for (int g = 0; g < groups; g++) {
@@ -403,7 +653,7 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
 
             // ---- keys of the lane's 32 offsets; the lane's best joins its running best ------------------------------
             SlicedKeys<NB, K> keys;                                 // stripe mode is only entered when the bit-sliced keys apply
-            keys.build(T, len2, A, B, C, racc, key_planes, key_bias);
+            keys.build(SP, A, B, C, racc);
             const int jlo = (p * 32) / S;
             const int jhi = ((p * 32 + 31) / S) < (nqt - 1) ? ((p * 32 + 31) / S) : (nqt - 1);
             // One arg-max over ALL valid offsets, resolved keys and unresolved bounds alike.  Resolved winner: it is the lane's
@@ -498,11 +748,11 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     }
 }
 
-size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, bool rank_pass)
+size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, int rank_planes_read)
 {
-    size_t b = size_t(kPlaneRows) * g.Wn * (rank_pass ? 12 : 8);
+    size_t b = size_t(kPlaneRows) * g.Wn * (8 + (rank_planes_read == 2 ? 8 : rank_planes_read == 1 ? 4 : 0));
     b += size_t(std::max<int64_t>(stripe_seq1_span(g), (len1 + 15) & ~int64_t(15)));
-    b += size_t(g.teams) * g.Q * g.ro_stride * 4 * (rank_pass ? 2 : 1);
+    b += size_t(g.teams) * g.Q * g.ro_stride * 4 * (rank_planes_read == 1 ? 2 : 1);
     b += size_t(g.teams) * g.T * g.Q * sizeof(StripeSlot);
     return b;
 }
@@ -511,7 +761,7 @@ size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, bool rank_pass)
 
 // Shape of a stripe-mode launch for nq queries of len2 symbols against len1, or ok = 0 when the mode does not apply
 // (window beyond shared memory, or so few lanes per query that whole warps would idle).
-StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, int sm_count, bool force)
+StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, int rank_planes_read, int sm_count, bool force)
 {
     StripeGeom g{};
     const int64_t noff = len1 - len2 + 1;
@@ -524,7 +774,9 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, i
     // per two cycles per scheduler) plus its epilogue; a task adds row offsets, barriers and the finish.  The block takes
     // the larger of (all its work spread over 4 schedulers) and (the longest chain one team runs in sequence, stretched
     // when fewer than four warps per scheduler are counting and the ALU pipe cannot be kept full).
-    const double pass_c = double(steps / 32) * 560.0 + 700.0;
+    // per pass: the unrolled groups plus the epilogue -- ~400 cycles when one warp owns the task (running best in bit planes),
+    // ~1100 when several warps share it (arg-max, settling and slot traffic per pass)
+    const double pass_groups_c = double(steps / 32) * 560.0;
     double best_cost = 0, best_busy = 0;
     bool have = false;
     g.threads = stripe_threads_for_len2(len2);
@@ -543,11 +795,12 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, i
             if (teams < 1 || (dbg_t > 0 && Tw != dbg_t)) continue;
             StripeGeom c = g;
             c.Q = Q; c.passes = passes; c.T = Tw; c.teams = teams; c.ntasks = ntasks;
-            if (stripe_smem_bytes(c, len1, rank_pass) > kStripeSmemMax) continue;
+            if (stripe_smem_bytes(c, len1, rank_planes_read) > kStripeSmemMax) continue;
             const int ppw = (passes + Tw - 1) / Tw;                                      // passes per warp, in sequence
             const int rounds = (tasks_b + teams - 1) / teams;                            // tasks per team, in sequence
             const double busy = double(std::min(teams, tasks_b)) * Tw;                   // warps counting at the same time
-            const double stretch = std::max(1.0, 16.0 / busy);
+            const double stretch = std::max(1.0, 0.75 + 4.0 / busy);                      // few warps per scheduler: dependent ALU chains show
+            const double pass_c = pass_groups_c + (Tw == 1 ? 400.0 : 1100.0);
             const double task_c = 500.0 + (Tw > 1 ? 300.0 : 0.0);
             const double util = double(Q) * double(S) / (32.0 * passes);                 // lanes that hold offsets
             const double spread = std::ceil(double(tasks_b) * passes / 4.0) * pass_c;    // warp w issues on scheduler w % 4
@@ -566,7 +819,8 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, i
     if (!have) return g;
     // lanes that idle in the last pass of a task: below ~70 % the linear kernels' packing does better
     if (!force && double(g.Q) * double(S) / (32.0 * g.passes) < 0.70) return g;
-    g.smem = stripe_smem_bytes(g, len1, rank_pass);
+    g.smem = stripe_smem_bytes(g, len1, rank_planes_read);
+    g.rank_planes_read = rank_planes_read;
     g.blocks = std::min(sm_count, g.ntasks);
     g.ok = 1;
     return g;
@@ -574,10 +828,36 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, bool rank_pass, i
 
 namespace {
 
-template <int NB, int K>
-void launch_stripe_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, const StripeGeom& SG, bool derive,
-                        int key_planes, int64_t key_bias, cudaStream_t stream)
+// the constants SlicedKeys::build derives from the table, for K tracked rank planes (mirrors that function line by line)
+SlicedPlan make_sliced_plan(const DeviceTable& T, int64_t len2, int K, int64_t bias)
 {
+    SlicedPlan S{};
+    S.ka = int32_t(T.kcls[1] - T.kcls[0]);
+    S.kb = int32_t(T.kcls[2] - T.kcls[0]);
+    S.kc = int32_t(T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0]);
+    const int floor_rank = T.nranks - K;
+    S.floor_none = floor_rank <= 0;
+    S.floor_exact = S.floor_none || (floor_rank == 1 && !T.has_none);
+    S.kfl = S.floor_none ? 0 : T.kdiff[floor_rank];
+    int64_t ktop[4] = { 0, 0, 0, 0 };
+    int64_t dmin = S.floor_none ? INT64_MAX : S.kfl;
+    for (int k = 0; k < K; k++) {
+        ktop[k] = T.kdiff[(T.nranks - k) > 0 ? (T.nranks - k) : 0];
+        dmin = std::min(dmin, ktop[k]);
+    }
+    if (dmin == INT64_MAX) dmin = 0;
+    S.c0 = uint32_t(bias + len2 * T.kcls[0] + dmin);
+    for (int k = 0; k < K; k++) S.dv[k] = uint32_t(ktop[k] - dmin);
+    S.dv_floor = S.floor_none ? 0u : uint32_t(S.kfl - dmin);
+    S.bias = bias;
+    return S;
+}
+
+template <int NB>
+void launch_stripe_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, const StripeGeom& SG, int K, bool derive,
+                      int64_t key_bias, cudaStream_t stream)
+{
+    const SlicedPlan SP = make_sliced_plan(T, G.uniform_len2, K, key_bias);
     auto go = [&](auto kernel, bool (&done)[64]) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -585,17 +865,14 @@ void launch_stripe_inst(const DeviceTable& T, const BatchGeom& G, const BatchPtr
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripeSmemMax));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
-        kernel<<<SG.blocks, SG.threads, SG.smem, stream>>>(T, G, P, SG, key_planes, key_bias);
+        kernel<<<SG.blocks, SG.threads, SG.smem, stream>>>(T, G, P, SG, SP);
     };
-    if constexpr (K == 1) {
-        if (derive) {
-            static bool done_dr[64];
-            go(k_stripe<NB, K, true>, done_dr);
-            return;
-        }
-    }
-    static bool done[64];
-    go(k_stripe<NB, K, false>, done);
+    static bool done[8][64];
+    const bool seq = SG.T == 1;
+    if (K == 0) { if (seq) go(k_stripe<NB, 0, false, true>, done[0]); else go(k_stripe<NB, 0, false, false>, done[1]); }
+    else if (derive) { if (seq) go(k_stripe<NB, 1, true, true>, done[2]); else go(k_stripe<NB, 1, true, false>, done[3]); }
+    else if (K == 1) { if (seq) go(k_stripe<NB, 1, false, true>, done[4]); else go(k_stripe<NB, 1, false, false>, done[5]); }
+    else { if (seq) go(k_stripe<NB, 2, false, true>, done[6]); else go(k_stripe<NB, 2, false, false>, done[7]); }
 }
 
 } // namespace
@@ -618,15 +895,12 @@ void launch_stripe(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P,
     const int64_t len2 = G.uniform_len2;
     int64_t key_bias = 0;
     const int nb = len2 <= 127 ? 7 : 10;
-    const int key_planes = sliced_key_planes(T, len2, nb, &key_bias);
+    sliced_key_planes(T, len2, nb, &key_bias);
     const bool derive = stripe_derives_rank(T, rank_planes, allow_derive);
-    if (nb == 7) {
-        if (rank_planes == 0) launch_stripe_inst<7, 0>(T, G, P, SG, derive, key_planes, key_bias, stream);
-        else launch_stripe_inst<7, 1>(T, G, P, SG, derive, key_planes, key_bias, stream);
-    } else {
-        if (rank_planes == 0) launch_stripe_inst<10, 0>(T, G, P, SG, derive, key_planes, key_bias, stream);
-        else launch_stripe_inst<10, 1>(T, G, P, SG, derive, key_planes, key_bias, stream);
-    }
+    // planes the kernel reads: none when the top rank is derived (or no plane is tracked), else what the planner reserved room for
+    const int K = rank_planes == 0 ? 0 : derive ? 1 : SG.rank_planes_read;
+    if (nb == 7) launch_stripe_nb<7>(T, G, P, SG, K, derive, key_bias, stream);
+    else launch_stripe_nb<10>(T, G, P, SG, K, derive, key_bias, stream);
 }
 
 } // namespace psa

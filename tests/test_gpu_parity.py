@@ -499,16 +499,18 @@ def test_stripe_mode_dispatch(ctx, port, synth):
     assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("kernel_launches")) == (1, 79, 1)
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
-    wl = synth.workload("c5", nq=3000)                                    # short queries: batch mode unless stripe mode is forced
+    wl = synth.workload("c5", nq=6000)                                    # short queries, many of them: one warp per task
     got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
-    assert (ctx.stat("stripe_mode"), ctx.stat("batch_mode")) == (0, 1)
-    ctx.set_option("stripe_mode", 1)
-    forced = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
     assert (ctx.stat("stripe_mode"), ctx.stat("stripe_lanes"), ctx.stat("stripe_team_warps"), ctx.stat("kernel_launches")) == (1, 311, 1, 1)
+    ctx.set_option("stripe_mode", 0)
+    linear = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    assert (ctx.stat("stripe_mode"), ctx.stat("batch_mode")) == (0, 1)
     ctx.set_option("stripe_mode", -1)
     exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:500])
     assert all(same_answer(g, e) and g.counts == e.counts for g, e in zip(got, exp))
-    assert [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in forced] == [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in got]
+    assert [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in linear] == [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in got]
+    few = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:40])  # short queries, few of them: teams of several warps -> linear kernels
+    assert ctx.stat("stripe_mode") == 0 and all(same_answer(g, e) for g, e in zip(few, exp))
     wl = synth.workload("c3", nq=40)
     ctx.search_batch([1.5, 2.6, 0.1, 0.2], True, wl.seq1, wl.queries)              # order needs the reference's double
     assert ctx.stat("stripe_mode") == 0
