@@ -97,6 +97,8 @@ const char* psa_last_error(const psa_context* ctx);
                      order with small keys, all offsets, window within shared memory.  Then ONE kernel does everything:
                      each persistent block builds a striped bit-plane window of Seq1 in shared memory and its warp teams
                      scan and finish their queries against it (no k_profile / k_finish launch)
+     "single_launch" 1 a single query in exact integer order runs as ONE cooperative launch (k_single: per-block striped windows,
+                     grid barrier, combine, finish) | 0 the k_profile / k_scan (slices) / k_combine chain
      "slices"        0 auto | 1 never | n>=2 cut a single query into n ranges of alignment steps
      "sliced_keys"   1 bit-sliced epilogue when the weights allow it | 0 transpose + scalar keys
      "fused_finish"  1 the finish step runs inside the kernel before it where that saves a launch: in the scan block when
@@ -111,7 +113,7 @@ const char* psa_last_error(const psa_context* ctx);
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
    order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact",
-   "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", and the host-side split of the
+   "single_launch", "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", and the host-side split of the
    last psa_search_batch in ns: "host_plan_ns", "host_prepare_ns", "host_enqueue_ns", "host_wait_ns", "host_total_ns".
    Unknown -> -1. */
 long long psa_get_stat(const psa_context* ctx, const char* name);

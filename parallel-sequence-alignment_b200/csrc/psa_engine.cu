@@ -50,9 +50,10 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants, sync;
     SliceGeom SG{};
     StripeGeom stripe{};       // ok != 0: this shard runs in stripe mode (one launch: window + scan + finish)
+    SingleGeom single{};       // ok != 0: this shard (one query, exact order) runs as one cooperative launch (k_single)
     PinBuf h_qoff, h_tile_start, h_out;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
@@ -103,6 +104,7 @@ struct psa_context {
     int opt_sliced_keys = 1;   // 1: bit-sliced epilogue when the keys allow it, 0: always transpose + scalar keys
     int opt_batch_mode = -1;   // -1 auto, 0 never, 1 whenever the queries fit one window
     int opt_stripe_mode = -1;  // -1 auto, 0 never, 1 whenever the batch qualifies (equal lengths, exact order, window fits)
+    int opt_single_launch = 1; // 1: a single query in exact order runs as one cooperative launch (k_single), 0: the k_profile / k_scan / k_combine chain
     // current batch
     bool prepared = false, ran = false;
     bool range_split = false;  // single query split by offset range over the GPUs
@@ -175,7 +177,7 @@ void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
     for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
-                       &d.cls_planes, &d.rank_planes, &d.mutants })
+                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
@@ -284,10 +286,26 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         ht[nq] = (int32_t)tiles;
     }
 
+    // One query, exact order, few warp-tiles: the whole search as one cooperative launch (k_single)
+    d.single = SingleGeom{};
+    if (scan && nq == 1 && last >= 0 && ctx->table.exact && ctx->rank_planes <= 1 && ctx->opt_single_launch != 0 && ctx->opt_slices == 0 &&
+        ctx->opt_scan_warps == 0 && ctx->max_len2 >= 64)
+        d.single = single_plan(len1, ctx->max_len2, first, last, d.sm_count);
+
     // Slice mode: one query whose warp-tiles cannot fill the GPU is also cut along the alignment steps
     d.SG = SliceGeom{};
     d.SG.allow_derive = ctx->opt_derive_rank != 0;
     int fin_tile = tile;
+    if (d.single.ok) {
+        fin_tile = kCombineTile;
+        tiles = (last - tile_base(first) + fin_tile - 1) / fin_tile;    // tile records come from the combine phase
+        uniform = tiles;
+        if ((rc = ensure_dev(ctx, d.partial, sizeof(uint2) * (size_t)d.single.slices * d.single.tiles * 1024))) return rc;
+        if (!d.sync.p) {
+            if ((rc = ensure_dev(ctx, d.sync, 64))) return rc;
+            PSA_CUDA(ctx, cudaMemsetAsync(d.sync.p, 0, 64, d.stream));
+        }
+    } else
     if (scan && !ctx->batch_mode && nq == 1 && last >= 0 && ctx->opt_slices != 1 && ctx->max_len2 >= 256) {
         const int64_t span = last - tile_base(first);
         const int64_t warp_tiles = (span + 1023) / 1024;
@@ -397,7 +415,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
     d.P.code_table = (uint8_t*)d.code_table.p;
     d.P.partial = (uint2*)d.partial.p;
-    d.P.partial_stride = int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
+    d.P.partial_stride = d.single.ok ? int64_t(d.single.tiles) * 1024 : int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
+    d.P.sync = (int32_t*)d.sync.p;
     d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // the counter sits behind the records
     d.P.err_flag = d.h_err;                                                  // unified addressing: the host pointer is the device pointer
     d.P.cls_planes = (uint2*)d.cls_planes.p;
@@ -422,6 +441,16 @@ int run_device(psa_context* ctx, DeviceState& d, bool timed)
     PSA_CUDA(ctx, cudaSetDevice(d.dev));
     if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     d.P.run_tag = next_run_tag(d);
+    if (ctx->engine == 2 && d.single.ok) {
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
+        launch_single(ctx->table, d.G, d.P, ctx->rank_planes, d.single, d.stream);
+        if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk1, d.stream));
+        d.st_launches += 1;
+        PSA_CUDA(ctx, cudaGetLastError());
+        if (timed) PSA_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+        d.st_tiles += d.G.total_tiles;
+        return PSA_OK;
+    }
     if (ctx->engine == 2 && d.stripe.ok) {
         if (timed && ctx->opt_kernel_events) PSA_CUDA(ctx, cudaEventRecord(d.evk0, d.stream));
         launch_stripe(ctx->table, d.G, d.P, ctx->rank_planes, ctx->opt_derive_rank != 0, d.stripe, d.stream);
@@ -571,6 +600,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "batch_mode") && value >= -1 && value <= 1) { ctx->opt_batch_mode = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "stripe_mode") && value >= -1 && value <= 1) { ctx->opt_stripe_mode = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "single_launch") && value >= 0 && value <= 1) { ctx->opt_single_launch = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "scan_warps") && value >= 0 && value <= kScanWarps) { ctx->opt_scan_warps = (int)value; return PSA_OK; }
     return PSA_ERR_ARG;
 }
@@ -613,12 +643,13 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
     auto first_active = [ctx]() -> const DeviceState* { for (const DeviceState& d : ctx->devs) if (d.active) return &d; return nullptr; };
     if (!std::strcmp(name, "stripe_mode")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? 1 : 0; }
+    if (!std::strcmp(name, "single_launch")) { const DeviceState* d = first_active(); return d && d->single.ok ? 1 : 0; }
     if (!std::strcmp(name, "stripe_queries_per_task")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.Q : 0; }
     if (!std::strcmp(name, "stripe_team_warps")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.T : 0; }
     if (!std::strcmp(name, "stripe_teams")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.teams : 0; }
     if (!std::strcmp(name, "stripe_lanes")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.S : 0; }
     if (!std::strcmp(name, "batch_mode")) { const DeviceState* d = first_active(); return ctx->batch_mode && !(d && d->stripe.ok) ? 1 : 0; }
-    if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.slices; return 1; }
+    if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.single.ok ? d.single.slices : d.SG.slices; return 1; }
     if (!std::strcmp(name, "packed_queries")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_q; return 0; }
     if (!std::strcmp(name, "packed_warps")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.SG.pack_warps; return 0; }
     if (!std::strcmp(name, "exact")) return ctx->table.exact;

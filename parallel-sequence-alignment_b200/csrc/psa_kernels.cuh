@@ -25,6 +25,7 @@ struct BatchPtrs {
     uint2*         cls_planes;
     uint32_t*      rank_planes;
     int64_t        plane_words; // words per row
+    int32_t*       sync;        // k_single: [0] grid barrier, [1] "last block" ticket; zero between launches (the last block resets them)
 };
 
 #if defined(__CUDACC__)
@@ -91,6 +92,22 @@ void launch_stripe(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P,
                    const StripeGeom& SG, cudaStream_t stream);
 // bit-sliced key epilogue: plane count for this table and query length (0 = keys too wide), and the bias that makes keys non-negative
 int sliced_key_planes(const DeviceTable& T, int64_t max_len2, int nb, int64_t* bias_out);
+
+// One query in one launch (psa_single.cu): (1024-offset tile) x (step slice) units build their own striped windows, a grid
+// barrier, then combine + finish in the same kernel.
+struct SingleGeom {
+    int ok = 0;
+    int slice_steps = 0;   // alignment steps per slice (multiple of 32, <= 992)
+    int slices = 0;
+    int tiles = 0;         // 1024-offset tiles from tile_base(first)
+    int units = 0;         // tiles x slices
+    int Wn = 0;            // window words per plane row = 32 + slice_steps
+    int span = 0;          // Seq1 symbols a unit can touch
+    int blocks = 0;
+    size_t smem = 0;
+};
+SingleGeom single_plan(int64_t len1, int64_t len2, int64_t first, int64_t last, int sm_count);
+void launch_single(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, int rank_planes, const SingleGeom& SG, cudaStream_t stream);
 
 // ---- launchers (all asynchronous on `stream`) -------------------------------------------------
 // exact scalar kernel over every tile (engine 1)

@@ -488,5 +488,98 @@ __device__ __forceinline__ void finish_query_warp(const DeviceTable& T, const Ba
 }
 
 
+// -------------------------------------------------------------------------------------------------
+// Combine (slice mode): one thread per offset of a 256-offset tile adds the slices' partial counts, forms the key, and the
+// block reduces to the tile's best.  Offsets that met no tracked rank plane are settled here when the order must be exact:
+// those whose bound could beat the block's best walk the alignment for their true best rank (rare, and only for the few
+// that matter).  Used by k_combine (psa_scan.cu, one tile per block) and k_single (psa_single.cu, tiles round the blocks
+// after a grid barrier -- there the partial counts were written by other blocks of the SAME launch: ld.cg).
+// -------------------------------------------------------------------------------------------------
+constexpr int kCombineThreads = 256;
+
+template <int K, bool PDL>
+__device__ __forceinline__ void combine_tile(const DeviceTable& T, const BatchGeom& G, const BatchPtrs& P, const int slices, const int tile)
+{
+    __shared__ Cand s_part[kCombineThreads / 32];
+    __shared__ int64_t s_top[kCombineThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len2 = G.uniform_len2;
+    const int64_t first = G.first, last = G.last;                   // slice mode always runs on an explicit range
+    const int64_t rel = int64_t(tile) * kCombineThreads + tid;
+    PSA_CHECK(tile < G.total_tiles && G.uniform_len2 > 0 && G.last >= 0);
+    const int64_t n = tile_base(first) + rel;
+    const bool valid = n >= first && n < last;
+
+    int64_t key = kKeyNone;
+    bool unresolved = false;
+    const int floor_rank = T.nranks - K;
+    const bool floor_none = floor_rank <= 0;
+    const bool floor_exact = floor_none || (floor_rank == 1 && !T.has_none);
+    const int64_t kfloor = floor_none ? 0 : T.kdiff[floor_rank];
+    if (valid) {
+        uint32_t na = 0, nb = 0, nc = 0, rb = 0;
+        for (int sl = 0; sl < slices; sl++) {
+            PSA_CHECK(rel < P.partial_stride);
+            const uint2 v = __ldcg(P.partial + int64_t(sl) * P.partial_stride + rel);
+            na += v.x & 0xFFFFu; nb += v.x >> 16; nc += v.y & 0xFFFFu; rb |= v.y >> 16;
+        }
+        const int64_t ka = T.kcls[1] - T.kcls[0], kb = T.kcls[2] - T.kcls[0];
+        const int64_t kc = T.kcls[3] - T.kcls[1] - T.kcls[2] + T.kcls[0];
+        key = int64_t(len2) * T.kcls[0] + int64_t(na) * ka + int64_t(nb) * kb + int64_t(nc) * kc;
+        if (K > 0 && rb) {
+            key += T.kdiff[T.nranks - (__ffs(int(rb)) - 1)];        // lowest set plane = best rank present
+        } else if (floor_none) {
+            key = kKeyNone;
+        } else {
+            key += kfloor;
+            unresolved = !floor_exact;
+        }
+    }
+    Cand mine{ unresolved ? kKeyNone : key, unresolved || key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
+    Cand best = block_best<kCombineThreads>(mine, s_part);
+    if (PDL) pdl_launch_dependents();
+    if (T.exact) {
+        // settle: any unresolved offset whose bound could beat the block's best looks up its true rank
+        int again = __syncthreads_or(unresolved && !better(best.key, best.off, key, int32_t(n)));
+        while (again) {
+            if (unresolved && !better(best.key, best.off, key, int32_t(n))) {
+                uint32_t rmax = 0;
+                for (int i = 0; i < len2; i++) {
+                    uint32_t c1 = symbol_of(P.seq1[n + i]), c2 = symbol_of(P.seq2s[i]);
+                    if (c1 == 0xFFu || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+                    rmax = max(rmax, uint32_t(__ldg(P.code_table + c2 * kRowPad + c1)) >> 2);
+                }
+                key = rmax ? key - kfloor + T.kdiff[rmax] : kKeyNone;
+                unresolved = false;
+                mine = Cand{ key, key == kKeyNone ? 0x7FFFFFFF : int32_t(n) };
+            }
+            best = block_best<kCombineThreads>(mine, s_part);
+            again = __syncthreads_or(unresolved && !better(best.key, best.off, key, int32_t(n)));
+        }
+    } else {
+        // re-score mode: per 32-offset word an upper estimate of its keys for k_finish
+        int64_t top = valid ? key : kKeyNone;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int64_t o = __shfl_xor_sync(0xFFFFFFFFu, top, d);
+            top = o > top ? o : top;
+        }
+        if (lane == 0) {
+            P.lane_keys[int64_t(tile) * (kCombineThreads / 32) + warp] = top;
+            s_top[warp] = top;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        TileRec rec;
+        rec.key = best.key; rec.offset = best.off;
+        rec.ub_key = kKeyNone;
+        if (!T.exact)
+            for (int w = 0; w < kCombineThreads / 32; w++) rec.ub_key = s_top[w] > rec.ub_key ? s_top[w] : rec.ub_key;
+        rec.ub_offset = 0x7FFFFFFF; rec.score = 0.0; rec.flags = 0; rec.pad = 0;
+        P.tiles[tile] = rec;
+    }
+}
+
 } // namespace
 } // namespace psa

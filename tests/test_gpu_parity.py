@@ -300,6 +300,7 @@ def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes,
     _set_engine(ctx, 2, planes)
     ctx.set_option("slices", slices)
     ctx.set_option("fused_finish", fused)
+    ctx.set_option("single_launch", 0)                                    # this test is about the k_profile / k_scan / k_combine chain
     try:
         for b in (input_blocks[0], input_blocks[4], input_blocks[6], input_blocks[9]):
             r = ctx.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"])
@@ -319,6 +320,42 @@ def test_slice_mode_single_query(ctx, port, synth, input_blocks, slices, planes,
     finally:
         ctx.set_option("slices", 0)
         ctx.set_option("fused_finish", 1)
+        ctx.set_option("single_launch", 1)
+        _set_engine(ctx, 0)
+
+
+@pytest.mark.parametrize("planes", [-1, 0])
+def test_single_query_in_one_launch(ctx, port, synth, input_blocks, planes):
+    """k_single: one query in exact order = ONE cooperative launch ((tile, slice) units with their own striped windows, grid
+    barrier, combine, finish).  The reference's own problems, planted ties, explicit offset ranges (the gpu_run_program
+    contract), unresolved ranks (0 planes), queries from 64 to 5000 symbols; weights that need the re-score keep the chain."""
+    _set_engine(ctx, 2, planes)
+    try:
+        for b in input_blocks:
+            r = ctx.search(b["weights"], b["goal"] == "maximum", b["seq1"], b["seq2"])
+            assert same_answer(r, b["expect"]), (planes, b["weights_text"], r)
+            if len(b["seq2"]) >= 64 and ctx.stat("exact"):
+                assert (ctx.stat("single_launch"), ctx.stat("kernel_launches")) == (1, 1), b["weights_text"]
+        s1 = synth.letters(191, 30000)
+        core = synth.letters(193, 900)
+        tied = synth.letters(194, 3000) + core + synth.letters(195, 4000) + core + synth.letters(196, 100)
+        for n2 in (64, 65, 777, 2047, 5000):
+            s2 = synth.letters(192, n2)
+            for w in ([1, 3, 4, 2], [1, 1, 1, 1], [5, 1, 2, 3]):
+                for is_max in (True, False):
+                    assert same_answer(ctx.search(w, is_max, s1, s2), port.search(w, is_max, s1, s2, nthreads=4)), (n2, w, is_max)
+                    assert ctx.stat("single_launch") == 1
+                    assert same_answer(ctx.search_range(w, is_max, s1, s2, 1000, 20011), port.search(w, is_max, s1, s2, 1000, 20011)), (n2, w)
+                    assert same_answer(ctx.search_range(w, is_max, s1, s2, 77, 78), port.search(w, is_max, s1, s2, 77, 78))
+        for w in ([1, 3, 4, 2], [1, 1, 1, 1]):
+            for is_max in (True, False):
+                assert same_answer(ctx.search(w, is_max, tied, core), port.search(w, is_max, tied, core))
+        ctx.search([1.5, 2.6, 0.1, 0.2], True, s1, synth.letters(192, 777))              # order needs the reference's double
+        assert ctx.stat("single_launch") == 0
+        with pytest.raises(Exception):
+            ctx.search([1, 3, 4, 2], True, s1, "AB?D" * 50)
+        assert same_answer(ctx.search([1, 3, 4, 2], True, tied, core), port.search([1, 3, 4, 2], True, tied, core))   # and it recovers
+    finally:
         _set_engine(ctx, 0)
 
 
