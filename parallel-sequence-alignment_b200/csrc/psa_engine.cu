@@ -50,7 +50,7 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
-    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants, sync;
+    DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants, sync, table;
     SliceGeom SG{};
     StripeGeom stripe{};       // ok != 0: this shard runs in stripe mode (one launch: window + scan + finish)
     SingleGeom single{};       // ok != 0: this shard (one query, exact order) runs as one cooperative launch (k_single)
@@ -177,7 +177,7 @@ void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
     for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
-                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync })
+                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync, &d.table })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
@@ -362,7 +362,9 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 
     const int64_t plane_words = scan_plane_words(len1);
     if ((rc = ensure_dev(ctx, d.code_table, kSymbols * kRowPad))) return rc;
+    if ((rc = ensure_dev(ctx, d.table, sizeof(DeviceTable)))) return rc;
     if (d.table_epoch != ctx->table_epoch) {
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.table.p, &ctx->table, sizeof(DeviceTable), cudaMemcpyHostToDevice, d.stream));
         // the pair table in global memory for the kernels that index it per thread (divergent reads of a kernel
         // parameter are slow); uploaded when the table changes, not per batch
         PSA_CUDA(ctx, cudaMemcpyAsync(d.code_table.p, ctx->table.code, kSymbols * kRowPad, cudaMemcpyHostToDevice, d.stream));
@@ -417,6 +419,7 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.P.partial = (uint2*)d.partial.p;
     d.P.partial_stride = d.single.ok ? int64_t(d.single.tiles) * 1024 : int64_t(d.SG.scan_tiles) * d.SG.scan_tile;
     d.P.sync = (int32_t*)d.sync.p;
+    d.P.table = (const DeviceTable*)d.table.p;
     d.P.cand_count = (int32_t*)((char*)d.out.p + sizeof(QueryRec) * nq);     // the counter sits behind the records
     d.P.err_flag = d.h_err;                                                  // unified addressing: the host pointer is the device pointer
     d.P.cls_planes = (uint2*)d.cls_planes.p;

@@ -25,6 +25,8 @@ struct BatchPtrs {
     uint2*         cls_planes;
     uint32_t*      rank_planes;
     int64_t        plane_words; // words per row
+    const DeviceTable* table;   // the whole resolved table in global memory (uploaded when it changes): kernels that copy it to shared
+                                //   memory take this pointer instead of a 3.7 KB by-value parameter
     int32_t*       sync;        // k_single: [0] grid barrier, [1] "last block" ticket; zero between launches (the last block resets them)
 };
 

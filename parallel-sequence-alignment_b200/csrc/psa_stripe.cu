@@ -149,24 +149,30 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
         const uint8_t* b = P.seq2s + qbeg;
         const uint32_t want = uint32_t(T.nranks);
         int found = -1;
+        uint32_t found_c2 = 0;                                          // the query symbol at the position found (no second trip to global memory)
         uint8_t nxt = lane < len2 ? b[lane] : uint8_t('A');
         for (int base = 0; base < len2 && found < 0; base += 32) {
             const uint8_t cur = nxt;
             if (base + 32 + lane < len2) nxt = b[base + 32 + lane];
             const int i = base + lane;
             bool hit = false;
+            uint32_t c2 = 0;
             if (i < len2) {
-                uint32_t c1 = a[i], c2 = symbol_of(cur);
+                uint32_t c1 = a[i];
+                c2 = symbol_of(cur);
                 if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
                 hit = (uint32_t(s_code[c2 * kRowPad + c1]) >> 2) == want;
             }
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-            if (m) found = base + __ffs(int(m)) - 1;
+            if (m) {
+                found = base + __ffs(int(m)) - 1;
+                found_c2 = __shfl_sync(0xFFFFFFFFu, c2, __ffs(int(m)) - 1);
+            }
         }
         PSA_CHECK(found >= 0);
         if (lane == 0 && found >= 0) {
-            uint32_t c1 = a[found], c2 = symbol_of(b[found]);
-            if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+            uint32_t c1 = a[found], c2 = found_c2;
+            if (c1 > 26u) { c1 = 0; c2 = 0; }
             const int64_t n1 = int64_t(w.na) - w.nc, n2 = int64_t(w.nb) - w.nc, n3 = w.nc;
             out.offset = r.off;
             out.char_offset = found;
@@ -308,9 +314,16 @@ __device__ __forceinline__ void stripe_emit(const DeviceTable& T, const BatchPtr
 // SEQ : teams of one warp (T == 1) -- the warp owns all passes of its task and keeps its running best in bit planes
 template <int NB, int K, bool DR, bool SEQ>
 __global__ void __launch_bounds__(stripe_threads(NB), 1)
-k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPtrs P, const StripeGeom SG,
-         const __grid_constant__ SlicedPlan SP)
+k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid_constant__ SlicedPlan SP)
 {
+    // the resolved table comes from global memory with coalesced loads into shared memory (as a 3.7 KB by-value parameter it made
+    // the launch heavier and its per-thread reads of the constant bank serialised)
+    __shared__ __align__(16) DeviceTable s_table;
+    static_assert(sizeof(DeviceTable) % 16 == 0, "DeviceTable is copied in 16-byte pieces");
+    for (int k = threadIdx.x; k < int(sizeof(DeviceTable) / 16); k += blockDim.x)
+        reinterpret_cast<uint4*>(&s_table)[k] = reinterpret_cast<const uint4*>(P.table)[k];
+    __syncthreads();
+    const DeviceTable& T = s_table;
     constexpr int NUP = NB - 5;
     constexpr bool kRankPass = K > 0 && !DR;                        // rank planes are read (not derived from the class counts)
     constexpr bool kRank2 = kRankPass && K == 2;                    // two planes as uint2 at the class pitch (no second offset vector)
@@ -326,8 +339,7 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     uint32_t* s_ror_all = s_ro_all + size_t(SG.teams) * ro_team;                            // rank offsets (kRankPass)
     StripeSlot* s_slot_all = reinterpret_cast<StripeSlot*>(s_ror_all + (kRor ? size_t(SG.teams) * ro_team : 0));
     const int slots_team = SG.T * SG.Q;                                                     // [warp of the team][query of the task]
-    __shared__ uint32_t s_col[4][32];
-    __shared__ __align__(16) uint8_t s_code[kSymbols * kRowPad];                            // the pair table, for the finish step
+    const uint8_t* s_code = &T.code[0][0];                                                  // the pair table (in shared memory with T)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int len2 = G.uniform_len2;
@@ -393,9 +405,6 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     if (team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
 
     // ---- the striped window, built once per block ------------------------------------------------------
-    for (int k = tid; k < 4 * 32; k += nthreads) s_col[k >> 5][k & 31] = T.col[k >> 5][k & 31];
-    for (int k = tid; k < kSymbols * kRowPad / 4; k += nthreads)
-        reinterpret_cast<uint32_t*>(s_code)[k] = reinterpret_cast<const uint32_t*>(&T.code[0][0])[k];
     {
         // Seq1 as symbol indices; everything past len1 (and any byte outside [A-Z-]) becomes 31, whose columns are all zero
         bool bad = false;
@@ -425,31 +434,46 @@ k_stripe(const __grid_constant__ DeviceTable T, const BatchGeom G, const BatchPt
     }
     __syncthreads();
     PSA_TRACE_MARK(1);
-    // One task per (stripe column p < S, plane kind): the 32 stripes of column p are one 32x32 bit transpose; the words
-    // p + S, p + 2S, ... of the same column hold the same stripes moved up by one (word p + kS, bit t = position
-    // p + (t + k) S), so each follows from its predecessor by a one-bit shift that takes in ONE new position per row --
-    // 2 ALU instructions per row instead of another transpose (the window has S + steps words, only S distinct columns).
+    // The window has S + steps words per row but only S distinct columns.  Step 1, one task per (column p < S, plane kind): the
+    // 32 stripes of column p are one 32x32 bit transpose -> word p of every row.  Step 2: the words p + S, p + 2S, ... of a
+    // column hold the same stripes moved up by one (word p + kS, bit t = position p + (t + k) S), so each follows from its
+    // predecessor by a one-bit shift that takes in ONE new position per row -- 2 ALU instructions per row instead of another
+    // transpose.  These chains are independent per row: four tasks per (column, kind), seven rows each, so that every warp of
+    // the block has a share (the transposes alone keep only S * kinds / 32 warps busy).
     {
         constexpr int nkinds = kRankPass ? 2 + K : 2;
         for (int task = tid; task < S * nkinds; task += nthreads) {
             const int kind = task / S, p = task - kind * S;
-            const uint32_t* col = s_col[kind];
+            const uint32_t* col = T.col[kind];
             uint32_t m[32];
 #pragma unroll
             for (int t = 0; t < 32; t++) m[t] = col[s_seq1[p + t * S]];
             transpose32(m);
             uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk) + (kRank2 ? kind - 2 : 0);
             const int wstep = (kind < 2 || kRank2) ? 2 : 1;                                 // words between neighbours of a row
-            for (int k = 0;; k++) {
-                const int word = p + k * S;
-                if (word >= Wn) break;
-                if (k > 0) {
-                    const uint32_t c = col[s_seq1[word + 31 * S]];                          // the position that enters at bit 31
 #pragma unroll
-                    for (int r = 0; r < kPlaneRows; r++) m[r] = __funnelshift_r(m[r], c >> r, 1);
+            for (int r = 0; r < kPlaneRows; r++) dst[(size_t(r) * Wn + p) * wstep] = m[r];
+        }
+        __syncthreads();
+        constexpr int kRowGroups = 4, kRowsPer = kPlaneRows / kRowGroups;                   // 28 rows = 4 x 7
+        for (int task = tid; task < S * nkinds * kRowGroups; task += nthreads) {
+            const int rg = task % kRowGroups, ck = task / kRowGroups;
+            const int kind = ck / S, p = ck - kind * S;
+            if (p + S >= Wn) continue;                                                      // a column with a single word
+            const uint32_t* col = T.col[kind];
+            uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk) + (kRank2 ? kind - 2 : 0);
+            const int wstep = (kind < 2 || kRank2) ? 2 : 1;
+            const int r0 = rg * kRowsPer;
+            uint32_t m[kRowsPer];
+#pragma unroll
+            for (int r = 0; r < kRowsPer; r++) m[r] = dst[(size_t(r0 + r) * Wn + p) * wstep];
+            for (int word = p + S; word < Wn; word += S) {
+                const uint32_t c = col[s_seq1[word + 31 * S]] >> r0;                        // the position that enters at bit 31
+#pragma unroll
+                for (int r = 0; r < kRowsPer; r++) {
+                    m[r] = __funnelshift_r(m[r], c >> r, 1);
+                    dst[(size_t(r0 + r) * Wn + word) * wstep] = m[r];
                 }
-#pragma unroll
-                for (int r = 0; r < kPlaneRows; r++) dst[(size_t(r) * Wn + word) * wstep] = m[r];
             }
         }
     }
@@ -865,7 +889,7 @@ void launch_stripe_nb(const DeviceTable& T, const BatchGeom& G, const BatchPtrs&
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripeSmemMax));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
-        kernel<<<SG.blocks, SG.threads, SG.smem, stream>>>(T, G, P, SG, SP);
+        kernel<<<SG.blocks, SG.threads, SG.smem, stream>>>(G, P, SG, SP);
     };
     static bool done[8][64];
     const bool seq = SG.T == 1;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Longer randomized parity run than tests/test_gpu_parity.py::test_random_batches (same generator, any seed, any count,
-random tuning knobs): python tools/fuzz_batches.py [trials] [seed]   (PSA_FUZZ_GPUS=n for a multi-GPU context).
+random tuning knobs): python tools/fuzz_batches.py [trials] [seed]   (PSA_FUZZ_GPUS=n for a multi-GPU context,
+PSA_FUZZ_SLOTS=n for n device slots on GPU 0).
 Needs a B200; checks against the C oracle."""
 import importlib
 import os
@@ -29,7 +30,9 @@ def main():
     wsets = [[1, 3, 4, 2], [1, 1, 1, 1], [2, 1.5, 1.1, 1.3], [5, 1, 2, 3], [0.1, 0.7, 0.3, 0.9], [10, 2, 3, 4], [1.5, 2.6, 0.1, 0.2],
              [0, 0, 0, 0], [7, 0, 2, 0.5], [3, 3, 3, 3], [1e6, 1, 1e-3, 5]]
     bad = 0
-    with psa.Context(ngpus=int(os.environ.get("PSA_FUZZ_GPUS", "1"))) as ctx:
+    slots = int(os.environ.get("PSA_FUZZ_SLOTS", "0"))
+    modes = {}
+    with (psa.Context(devices=[0] * slots) if slots else psa.Context(ngpus=int(os.environ.get("PSA_FUZZ_GPUS", "1")))) as ctx:
         for trial in range(trials):
             w = rng.choice(wsets)
             is_max = bool(rng.getrandbits(1))
@@ -47,17 +50,21 @@ def main():
             qs = ["".join(rng.choice(alpha) for _ in range(n)) for n in lens]
             knobs = {"rank_planes": rng.choice([-1, -1, 0, 1, 2, 4]), "sliced_keys": rng.choice([1, 1, 0]), "pack_queries": rng.choice([1, 1, 0, 2, 3, 8]),
                      "fused_finish": rng.choice([1, 1, 0]), "derive_rank": rng.choice([1, 1, 0]), "zero_copy_results": rng.choice([1, 1, 0]),
-                     "batch_mode": rng.choice([-1, -1, 0, 1]), "scan_warps": rng.choice([0, 0, 1, 2, 3, 4])}
+                     "batch_mode": rng.choice([-1, -1, 0, 1]), "scan_warps": rng.choice([0, 0, 1, 2, 3, 4]),
+                     "stripe_mode": rng.choice([-1, -1, 1, 1, 0]), "single_launch": rng.choice([1, 1, 0])}
             for k, v in knobs.items():
                 ctx.set_option(k, v)
             got = ctx.search_batch(w, is_max, s1, qs)
+            mode = "stripe" if ctx.stat("stripe_mode") else "single" if ctx.stat("single_launch") else "batch" if ctx.stat("batch_mode") else \
+                "packed" if ctx.stat("packed_queries") > 0 else "sliced" if ctx.stat("slices") > 1 else "scalar" if ctx.stat("engine") == 1 else "long"
+            modes[mode] = modes.get(mode, 0) + 1
             exp = port.search_batch(w, is_max, s1, qs)
             for k, (g, e) in enumerate(zip(got, exp)):
                 if not same(g, e) or tuple(g.counts) != tuple(e.counts):
                     bad += 1
                     print("MISMATCH trial", trial, w, is_max, len1, lens[k], nq, "".join(alpha) if isinstance(alpha, list) else alpha, knobs, k, g, e, flush=True)
                     break
-    print("fuzz: %d trials, seed %d, %d mismatching batches" % (trials, seed, bad))
+    print("fuzz: %d trials, seed %d, %d mismatching batches; kernels used: %s" % (trials, seed, bad, sorted(modes.items())))
     return 1 if bad else 0
 
 
