@@ -233,10 +233,11 @@ def plan_packing(len1: int, len2: int, nq: int, force: int = 0):
     return q.value, w.value
 
 
-def plan_stripes(len1: int, len2: int, nq: int, rank_pass: bool = False, sm_count: int = 148) -> dict:
-    """Launch shape of stripe mode (host only, no GPU needed); {"ok": 0, ...} when the mode does not apply."""
+def plan_stripes(len1: int, len2: int, nq: int, rank_planes: int = 0, sm_count: int = 148) -> dict:
+    """Launch shape of stripe mode (host only, no GPU needed) for a window that carries `rank_planes` rank bit planes (0, 1 or 2);
+    {"ok": 0, ...} when the mode does not apply."""
     shape = (C.c_int * 8)()
-    rc = _lib.psa_plan_stripes(len1, len2, nq, int(bool(rank_pass)), sm_count, shape)
+    rc = _lib.psa_plan_stripes(len1, len2, nq, int(rank_planes), sm_count, shape)
     if rc:
         raise PsaError(rc, "psa_plan_stripes")
     return dict(zip(("ok", "lanes", "queries_per_task", "passes", "team_warps", "teams", "blocks", "smem_bytes"), list(shape)))

@@ -83,6 +83,9 @@ struct StripeGeom {
 // threads of the one block per SM: 20 warps at <= 96 registers (28 warps at 72 registers measured no faster on short queries)
 __host__ __device__ constexpr int stripe_threads(int nb) { return nb <= 7 ? 640 : 640; }
 inline int stripe_threads_for_len2(int64_t len2) { return stripe_threads(len2 <= 127 ? 7 : 10); }
+// two rank planes (uint2 entries) sit at this FIXED distance behind the class window, so that one address register serves both
+// loads of a step (LDS [addr] and LDS [addr + kStripeRankBase]); the class window must fit below it: 28 x Wn x 8 <= 96 KB
+constexpr int kStripeRankBase = 96 * 1024;
 constexpr int kStripeMaxQ = 32;                     // queries per task
 constexpr int kStripeMaxPasses = 64;                // passes per task
 constexpr size_t kStripeSmemMax = 224 * 1024;        // of the 227 KB a block may have (a little static shared memory on top)

@@ -69,6 +69,35 @@ __device__ __forceinline__ void stripe_class_group(VCounter<NUP>& A, VCounter<NU
     }
 }
 
+// The same with two rank planes ("best rank here is the top / the second rank") riding along: their uint2 entries sit
+// kStripeRankBase bytes behind the class entries, so the step's one address serves both loads and the rank planes cost one
+// LDS.64 and one LOP3 per step -- no pass of their own (short queries: there is no early exit to lose).
+template <int NUP>
+__device__ __forceinline__ void stripe_class_rank_group(VCounter<NUP>& A, VCounter<NUP>& B, VCounter<NUP>& C, uint32_t (&racc)[2],
+                                                        const char* pw, const uint32_t* ro)
+{
+    uint32_t pa[5], pb[5], pn[5];
+#pragma unroll
+    for (int s4 = 0; s4 < 32; s4 += 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
+        const uint32_t offs[4] = { o4.x, o4.y, o4.z, o4.w };
+        uint2 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s4 + u;
+            const uint2 x = *reinterpret_cast<const uint2*>(pw + offs[u]);
+            r[u] = *reinterpret_cast<const uint2*>(pw + offs[u] + kStripeRankBase);
+            vc_feed(A, pa, x.x, s);
+            vc_feed(B, pb, x.y, s);
+            vc_feed(C, pn, x.x & x.y, s);
+        }
+        racc[0] |= r[0].x | r[1].x;
+        racc[0] |= r[2].x | r[3].x;
+        racc[1] |= r[0].y | r[1].y;
+        racc[1] |= r[2].y | r[3].y;
+    }
+}
+
 //   pr : s_rnk + l * 4;  ro : byte offsets (row * Wn * 4 + step * 4)
 __device__ __forceinline__ void stripe_rank_group(uint32_t& racc, const char* pr, const uint32_t* ro)
 {
@@ -84,22 +113,6 @@ __device__ __forceinline__ void stripe_rank_group(uint32_t& racc, const char* pr
 
 // bytes of the Seq1 symbol area: the window build gathers positions up to (Wn - 1) + 31 S (rounded up to whole 16-byte stores)
 __host__ __device__ inline int stripe_seq1_span(const StripeGeom& g) { return (g.Wn + 31 * g.S + 16 + 15) & ~15; }
-
-// Two rank planes ("best rank here is the top / the second rank") interleaved as uint2 at the class window's 8-byte pitch:
-//   pr : s_rnk + l * 8;  ro : the class pass's byte offsets (row * Wn * 8 + step * 8)
-__device__ __forceinline__ void stripe_rank_group2(uint32_t (&racc)[2], const char* pr, const uint32_t* ro)
-{
-#pragma unroll
-    for (int s4 = 0; s4 < 32; s4 += 4) {
-        const uint4 o4 = *reinterpret_cast<const uint4*>(ro + s4);
-        const uint2 a = *reinterpret_cast<const uint2*>(pr + o4.x), b = *reinterpret_cast<const uint2*>(pr + o4.y);
-        const uint2 c = *reinterpret_cast<const uint2*>(pr + o4.z), d = *reinterpret_cast<const uint2*>(pr + o4.w);
-        racc[0] |= a.x | b.x;
-        racc[0] |= c.x | d.x;
-        racc[1] |= a.y | b.y;
-        racc[1] |= c.y | d.y;
-    }
-}
 
 __device__ __forceinline__ void team_sync(int team, int team_threads)
 {
@@ -331,7 +344,7 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wn = SG.Wn, S = SG.S, steps = SG.steps;
     unsigned char* s_cls = smem;                                                            // uint2 [28][Wn]
-    unsigned char* s_rnk = s_cls + size_t(kPlaneRows) * Wn * 8;                             // uint32 [28][Wn]
+    unsigned char* s_rnk = s_cls + (K == 2 && !DR ? size_t(kStripeRankBase) : size_t(kPlaneRows) * Wn * 8);   // uint32 [28][Wn], or uint2 [28][Wn] at the fixed base
     unsigned char* s_seq1 = s_rnk + (kRankPass ? size_t(kPlaneRows) * Wn * (kRank2 ? 8 : 4) : 0);   // symbols of Seq1
     const int seq1_span = stripe_seq1_span(SG);                                             // every position the build gathers
     uint32_t* s_ro_all = reinterpret_cast<uint32_t*>(s_seq1 + seq1_span);
@@ -544,13 +557,7 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
 #pragma unroll
                 for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0u;
                 racc[0] = ~vmask;
-                if constexpr (kRank2) {
-                    const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(lc) * 8;
-                    for (int g = 0; g < groups; g++) {
-                        stripe_rank_group2(racc, pr, ro + g * 32);
-                        if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
-                    }
-                } else if constexpr (kRankPass) {
+                if constexpr (kRankPass && !kRank2) {
                     const uint32_t* ror = s_ror + jc * SG.ro_stride;
                     const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(lc) * 4;
                     for (int g = 0; g < groups; g++) {
@@ -560,7 +567,11 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
                 }
                 A.clear(); B.clear(); C.clear();
                 const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(lc) * 8;
-                for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+                if constexpr (kRank2) {
+                    for (int g = 0; g < groups; g++) stripe_class_rank_group<NUP>(A, B, C, racc, pw, ro + g * 32);
+                } else {
+                    for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+                }
                 if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
             };
 
@@ -654,13 +665,7 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
 #pragma unroll
             for (int k = 0; k < (K > 0 ? K : 1); k++) racc[k] = 0u;
             racc[0] = ~vmask;                                       // offsets outside the range count as saturated
-            if constexpr (kRank2) {
-                const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 8;
-                for (int g = 0; g < groups; g++) {
-                    stripe_rank_group2(racc, pr, ro + g * 32);
-                    if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
-                }
-            } else if constexpr (kRankPass) {
+            if constexpr (kRankPass && !kRank2) {
                 const uint32_t* ror = s_ror + j * SG.ro_stride;
                 const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 4;
                 for (int g = 0; g < groups; g++) {
@@ -671,7 +676,11 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
             VCounter<NUP> A, B, C;
             A.clear(); B.clear(); C.clear();
             const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(l) * 8;
-            for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+            if constexpr (kRank2) {
+                for (int g = 0; g < groups; g++) stripe_class_rank_group<NUP>(A, B, C, racc, pw, ro + g * 32);
+            } else {
+                for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+            }
             if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
             PSA_TRACE_MARK(4);
 
@@ -774,7 +783,8 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
 
 size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, int rank_planes_read)
 {
-    size_t b = size_t(kPlaneRows) * g.Wn * (8 + (rank_planes_read == 2 ? 8 : rank_planes_read == 1 ? 4 : 0));
+    if (rank_planes_read == 2 && size_t(kPlaneRows) * g.Wn * 8 > size_t(kStripeRankBase)) return size_t(1) << 30;    // class window beyond the fixed rank base
+    size_t b = rank_planes_read == 2 ? size_t(kStripeRankBase) + size_t(kPlaneRows) * g.Wn * 8 : size_t(kPlaneRows) * g.Wn * (8 + (rank_planes_read == 1 ? 4 : 0));
     b += size_t(std::max<int64_t>(stripe_seq1_span(g), (len1 + 15) & ~int64_t(15)));
     b += size_t(g.teams) * g.Q * g.ro_stride * 4 * (rank_planes_read == 1 ? 2 : 1);
     b += size_t(g.teams) * g.T * g.Q * sizeof(StripeSlot);
