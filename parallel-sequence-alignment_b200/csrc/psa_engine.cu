@@ -54,6 +54,8 @@ struct DeviceState {
     SliceGeom SG{};
     StripeGeom stripe{};       // ok != 0: this shard runs in stripe mode (one launch: window + scan + finish)
     SingleGeom single{};       // ok != 0: this shard (one query, exact order) runs as one cooperative launch (k_single)
+    int64_t plan_key[5] = { -1, -1, -1, -1, -1 };   // (len1, len2, nq, rank planes asked, forced) of the cached stripe plan:
+    StripeGeom plan_cached{};                        //   the planner's search over (Q, T) is not repeated for a repeated batch shape
     PinBuf h_qoff, h_tile_start, h_out;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
@@ -352,8 +354,14 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
         const bool rank_pass = ctx->rank_planes == 1 && !stripe_derives_rank(ctx->table, ctx->rank_planes, ctx->opt_derive_rank != 0);
         const int avail = ctx->table.nranks - (ctx->table.has_none ? 0 : 1);
         const bool force = ctx->opt_stripe_mode == 1;
-        if (rank_pass && avail >= 2) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, 2, d.sm_count, force);
-        if (!d.stripe.ok) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass ? 1 : 0, d.sm_count, force);
+        const int64_t key[5] = { len1, ctx->uniform_len2, nq, rank_pass ? (avail >= 2 ? 2 : 1) : 0, force ? 1 : 0 };
+        if (std::memcmp(key, d.plan_key, sizeof(key)) == 0) d.stripe = d.plan_cached;
+        else {
+            if (rank_pass && avail >= 2) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, 2, d.sm_count, force);
+            if (!d.stripe.ok) d.stripe = stripe_plan(len1, ctx->uniform_len2, nq, rank_pass ? 1 : 0, d.sm_count, force);
+            std::memcpy(d.plan_key, key, sizeof(key));
+            d.plan_cached = d.stripe;
+        }
         // auto: short queries only in the one-warp-per-task shape (running best in bit planes: config 5 2.02 -> 1.39 ms); with
         // several warps per task their per-pass epilogue makes stripe mode no faster than batch mode's shared windows
         if (d.stripe.ok && !force && ctx->uniform_len2 < 128 && d.stripe.T != 1) d.stripe = StripeGeom{};
