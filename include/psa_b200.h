@@ -107,13 +107,18 @@ const char* psa_last_error(const psa_context* ctx);
      "derive_rank"   1 take the top-rank bit from the class planes when the table allows it | 0 always use a rank plane
      "pack_queries"  1 auto: equal-length queries that fit one window share blocks lane by lane when whole warps per
                      query would idle | 0 never | 2..8 force that many queries per block
-     "zero_copy_results" 1 result sets up to 128 KB are stored by the kernels straight into page-locked host memory (the
-                     caller's array if it is page-locked, else the context's staging buffer) | 0 always copy back
+     "zero_copy_results" 1 result sets up to 128 KB -- of any size in stripe mode, which stores a record as one 56-byte write --
+                     are stored by the kernels straight into page-locked host memory (the caller's array if it is page-locked,
+                     else the context's staging buffer) | 0 always copy back
+     "stream_queries" 1 a one-shot stripe-mode call (psa_search_batch) copies its queries on a second stream in up to 8 pieces
+                     while the kernel is already building its window; the kernel waits per task for the piece that holds the
+                     task's queries | 0 one copy in front of the kernel
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
    order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact",
-   "single_launch", "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", and the host-side split of the
+   "single_launch", "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", "streamed_chunks" (pieces the
+   last one-shot call streamed its queries in; 0 = one plain copy), and the host-side split of the
    last psa_search_batch in ns: "host_plan_ns", "host_prepare_ns", "host_enqueue_ns", "host_wait_ns", "host_total_ns".
    Unknown -> -1. */
 long long psa_get_stat(const psa_context* ctx, const char* name);

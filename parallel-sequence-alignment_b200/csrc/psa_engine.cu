@@ -14,6 +14,7 @@
 #include "psa_kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <cuda.h>            // types and the prototype of cuStreamWriteValue32 only: the entry point is looked up at run time
 
 #include <algorithm>
 #include <chrono>
@@ -49,6 +50,10 @@ struct DeviceState {
     int dev = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // streamed batches: the queries' host-to-device copies (the kernel is already running)
+    DevBuf ready;                            //   flags the copy stream writes behind each piece (BatchPtrs::ready)
+    int32_t* h_tags = nullptr;               //   page-locked source of those flag values when stream memory operations are not available
+    int32_t ready_tag = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole run / dominant kernel
     DevBuf seq1, seq2s, qoff, tile_start, tiles, out, lane_keys, cls_planes, rank_planes, partial, code_table, mutants, sync, table;
     SliceGeom SG{};
@@ -63,12 +68,14 @@ struct DeviceState {
     BatchPtrs P{};
     bool active = false;
     long long st_launches = 0, st_tiles = 0, st_main_ns = 0;   // counters of the last run on this GPU
+    long long st_chunks = 0;                                   // pieces the last one-shot call streamed its queries in (0: one plain copy)
     long long st_prepare_ns = 0, st_enqueue_ns = 0, st_wait_ns = 0;   // host time of the last one-shot search on this GPU's thread
     int32_t* h_err = nullptr;  // mapped page-locked word the kernels write the run's tag into on a bad symbol (no copy, no memset)
     int32_t run_tag = 0;
     long long table_epoch = -1;   // ctx->table_epoch whose pair table is in code_table
     bool zc_out = false;       // this run's records are written over the bus by the kernels themselves (no device-to-host copy)
     bool zc_direct = false;    //   ... into the caller's page-locked array (else into h_out)
+    bool streamed = false;     // this run's queries arrive on copy_stream while the kernel runs
     float run_ms = 0.f;
 };
 
@@ -98,7 +105,8 @@ struct psa_context {
     int opt_fused_finish = 1;  // 0: always run k_finish as its own kernel
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_pack_queries = 1;  // 0 never pack | 1 auto | 2..8 force that many queries per block (tests)
-    int opt_zero_copy = 1;     // 1: small result sets are written by the kernels straight into page-locked host memory
+    int opt_zero_copy = 1;     // 1: result sets are written by the kernels straight into page-locked host memory (small ones; any size in stripe mode)
+    int opt_stream_queries = 1; // 1: one-shot stripe-mode batches copy their queries on a second stream while the kernel builds its window
     long long table_epoch = 0; // bumped whenever `table` is rebuilt
     bool one_shot = false;     // the batch being prepared belongs to a prepare + run + fetch call (psa_search_batch / _range)
     int opt_kernel_events = 0; // 1: psa_batch_run also brackets the dominant kernel with events (stat main_kernel_ns)
@@ -179,11 +187,13 @@ void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
     for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
-                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync, &d.table })
+                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync, &d.table, &d.ready })
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
         if (b->p) cudaFreeHost(b->p);
     if (d.h_err) cudaFreeHost(d.h_err);
+    if (d.h_tags) cudaFreeHost(d.h_tags);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.evk0) cudaEventDestroy(d.evk0);
@@ -243,6 +253,75 @@ void worker_loop(Worker* w)
         w->pending = false;
         w->cv.notify_all();
     }
+}
+
+// ---- streamed batches -------------------------------------------------------------------------------------------
+// A one-shot stripe-mode call does not wait for its queries before it launches: Seq1 (a few KB) goes ahead on the main
+// stream, the queries follow on `copy_stream` in up to kStreamMaxChunks pieces, each with a flag written behind it by a
+// stream memory operation (cuStreamWriteValue32; a 4-byte copy from page-locked memory where that is not available), and
+// k_stripe -- launched right after the copies are enqueued -- builds its window while they are in flight and waits per task
+// for the piece that holds the task's queries (stream_wait, psa_kernels.cuh).  Everything the kernel waits for is enqueued
+// BEFORE the kernel is, so a failing copy can never leave a launched kernel waiting.
+constexpr int kStreamMaxChunks = 8;
+constexpr int64_t kStreamChunkBytes = 512 * 1024;
+constexpr int64_t kStreamMinBytes = 64 * 1024;
+
+using WriteValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WriteValue32Fn stream_write_value32()
+{
+    static const WriteValue32Fn fn = []() -> WriteValue32Fn {
+        if (std::getenv("PSA_NO_STREAM_MEMOPS")) return nullptr;            // tests: force the copy-based flags
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st{};
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<WriteValue32Fn>(p);
+    }();
+    return fn;
+}
+
+// copies of the queries in pieces on the copy stream + their flags; fills the ready fields of d.P
+int enqueue_streamed_queries(psa_context* ctx, DeviceState& d, const char* src, int64_t bytes)
+{
+    int rc;
+    if (!d.copy_stream) PSA_CUDA(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    if (!d.ready.p) {
+        if ((rc = ensure_dev(ctx, d.ready, sizeof(int32_t) * kStreamMaxChunks))) return rc;
+        PSA_CUDA(ctx, cudaMemset(d.ready.p, 0, sizeof(int32_t) * kStreamMaxChunks));
+        PSA_CUDA(ctx, cudaHostAlloc((void**)&d.h_tags, sizeof(int32_t) * kStreamMaxChunks, cudaHostAllocDefault));
+    }
+    if (d.ready_tag >= 0x7FFFFFF0) {                                        // no run is in flight here
+        PSA_CUDA(ctx, cudaMemset(d.ready.p, 0, sizeof(int32_t) * kStreamMaxChunks));
+        d.ready_tag = 0;
+    }
+    const int32_t tag = ++d.ready_tag;
+    int64_t chunks = std::min<int64_t>(std::max<int64_t>(bytes / kStreamChunkBytes, 1), kStreamMaxChunks);
+    const int64_t cb = ((bytes + chunks - 1) / chunks + 127) & ~int64_t(127);
+    chunks = (bytes + cb - 1) / cb;
+    static bool memops_ok = true;                                            // cleared for good the first time the driver refuses one
+    const WriteValue32Fn wv = memops_ok ? stream_write_value32() : nullptr;
+    for (int64_t c = 0; c < chunks; c++) {
+        const int64_t b0 = c * cb, n = std::min(cb, bytes - b0);
+        PSA_CUDA(ctx, cudaMemcpyAsync((char*)d.seq2s.p + b0, src + b0, (size_t)n, cudaMemcpyHostToDevice, d.copy_stream));
+        bool flagged = false;
+        if (wv && memops_ok) {
+            flagged = wv((CUstream)d.copy_stream, (CUdeviceptr)((int32_t*)d.ready.p + c), (cuuint32_t)tag, 0u) == CUDA_SUCCESS;
+            if (!flagged) memops_ok = false;
+        }
+        if (!flagged) {
+            d.h_tags[c] = tag;
+            PSA_CUDA(ctx, cudaMemcpyAsync((int32_t*)d.ready.p + c, d.h_tags + c, sizeof(int32_t), cudaMemcpyHostToDevice, d.copy_stream));
+        }
+    }
+    d.P.ready = (const int32_t*)d.ready.p;
+    d.P.ready_tag = tag;
+    d.P.ready_chunks = (int32_t)chunks;
+    d.P.ready_chunk_bytes = cb;
+    d.streamed = true;
+    d.st_chunks = chunks;
+    return PSA_OK;
 }
 
 // Enqueue H2D copies and geometry for one GPU's slice. first/last >= 0 selects range mode (nq == 1).
@@ -396,7 +475,13 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     }
 
     PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
-    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2s + byte0, (size_t)seq2_bytes, cudaMemcpyHostToDevice, d.stream));
+    d.streamed = false;
+    d.st_chunks = 0;
+    d.P.ready = nullptr; d.P.ready_tag = 0; d.P.ready_chunks = 0; d.P.ready_chunk_bytes = 128;
+    if (ctx->one_shot && d.stripe.ok && ctx->opt_stream_queries != 0 && seq2_bytes >= kStreamMinBytes) {
+        if ((rc = enqueue_streamed_queries(ctx, d, seq2s + byte0, seq2_bytes))) return rc;
+    } else
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.seq2s.p, seq2s + byte0, (size_t)seq2_bytes, cudaMemcpyHostToDevice, d.stream));
     if (!uniform_len) {
         PSA_CUDA(ctx, cudaMemcpyAsync(d.qoff.p, d.h_qoff.p, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
         PSA_CUDA(ctx, cudaMemcpyAsync(d.tile_start.p, d.h_tile_start.p, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, d.stream));
@@ -419,7 +504,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     // takes the device-to-host copy (an extra stream operation, ~4 us) off the end of the chain.  Large ones (config 5:
     // 3.7 MB) stay on the copy engine -- one DMA beats half a million 8-byte posted writes.
     // Only the one-shot calls do this: the split-phase form keeps its results resident until psa_batch_fetch.
-    d.zc_out = ctx->one_shot && ctx->opt_zero_copy != 0 && sizeof(QueryRec) * (size_t)nq <= kZeroCopyMaxBytes;
+    // Stripe mode stores a record as one 56-byte write (warp_store_record) spread over the whole run, so there any size goes.
+    d.zc_out = ctx->one_shot && ctx->opt_zero_copy != 0 && (sizeof(QueryRec) * (size_t)nq <= kZeroCopyMaxBytes || d.stripe.ok);
     d.zc_direct = false;
     d.P.out = d.zc_out ? (QueryRec*)d.h_out.p : (QueryRec*)d.out.p;
     d.P.lane_keys = (int64_t*)d.lane_keys.p;
@@ -440,10 +526,11 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
 // stream has drained.  Nothing to clear between runs, nothing to copy back.
 static int32_t next_run_tag(DeviceState& d)
 {
-    if (d.run_tag >= 0x7FFFFFF0) { d.run_tag = 0; *(volatile int32_t*)d.h_err = 0; }      // no run is in flight here
+    if (d.run_tag >= 0x7FFFFFF0) { d.run_tag = 0; ((volatile int32_t*)d.h_err)[0] = 0; ((volatile int32_t*)d.h_err)[1] = 0; }   // no run is in flight here
     return ++d.run_tag;
 }
 static bool bad_symbol_seen(const DeviceState& d) { return *(volatile const int32_t*)d.h_err == d.run_tag; }
+static bool stream_wait_timed_out(const DeviceState& d) { return ((volatile const int32_t*)d.h_err)[1] == d.run_tag; }
 
 int run_device(psa_context* ctx, DeviceState& d, bool timed)
 {
@@ -606,6 +693,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "derive_rank") && value >= 0 && value <= 1) { ctx->opt_derive_rank = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "pack_queries") && value >= 0 && value <= kPackMaxQ) { ctx->opt_pack_queries = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "zero_copy_results") && value >= 0 && value <= 1) { ctx->opt_zero_copy = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "stream_queries") && value >= 0 && value <= 1) { ctx->opt_stream_queries = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
@@ -654,6 +742,7 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "scan_warps")) return ctx->scan_tile / 1024;
     auto first_active = [ctx]() -> const DeviceState* { for (const DeviceState& d : ctx->devs) if (d.active) return &d; return nullptr; };
     if (!std::strcmp(name, "stripe_mode")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? 1 : 0; }
+    if (!std::strcmp(name, "streamed_chunks")) { long long n = 0; for (const DeviceState& d : ctx->devs) if (d.active) n = std::max<long long>(n, d.st_chunks); return n; }
     if (!std::strcmp(name, "single_launch")) { const DeviceState* d = first_active(); return d && d->single.ok ? 1 : 0; }
     if (!std::strcmp(name, "stripe_queries_per_task")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.Q : 0; }
     if (!std::strcmp(name, "stripe_team_warps")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.T : 0; }
@@ -928,6 +1017,8 @@ static int fetch_shard(psa_context* ctx, DeviceState& d, psa_result* out, bool d
 static int finish_fetch(psa_context* ctx, psa_result* out)
 {
     for (DeviceState& d : ctx->devs)
+        if (d.active && stream_wait_timed_out(d)) return fail(ctx, PSA_ERR_CUDA, "streamed queries did not reach cuda:%d in time", d.dev);
+    for (DeviceState& d : ctx->devs)
         if (d.active && bad_symbol_seen(d)) return fail(ctx, PSA_ERR_ALPHABET, "%s", psa_strerror(PSA_ERR_ALPHABET));
     if (ctx->nq == 1) {
         // per-GPU candidates of the single query in ascending offset order
@@ -1040,6 +1131,13 @@ static int search_prepared(psa_context* ctx, psa_result* out)
         if (d.zc_direct) {                                          // the caller's array is theirs again: a later
             d.P.out = (QueryRec*)d.h_out.p;                         // psa_batch_run on this batch writes the staging buffer
             d.zc_direct = false;
+        }
+        if (d.streamed) {
+            // a finished kernel has seen every flag, so the copies are done; on an error path make sure of it before the
+            // caller's buffers are theirs again.  The batch is resident from here on (psa_batch_run does not wait for flags).
+            if (r) { cudaStreamSynchronize(d.copy_stream); cudaGetLastError(); }
+            d.P.ready = nullptr;
+            d.streamed = false;
         }
         return r;
     });

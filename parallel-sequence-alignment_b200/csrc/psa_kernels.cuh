@@ -28,12 +28,77 @@ struct BatchPtrs {
     const DeviceTable* table;   // the whole resolved table in global memory (uploaded when it changes): kernels that copy it to shared
                                 //   memory take this pointer instead of a 3.7 KB by-value parameter
     int32_t*       sync;        // k_single: [0] grid barrier, [1] "last block" ticket; zero between launches (the last block resets them)
+    // Streamed batches (one-shot stripe mode): the queries arrive on a second stream in `ready_chunks` pieces of
+    // `ready_chunk_bytes` while the kernel already runs; ready[c] == ready_tag once every byte of piece c (and of the pieces
+    // before it) has landed.  ready == nullptr: the batch is resident.
+    const int32_t* ready;
+    int32_t        ready_tag;
+    int32_t        ready_chunks;
+    int64_t        ready_chunk_bytes;   // multiple of 128
 };
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void report_bad_symbol(const BatchPtrs& P)
 {
     *reinterpret_cast<volatile int32_t*>(P.err_flag) = P.run_tag;
+}
+
+// Streamed batches: wait (whole warp) until the query bytes [.., byte_end) have landed.  Lane 0 polls the piece's flag with an
+// acquire load at system scope (the writer is the copy stream: a DMA followed by a stream memory operation); the warp
+// barrier passes the ordering on to the other lanes.  The piece waited for is the one that holds the END of the last 128-byte
+// line touched, so no line can enter L1 before all of its bytes are final.  Bounded: should the flag not come within
+// kStreamWaitNs the warp reports it (err_flag[1]) and returns false -- the caller leaves the kernel, the host fails the call.
+constexpr unsigned long long kStreamWaitNs = 4000000000ull;
+__device__ __forceinline__ bool stream_wait(const BatchPtrs& P, int64_t byte_end)
+{
+    if (P.ready == nullptr) return true;
+    const int64_t line_last = ((byte_end + 127) & ~int64_t(127)) - 1;
+    int64_t c = line_last / P.ready_chunk_bytes;
+    if (c >= P.ready_chunks) c = P.ready_chunks - 1;
+    int ok = 1;
+    if ((threadIdx.x & 31) == 0) {
+        const int32_t* flag = P.ready + c;
+        unsigned long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            int32_t v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == P.ready_tag) break;
+            __nanosleep(64);
+            if ((spins & 1023u) == 1023u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kStreamWaitNs) { ok = 0; break; }
+            }
+        }
+        if (!ok) reinterpret_cast<volatile int32_t*>(P.err_flag)[1] = P.run_tag;
+    }
+    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+    return ok != 0;
+}
+
+// A 56-byte result record held by lane 0 leaves the warp as ONE store instruction (lanes 0..6, eight bytes each): one
+// contiguous write instead of seven -- what matters when `dst` is page-locked host memory and every store is a bus
+// transaction of its own.  All 32 lanes call this.
+__device__ __forceinline__ void warp_store_record(QueryRec* dst, const QueryRec& rec)
+{
+    static_assert(sizeof(QueryRec) == 56, "seven 8-byte words");
+    const int lane = threadIdx.x & 31;
+    unsigned long long w[7];
+    w[0] = (unsigned long long)(uint32_t)rec.offset | ((unsigned long long)(uint32_t)rec.char_offset << 32);
+    w[1] = (unsigned long long)(uint32_t)rec.ch | ((unsigned long long)(uint32_t)rec.rank << 32);
+    w[2] = (unsigned long long)__double_as_longlong(rec.score);
+    w[3] = (unsigned long long)rec.counts[0];
+    w[4] = (unsigned long long)rec.counts[1];
+    w[5] = (unsigned long long)rec.counts[2];
+    w[6] = (unsigned long long)rec.counts[3];
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const unsigned long long x = __shfl_sync(0xFFFFFFFFu, w[k], 0);
+        if (lane == k) mine = x;
+    }
+    if (lane < 7) reinterpret_cast<unsigned long long*>(dst)[lane] = mine;
 }
 #endif
 

@@ -151,7 +151,7 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
     out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
     out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
     if (r.key == kKeyNone) {
-        if (lane == 0) P.out[q] = out;
+        warp_store_record(P.out + q, out);
         return;
     }
     if (w.top) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
             }
         }
         PSA_CHECK(found >= 0);
-        if (lane == 0 && found >= 0) {
+        if (found >= 0) {                                               // warp-uniform; lane 0's record is the one stored
             uint32_t c1 = a[found], c2 = found_c2;
             if (c1 > 26u) { c1 = 0; c2 = 0; }
             const int64_t n1 = int64_t(w.na) - w.nc, n2 = int64_t(w.nb) - w.nc, n3 = w.nc;
@@ -196,9 +196,9 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
 #pragma unroll
             for (int c = 0; c < 4; c++) sc = __dadd_rn(sc, __dmul_rn(double(out.counts[c]), T.wcls[c]));     // exact (psa_table.cpp)
             out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[want]), 0.0);
-            P.out[q] = out;
+            warp_store_record(P.out + q, out);
+            return;
         }
-        if (found >= 0) return;
     }
     const uint8_t* a = s_seq1 + r.off;
     const uint8_t* b = P.seq2s + qbeg;
@@ -228,9 +228,9 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
 #pragma unroll
         for (int c = 0; c < 4; c++) cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], d);
     }
-    if (lane == 0) {
+    {                                                                   // every lane holds the reduced values; lane 0's record is stored
         const int rank = int(pos >> 32);
-        const int i = int(~uint32_t(pos));
+        const int i = pos ? int(~uint32_t(pos)) : 0;                    // pos == 0: rank 0, the record is overwritten below
         uint32_t c1 = a[i], c2 = symbol_of(b[i]);
         if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
         out.offset = r.off;
@@ -245,7 +245,7 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
         }
         out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
         if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
-        P.out[q] = out;
+        warp_store_record(P.out + q, out);
     }
 }
 
@@ -291,21 +291,20 @@ __device__ __forceinline__ void stripe_walk(const BatchPtrs& P, const uint8_t* s
 // the record of a query at which no offset has a possible mutation (what the reference returns then: cuda_funcs.cu:143-145)
 __device__ __forceinline__ void stripe_emit_none(const DeviceTable& T, const BatchPtrs& P, int q)
 {
-    if ((threadIdx.x & 31) != 0) return;
     QueryRec out;
     out.score = T.is_max ? -INFINITY : INFINITY;
     out.offset = -1; out.char_offset = -1; out.ch = 0; out.rank = 0;
     out.counts[0] = out.counts[1] = out.counts[2] = out.counts[3] = 0;
-    P.out[q] = out;
+    warp_store_record(P.out + q, out);
 }
 
-// the result record from a finished walk (lane 0 writes)
+// the result record from a finished walk (the walk's results are the same on every lane; the warp stores lane 0's record)
 __device__ __forceinline__ void stripe_emit(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_seq1, int q, int64_t qbeg, int off,
                                             const int (&cnt)[4], int rank, int first_i)
 {
-    if ((threadIdx.x & 31) != 0) return;
     QueryRec out;
-    uint32_t c1 = s_seq1[off + first_i], c2 = symbol_of(P.seq2s[qbeg + first_i]);
+    const int fi = first_i < 0 ? 0 : first_i;                           // rank 0 (no mutation anywhere): the record is overwritten below
+    uint32_t c1 = s_seq1[off + fi], c2 = symbol_of(P.seq2s[qbeg + fi]);
     if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
     out.offset = off;
     out.char_offset = first_i;
@@ -319,7 +318,7 @@ __device__ __forceinline__ void stripe_emit(const DeviceTable& T, const BatchPtr
     }
     out.score = __dadd_rn(__dadd_rn(sc, T.wdiff[rank]), 0.0);
     if (rank <= 0) { out.offset = -1; out.char_offset = -1; out.ch = 0; out.score = T.is_max ? -INFINITY : INFINITY; }
-    P.out[q] = out;
+    warp_store_record(P.out + q, out);
 }
 
 // NB : counter planes (len2 < 2^NB), RANKPASS : a rank plane is read (K = 1 and the top rank is not derivable),
@@ -415,7 +414,9 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(seq1_first.x), "=r"(seq1_first.y), "=r"(seq1_first.z), "=r"(seq1_first.w)
                      : "l"(P.seq1 + tid * 16));                     // the buffer is padded: vector loads stay inside
-    if (team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
+    // (a streamed batch's queries may not have landed yet: its first task is fetched after the window is built)
+    const bool streamed = P.ready != nullptr;
+    if (!streamed && team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
 
     // ---- the striped window, built once per block ------------------------------------------------------
     {
@@ -494,6 +495,17 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
     PSA_TRACE_MARK(2);
 
     if (team >= SG.teams) return;                                   // spare warps only helped to build the window
+
+    // bytes of the queries up to the end of `task`: what has to have landed before the task's row offsets are built
+    auto task_bytes_end = [&](int task) {
+        const int qe = (task + 1) * SG.Q < G.nq ? (task + 1) * SG.Q : G.nq;
+        return int64_t(qe) * len2;
+    };
+    if (streamed && first_task < SG.ntasks) {
+        if (!stream_wait(P, task_bytes_end(first_task))) return;    // (every warp of the team gives up at the same point)
+        build_row_offsets(first_task);
+        team_sync(team, team_threads);
+    }
 
     for (int task = first_task; task < SG.ntasks; task += task_stride) {
         const int q0 = task * SG.Q;
@@ -645,7 +657,10 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
                 stripe_emit(T, P, s_seq1, q, qbeg, off, cnt, rank, first_i);
             }
             __syncwarp();                                           // this task's row offsets and slots are consumed
-            if (task + task_stride < SG.ntasks) build_row_offsets(task + task_stride);
+            if (task + task_stride < SG.ntasks) {
+                if (!stream_wait(P, task_bytes_end(task + task_stride))) return;
+                build_row_offsets(task + task_stride);
+            }
             __syncwarp();
             continue;
         }
@@ -765,7 +780,10 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
         PSA_TRACE_MARK(5);
         team_sync(team, team_threads);                              // slots complete; nobody reads this task's row offsets any more
         PSA_TRACE_MARK(6);
-        if (task + task_stride < SG.ntasks) build_row_offsets(task + task_stride);       // in flight while the queries are finished
+        if (task + task_stride < SG.ntasks) {                       // in flight while the queries are finished
+            if (!stream_wait(P, task_bytes_end(task + task_stride))) return;
+            build_row_offsets(task + task_stride);
+        }
         // finish: one warp per query of the task -- best over the team's warps, then the record
         for (int jj = tw; jj < nqt; jj += SG.T) {
             StripeSlot r = s_slot[jj];

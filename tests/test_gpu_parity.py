@@ -2,11 +2,14 @@
 
 Bit-exact bar: offset, char_offset, substitute letter and the score double must equal the
 oracle's (== the reference's 1-thread CPU path, see tests/test_oracle.py)."""
+import os
 import random
+import subprocess
+import sys
 
 import pytest
 
-from conftest import same_answer
+from conftest import PKG, ROOT, same_answer
 
 pytestmark = pytest.mark.gpu
 ALPHA = [chr(65 + i) for i in range(26)] + ["-"]
@@ -577,6 +580,71 @@ def test_zero_copy_results_match_copied_results(psa, ctx, port, synth):
             ctx.search_batch(wl.weights, wl.is_max, wl.seq1, [wl.queries[0], b"AB?D"])
         assert same_answer(ctx.search(wl.weights, wl.is_max, wl.seq1, wl.queries[5]), exp[5])      # and it recovers
     ctx.set_option("zero_copy_results", 1)
+
+
+def test_streamed_queries_and_large_zero_copy_results(psa, ctx, port, synth):
+    """One-shot stripe-mode calls copy their queries on a second stream in pieces while k_stripe is already running
+    (stream_wait on per-piece flags) and write every record straight into page-locked host memory, whatever the size of the
+    result set.  Same records with streaming on and off, pinned and pageable buffers, one piece and several, a second
+    call on the same context (fresh flag tag), and a later split-phase run of the same shape (resident: no flags)."""
+    import ctypes as C
+    for name, nq, pieces in (("c3", 300, 1), ("c5", 20000, 2), ("c5", 70000, 8)):
+        wl = synth.workload(name, nq=nq)
+        w = (C.c_double * 4)(*wl.weights)
+        exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:150])
+        ref_records = None
+        for stream in (1, 0, 1):
+            ctx.set_option("stream_queries", stream)
+            for pinned in (True, False):
+                batch = psa.Batch(wl.seq1, wl.queries, pinned=pinned)
+                out = ctx.new_result_array(batch.nq, pinned=pinned)
+                ctx.search_batch_raw(w, wl.is_max, batch, out)
+                assert ctx.stat("stripe_mode") == 1 and ctx.stat("kernel_launches") == 1
+                assert ctx.stat("streamed_chunks") == (pieces if stream else 0), (name, nq, stream, ctx.stat("streamed_chunks"))
+                recs = [ctx.result_from_array(out, k) for k in range(batch.nq)]
+                for k, e in enumerate(exp):
+                    assert same_answer(recs[k], e) and recs[k].counts == e.counts, (name, stream, pinned, k)
+                flat = [(r.offset, r.char_offset, r.ch, r.score, r.counts) for r in recs]
+                if ref_records is None:
+                    ref_records = flat
+                assert flat == ref_records, (name, stream, pinned)
+        ctx.set_option("stream_queries", 1)
+        # split phase after a streamed one-shot call of the same shape: the batch is resident, nothing waits for a flag
+        batch = psa.Batch(wl.seq1, wl.queries, pinned=True)
+        ctx.prepare(wl.weights, wl.is_max, batch)
+        ctx.run()
+        got = ctx.fetch()
+        assert [(r.offset, r.char_offset, r.ch, r.score, r.counts) for r in got] == ref_records
+    # a bad symbol in a streamed batch is still reported, and the context recovers
+    wl = synth.workload("c3", nq=300)
+    bad = list(wl.queries)
+    bad[250] = bad[250][:100] + b"?" + bad[250][101:]
+    with pytest.raises(psa.PsaError):
+        ctx.search_batch(wl.weights, wl.is_max, wl.seq1, bad)
+    assert ctx.stat("streamed_chunks") == 1
+    got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:32])
+    assert all(same_answer(g, e) for g, e in zip(got, exp))
+
+
+def test_streamed_queries_with_copied_flags(psa, synth):
+    """The same with the stream memory operation unavailable: the flags are 4-byte copies from page-locked memory
+    (PSA_NO_STREAM_MEMOPS is read once per process, hence the child process)."""
+    code = (
+        "import sys, importlib; sys.path.insert(0, %r)\n"
+        "psa = importlib.import_module(%r); synth = importlib.import_module(%r + '.synth')\n"
+        "import oracle; port = oracle.Port()\n"
+        "wl = synth.workload('c5', nq=20000)\n"
+        "with psa.Context(1) as ctx:\n"
+        "    for rep in range(2):\n"
+        "        got = ctx.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)\n"
+        "        assert ctx.stat('streamed_chunks') == 2, ctx.stat('streamed_chunks')\n"
+        "    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:100])\n"
+        "    assert all((g.offset, g.char_offset, g.ch, g.score, g.counts) == (e.offset, e.char_offset, e.ch, e.score, e.counts) for g, e in zip(got, exp))\n"
+        "print('ok')\n" % (ROOT, PKG, PKG))
+    env = dict(os.environ, PSA_NO_STREAM_MEMOPS="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
 
 
 def test_random_batches(ctx, port):
