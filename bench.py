@@ -169,7 +169,11 @@ def shared_config(name, wl):
     return {"workload": workload_name(name, wl),
             "per_gpu": "our arm: every rank owns one full batch of the workload (weak scaling, no data-path collective); "
                        "reference arm: a bounded sample of the same batch on the host cores",
-            "l2": "our arm: flushed between timed steps (512 MiB write); reference arm: CPU, not applicable"}
+            "l2": "our arm: flushed between timed steps (512 MiB write); reference arm: CPU, not applicable",
+            "timing": "our arm: `value` = per-step CUDA events on the library's stream; event + launch + event are enqueued behind a "
+                      "gate the host opens afterwards (psa_set_option gate_timed_runs), so the bracket holds device time and no host "
+                      "launch latency (tools/probes/launch_probe.cu, profiles/r02_launch_probe.txt); `e2e` = wall clock around "
+                      "psa_search_batch on host buffers; reference arm: wall clock"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -470,6 +474,7 @@ def run_ours(args, synth, rank, local_rank, world):
     peaks = load_peaks()
     wl = make_workload(synth, args.workload, rank)
     ctx = psa.Context(devices=[local_rank])
+    ctx.set_option("gate_timed_runs", 1)
     if args.engine:
         ctx.set_option("engine", args.engine)
     for kv in args.opt:                                                   # library tuning knobs (psa_set_option), for A/B runs
@@ -632,6 +637,7 @@ def run_ours(args, synth, rank, local_rank, world):
                 big = make_workload(synth, "c3", rank, nq=16 * batch.nq)
                 bb = psa.Batch(big.seq1, big.queries, pinned=True)
                 c3x.set_option("kernel_events", 1)
+                c3x.set_option("gate_timed_runs", 1)
                 c3x.prepare(big.weights, big.is_max, bb)
                 for _ in range(3):
                     c3x.run()
@@ -650,6 +656,7 @@ def run_ours(args, synth, rank, local_rank, world):
             # the other BASELINE.json configs, same method (resident value + host-buffer e2e), fewer steps
             others = {}
             with psa.Context(devices=[local_rank]) as c2:
+                c2.set_option("gate_timed_runs", 1)
                 for name in ("c1", "c2", "c4", "c5"):
                     if name != args.workload:
                         others[name] = quick_measure(psa, synth, c2, name, flush_l2, steps=max(3, args.steps // 4))

@@ -113,7 +113,10 @@ const char* psa_last_error(const psa_context* ctx);
      "stream_queries" 1 a one-shot stripe-mode call (psa_search_batch) copies its queries on a second stream in up to 8 pieces
                      while the kernel is already building its window; the kernel waits per task for the piece that holds the
                      task's queries | 0 one copy in front of the kernel
-     "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns") */
+     "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns")
+     "gate_timed_runs" 1 psa_batch_run enqueues its events and launches behind a gate (a stream wait on a page-locked word) that
+                     the host opens once everything is enqueued, so the reported device time holds no host launch latency;
+                     the first run of a prepared batch is never gated (lazy kernel loading) | 0 (default) no gate */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
    order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact",

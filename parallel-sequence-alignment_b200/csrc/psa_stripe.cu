@@ -330,11 +330,17 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
 {
     // the resolved table comes from global memory with coalesced loads into shared memory (as a 3.7 KB by-value parameter it made
     // the launch heavier and its per-thread reads of the constant bank serialised)
+    // The block starts with three cold reads -- the table, Seq1, the first task's queries -- that do not depend on each other:
+    // all three are issued before the first is waited for (one trip to L2 / HBM instead of three).
     __shared__ __align__(16) DeviceTable s_table;
     static_assert(sizeof(DeviceTable) % 16 == 0, "DeviceTable is copied in 16-byte pieces");
-    for (int k = threadIdx.x; k < int(sizeof(DeviceTable) / 16); k += blockDim.x)
-        reinterpret_cast<uint4*>(&s_table)[k] = reinterpret_cast<const uint4*>(P.table)[k];
-    __syncthreads();
+    constexpr int kTableVecs = int(sizeof(DeviceTable) / 16);
+    static_assert(kTableVecs <= stripe_threads(NB), "one 16-byte piece of the table per thread");
+    uint4 table_piece = make_uint4(0u, 0u, 0u, 0u);
+    if (int(threadIdx.x) < kTableVecs)
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(table_piece.x), "=r"(table_piece.y), "=r"(table_piece.z), "=r"(table_piece.w)
+                     : "l"(reinterpret_cast<const uint4*>(P.table) + threadIdx.x));
     const DeviceTable& T = s_table;
     constexpr int NUP = NB - 5;
     constexpr bool kRankPass = K > 0 && !DR;                        // rank planes are read (not derived from the class counts)
@@ -358,7 +364,6 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
     const int64_t noff = G.len1 - len2 + 1;
     PSA_CHECK(len2 > 0 && G.last < 0 && S * 32 >= noff && steps >= len2 && Wn >= S + steps && SG.T * SG.teams * 32 <= nthreads);
 
-    PSA_TRACE_MARK(0);
     if (blockIdx.x == 0 && tid == 0) { P.cand_count[0] = 0; P.cand_count[2] = 0; }          // statistics of the run (nothing is re-scored here)
 
     // ---- teams ---------------------------------------------------------------------------------------------
@@ -417,6 +422,9 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
     // (a streamed batch's queries may not have landed yet: its first task is fetched after the window is built)
     const bool streamed = P.ready != nullptr;
     if (!streamed && team < SG.teams && first_task < SG.ntasks) build_row_offsets(first_task);
+    if (tid < kTableVecs) reinterpret_cast<uint4*>(&s_table)[tid] = table_piece;
+    __syncthreads();                                                // the table is in shared memory from here on
+    PSA_TRACE_MARK(0);
 
     // ---- the striped window, built once per block ------------------------------------------------------
     {
@@ -481,12 +489,24 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
             uint32_t m[kRowsPer];
 #pragma unroll
             for (int r = 0; r < kRowsPer; r++) m[r] = dst[(size_t(r0 + r) * Wn + p) * wstep];
-            for (int word = p + S; word < Wn; word += S) {
-                const uint32_t c = col[s_seq1[word + 31 * S]] >> r0;                        // the position that enters at bit 31
+            // four words per round: the (dependent) symbol and column loads of all four are issued before the first shift
+            for (int word = p + S; word < Wn; word += 4 * S) {
+                uint32_t c[4];
 #pragma unroll
-                for (int r = 0; r < kRowsPer; r++) {
-                    m[r] = __funnelshift_r(m[r], c >> r, 1);
-                    dst[(size_t(r0 + r) * Wn + word) * wstep] = m[r];
+                for (int u = 0; u < 4; u++) {
+                    const int w = word + u * S;
+                    c[u] = w < Wn ? col[s_seq1[w + 31 * S]] >> r0 : 0u;                     // the position that enters at bit 31
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int w = word + u * S;
+                    if (w < Wn) {
+#pragma unroll
+                        for (int r = 0; r < kRowsPer; r++) {
+                            m[r] = __funnelshift_r(m[r], c[u] >> r, 1);
+                            dst[(size_t(r0 + r) * Wn + w) * wstep] = m[r];
+                        }
+                    }
                 }
             }
         }

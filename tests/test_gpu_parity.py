@@ -647,6 +647,35 @@ def test_streamed_queries_with_copied_flags(psa, synth):
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
 
 
+def test_gated_timed_runs(psa, port, synth):
+    """psa_batch_run behind the host-released gate (option gate_timed_runs): same answers, the first run of a prepared batch
+    is never gated (a kernel's first launch must not sit behind a closed gate), an option change in between makes the next
+    run a first run again; stripe mode, the single-query launch and the k_profile / k_scan / k_finish chain."""
+    with psa.Context(1) as c:
+        c.set_option("gate_timed_runs", 1)
+        for name, nq in (("c3", 64), ("c2", None), ("c5", 3000)):
+            wl = synth.workload(name, nq=nq)
+            b = psa.Batch(wl.seq1, wl.queries, pinned=True)
+            c.prepare(wl.weights, wl.is_max, b)
+            for k in range(4):
+                assert c.run() > 0
+                if k == 1:
+                    c.set_option("kernel_events", 1)
+            c.set_option("kernel_events", 0)
+            got = c.fetch()
+            exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:40])
+            assert all(same_answer(g, e) for g, e in zip(got, exp)), name
+        # re-scored order (the chain with programmatic dependent launches) and a ragged batch
+        wl = synth.workload("c3", nq=40)
+        for weights, queries in (([1.5, 2.6, 0.1, 0.2], wl.queries), (wl.weights, wl.queries[:-1] + [wl.queries[-1][:321]])):
+            b = psa.Batch(wl.seq1, queries, pinned=True)
+            c.prepare(weights, wl.is_max, b)
+            for _ in range(3):
+                assert c.run() > 0
+            exp = port.search_batch(weights, wl.is_max, wl.seq1, queries)
+            assert all(same_answer(g, e) for g, e in zip(c.fetch(), exp))
+
+
 def test_random_batches(ctx, port):
     """Random batches through the default dispatch (long / packed / batch mode, fused or separate finish, exact or
     re-scored order, zero-copy or copied results): equal-length and ragged, tiny and multi-tile, five alphabets."""
