@@ -153,11 +153,12 @@ def golden_c1():
     return b["weights"], b["goal"] == "maximum", b["seq1"].encode(), [b["seq2"].encode()]
 
 
-def make_workload(synth, name, rank, nq=None):
+def make_workload(synth, name, rank, nq=None, variant=0):
+    """variant: another batch of the same shape and distribution (the pipelined end-to-end leg takes a different one per step)."""
     if name == "c1":
         w, is_max, s1, qs = golden_c1()
         return synth.Workload("c1", w, is_max, s1, qs, FULL_NOTE["c1"])
-    return synth.workload(name, nq=nq, seed_shift=1000 * rank)
+    return synth.workload(name, nq=nq, seed_shift=1000 * rank + variant)
 
 
 def workload_name(name, wl):
@@ -399,6 +400,35 @@ def strong_scaling(psa, synth, torch, ngpus, steps, workloads=("c3", "c5", "c4")
                               "device_ms_max_over_gpus": dev / steps, "device_pair_evals_per_s": batch.pair_evals * steps / (dev * 1e-3),
                               "host_split_us": {k[5:-3]: v / steps * 1e-3 for k, v in split.items()},
                               "launches_per_call": c.stat("kernel_launches"), "oracle_check": chk}
+            # The same workload as a LIST of independent batches through psa_search_many (2 lanes per GPU, a batch is never
+            # split): what a stream of such batches gets out of the N GPUs of one process, end to end on host buffers.
+            if name != "c4":
+                per_gpu = {"c3": 48, "c5": 6}.get(name, 8)
+                distinct = {"c3": 16, "c5": 3}.get(name, 4)
+                wls = [wl] + [make_workload(synth, name, 0, variant=k) for k in range(1, distinct)]
+                built = [(wc, x.is_max, batch if k == 0 else psa.Batch(x.seq1, x.queries, pinned=True),
+                          psa.Context.new_result_array(batch.nq, pinned=True)) for k, x in enumerate(wls)]
+                many = {"how": "psa_search_many, 2 lanes per GPU, wall clock around the whole list (every batch pays its own copies)",
+                        "distinct_batches": distinct}
+                for n, c in ctxs.items():
+                    items = [built[k % distinct] for k in range(per_gpu * n)]
+                    plist = c.make_problem_list(items)
+                    c.search_many_raw(plist, min(len(items), 4 * n), 2)
+                    best = None
+                    for _ in range(3):
+                        flush_l2()
+                        t0 = time.perf_counter()
+                        c.search_many_raw(plist, len(items), 2)
+                        dt = time.perf_counter() - t0
+                        best = dt if best is None else min(best, dt)
+                    last = (len(items) - 1) % distinct
+                    chk = oracle_check(wls[last], [c.result_from_array(built[last][3], i) for i in range(min(32, batch.nq))], 32)
+                    many[f"n{n}"] = {"batches": len(items), "ms_per_batch": 1e3 * best / len(items),
+                                     "e2e_pair_evals_per_s": batch.pair_evals * len(items) / best, "oracle_check": chk}
+                if ngpus > 1:
+                    many["speedup"] = many[f"n{ngpus}"]["e2e_pair_evals_per_s"] / many["n1"]["e2e_pair_evals_per_s"]
+                    many["efficiency"] = many["speedup"] / ngpus
+                w["list_of_batches"] = many
             if ngpus > 1:
                 a, b = w["n1"], w[f"n{ngpus}"]
                 w["speedup_e2e"] = a["e2e_ms"] / b["e2e_ms"]
@@ -535,6 +565,29 @@ def run_ours(args, synth, rank, local_rank, world):
         e2e_s += time.perf_counter() - t0
         launches += ctx.stat("kernel_launches")
     barrier()
+    # ---- e2e, pipelined: the K steps as ONE list through psa_search_many ---------------------------------------------
+    # Step k is its own batch of the workload's shape (a different one per step, up to `distinct`), in its own pinned host
+    # buffers with its own pinned result array; psa_search_many runs the list over 2 lanes (stream + buffers + host thread
+    # each), so the copies, launch and wake-up of one step overlap the kernel of another.  Every step still pays its own
+    # H2D copies and gets its own records back; the wall clock is taken around the whole list.
+    distinct = min(args.steps, {"c3": 32, "c1": 32, "c2": 32}.get(args.workload, 6))
+    many_wl = [wl] + [make_workload(synth, args.workload, rank, variant=k) for k in range(1, distinct)]
+    many_built = [(wc, w_.is_max, batch if k == 0 else psa.Batch(w_.seq1, w_.queries, pinned=True),
+                   ctx.new_result_array(batch.nq, pinned=True)) for k, w_ in enumerate(many_wl)]
+    many_items = [many_built[k % distinct] for k in range(args.steps)]
+    many_list = ctx.make_problem_list(many_items)
+    lanes = 2
+    ctx.search_many_raw(many_list, min(args.steps, 2 * max(args.warmup, 2)), lanes)      # lanes created, kernels loaded
+    flush_l2()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.search_many_raw(many_list, args.steps, lanes)
+    many_s = time.perf_counter() - t0
+    barrier()
+    launches += args.steps * ctx.stat("kernel_launches")
+    many_s_max = max_over_ranks(many_s)
+    last = (args.steps - 1) % distinct
+    many_last = (many_wl[last], [ctx.result_from_array(many_built[last][3], i) for i in range(min(64, batch.nq))])
     if rank == 0:
         # the timed regions are a few ms in total, shorter than nvidia-smi's sampling period: keep running the same
         # step (untimed) until the sampler has seen the GPU under this load
@@ -569,7 +622,9 @@ def run_ours(args, synth, rank, local_rank, world):
     if rank == 0:
         value = total_pe * args.steps / (dev_ms_max * 1e-3)
         e2e_value = total_pe * args.steps / e2e_s_max
+        many_value = total_pe * args.steps / many_s_max
         check = oracle_check(wl, timed_results, 64) if args.workload != "c4" else {"queries_checked": 0, "note": "see strong.workloads.c4"}
+        many_check = oracle_check(many_last[0], many_last[1], 64) if args.workload != "c4" else {"queries_checked": 0, "note": "see strong.workloads.c4"}
         # roofline of the dominant kernel on this rank (its own events), per GPU
         k_s = main_ns * 1e-9 / args.steps
         achieved = pair_evals / k_s if k_s > 0 else 0.0
@@ -595,11 +650,20 @@ def run_ours(args, synth, rank, local_rank, world):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
             "config": shared_config(args.workload, wl),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes,
-                    "d2h_bytes_per_step": 56 * batch.nq, "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "d2h_path": "result records stored by the finishing threads straight into the caller's page-locked array" if 56 * batch.nq <= 128 * 1024
-                                else "one device-to-host copy into the caller's page-locked array",
-                    "oracle_check_of_timed_answers": check, "strong": strong},
+            "e2e": {"value": many_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes,
+                    "d2h_bytes_per_step": 56 * batch.nq, "ms_per_step": 1e3 * many_s_max / args.steps,
+                    "how": f"the K steps as ONE list through the C entry point psa_search_many ({lanes} lanes per GPU: stream, buffers and host "
+                           f"thread each): step k is its own batch of the workload's shape ({distinct} distinct batches, each in its own pinned host "
+                           "buffers) and pays its own host-to-device copies and gets its own records back; the copies, launch and wake-up of one "
+                           "step overlap the kernel of another; wall clock around the whole list, L2 flushed before it",
+                    "d2h_path": "result records stored by the finishing warps straight into the caller's page-locked arrays (stripe mode: one "
+                                "56-byte write per record)",
+                    "oracle_check_of_timed_answers": many_check,
+                    "one_call_at_a_time": {"value": e2e_value, "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                                           "how": "psa_search_batch on the same pinned buffers, one synchronous call per step, L2 flushed "
+                                                  "between calls, wall clock per call (the latency of a single batch)",
+                                           "oracle_check_of_timed_answers": check},
+                    "strong": strong},
             "gpu_launches": launches,
             "roofline": {"bound": "int-alu-issue", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak,
                          "traffic": (prof or {}).get("dram_bytes_per_launch"),

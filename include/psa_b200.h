@@ -179,6 +179,28 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max,
                      const char* seq2s, const int64_t* q_off, int32_t nq,
                      psa_result* out);
 
+/* Many independent problems in one call, pipelined: the stacked blocks of an input file, the per-Seq1 batches of a query
+   stream.  Every device slot of the context runs `lanes_per_device` lanes (1..4; 0 = the default, 2), each lane its own
+   stream, buffers and host thread; the lanes take problems off a shared counter, so the copies, launch and wake-up of one
+   problem overlap the kernel of another and the GPUs stay busy between problems (one psa_search_batch at a time leaves a
+   GPU idle for the ~30 us either side of a 40 us kernel).  A problem is never split: with N GPUs, N x lanes problems are
+   in flight.  problems[k].out receives problem k's records exactly as psa_search_batch would write them;
+   problems[k].status its status.  Returns PSA_OK when every problem succeeded, else the status of the first that failed.
+   The context's tuning knobs (psa_set_option) apply to every lane. */
+typedef struct psa_problem {
+    const double*  weights;    /* 4 weights */
+    int32_t        is_max;
+    int32_t        nq;
+    const char*    seq1;
+    int64_t        len1;
+    const char*    seq2s;      /* queries, concatenated */
+    const int64_t* q_off;      /* nq + 1 byte offsets into seq2s */
+    psa_result*    out;        /* nq records */
+    int32_t        status;     /* out */
+    int32_t        reserved;
+} psa_problem;
+int psa_search_many(psa_context* ctx, psa_problem* problems, int32_t nproblems, int lanes_per_device);
+
 /* One query restricted to absolute offsets [first,last) -- the gpu_run_program contract. */
 int psa_search_range(psa_context* ctx, const double weights[4], int is_max,
                      const char* seq1, int64_t len1, const char* seq2, int64_t len2,

@@ -64,6 +64,12 @@ class _CPairTable(C.Structure):
                 ("nranks", C.c_int32), ("exact", C.c_int32), ("frac_bits", C.c_int32), ("key_slack", C.c_int64)]
 
 
+class _CProblem(C.Structure):
+    """psa_problem (include/psa_b200.h): one entry of a psa_search_many list."""
+    _fields_ = [("weights", C.POINTER(C.c_double)), ("is_max", C.c_int32), ("nq", C.c_int32), ("seq1", C.c_void_p), ("len1", C.c_int64),
+                ("seq2s", C.c_void_p), ("q_off", C.c_void_p), ("out", C.c_void_p), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
 class _CShard(C.Structure):
     _fields_ = [("q_begin", C.c_int32), ("q_end", C.c_int32), ("first", C.c_int64), ("last", C.c_int64)]
 
@@ -129,6 +135,7 @@ def _sig():
     batch = [C.c_void_p, dp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     _lib.psa_search_batch.argtypes = batch + [C.POINTER(_CResult)]
     _lib.psa_batch_prepare.argtypes = batch
+    _lib.psa_search_many.argtypes = [C.c_void_p, C.POINTER(_CProblem), C.c_int32, C.c_int]
     _lib.psa_batch_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib.psa_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_CResult)]
     _lib.psa_search_range.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
@@ -367,6 +374,31 @@ class Context:
         result array from new_result_array().  No Python objects are created per result."""
         self._check(_lib.psa_search_batch(self._h, weights_c, int(bool(is_max)), batch.seq1_ptr, batch.len1,
                                           batch.seq2s_ptr, batch.q_off_ptr, batch.nq, out))
+
+    def make_problem_list(self, items):
+        """psa_problem array for search_many_raw: items = [(weights_c, is_max, Batch, result array), ...] (kept alive by the caller)."""
+        arr = (_CProblem * max(len(items), 1))()
+        for k, (wc, is_max, b, out) in enumerate(items):
+            arr[k].weights = C.cast(wc, C.POINTER(C.c_double))
+            arr[k].is_max = int(bool(is_max)); arr[k].nq = b.nq
+            arr[k].seq1 = b.seq1_ptr; arr[k].len1 = b.len1
+            arr[k].seq2s = b.seq2s_ptr; arr[k].q_off = b.q_off_ptr
+            arr[k].out = C.cast(out, C.c_void_p).value
+        return arr
+
+    def search_many_raw(self, problems, n: int, lanes: int = 0):
+        """The bare C call (psa_search_many): n problems pipelined over the context's device slots, `lanes` lanes each."""
+        self._check(_lib.psa_search_many(self._h, problems, n, lanes))
+
+    def search_many(self, items, lanes: int = 0) -> List[List[Result]]:
+        """items = [(weights, is_max, seq1, queries), ...] -> one result list per problem (psa_search_many)."""
+        built = []
+        for w, is_max, seq1, queries in items:
+            b = Batch(seq1, queries)
+            built.append((_w(w), is_max, b, (_CResult * max(b.nq, 1))()))
+        arr = self.make_problem_list(built)
+        self.search_many_raw(arr, len(built), lanes)
+        return [[_py(out[i]) for i in range(b.nq)] for (_, _, b, out) in built]
 
     @staticmethod
     def new_result_array(nq: int, pinned: bool = False):

@@ -327,24 +327,39 @@ int psa_run_files_all(psa_context* ctx, const char* input_path, const char* outp
     }
     std::fclose(f);
     if (tok.size() < 7) return PSA_ERR_IO;                      // not even one complete block
-    std::string text;
-    int done = 0;
-    for (size_t k = 0; k + 7 <= tok.size(); k += 7) {
-        double w[4];
+    // every complete block is one problem of a pipelined list (psa_search_many): the copies and launch of one block overlap
+    // the kernel of another, and on a multi-GPU context the blocks spread over the GPUs
+    const size_t nb = tok.size() / 7;
+    std::vector<double> weights(4 * nb);
+    std::vector<int64_t> q_off(2 * nb);
+    std::vector<psa_result> res(nb);
+    std::vector<psa_problem> problems(nb);
+    for (size_t b = 0; b < nb; b++) {
+        const size_t k = 7 * b;
         bool ok = true;
         for (int i = 0; i < 4 && ok; i++) {
             char* end = nullptr;
-            w[i] = std::strtod(tok[k + i].c_str(), &end);
+            weights[4 * b + i] = std::strtod(tok[k + i].c_str(), &end);
             ok = end && *end == '\0' && end != tok[k + i].c_str();
         }
         if (!ok) return PSA_ERR_IO;
         const std::string &s1 = tok[k + 4], &s2 = tok[k + 5];
-        const int is_max = tok[k + 6] == "maximum" ? 1 : 0;
-        const int64_t q_off[2] = { 0, (int64_t)s2.size() };
-        psa_result r;
-        int rc = psa_search_batch(ctx, w, is_max, s1.c_str(), (int64_t)s1.size(), s2.c_str(), q_off, 1, &r);
-        if (rc) return rc;
-        std::string mut(s2);
+        q_off[2 * b] = 0; q_off[2 * b + 1] = (int64_t)s2.size();
+        psa_problem& p = problems[b];
+        p.weights = &weights[4 * b];
+        p.is_max = tok[k + 6] == "maximum" ? 1 : 0;
+        p.nq = 1;
+        p.seq1 = s1.c_str(); p.len1 = (int64_t)s1.size();
+        p.seq2s = s2.c_str(); p.q_off = &q_off[2 * b];
+        p.out = &res[b];
+        p.status = PSA_OK; p.reserved = 0;
+    }
+    if (int rc = psa_search_many(ctx, problems.data(), (int32_t)nb, 0)) return rc;
+    std::string text;
+    int done = 0;
+    for (size_t b = 0; b < nb; b++) {
+        const psa_result& r = res[b];
+        std::string mut(tok[7 * b + 5]);
         if (r.mutant.char_offset >= 0) mut[(size_t)r.mutant.char_offset] = r.mutant.ch;
         char tail[96];
         std::snprintf(tail, sizeof(tail), "\n%d %g", r.mutant.offset, r.score);

@@ -17,6 +17,7 @@
 #include <cuda.h>            // types and the prototype of cuStreamWriteValue32 only: the entry point is looked up at run time
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -98,6 +99,8 @@ struct psa_context {
     std::vector<DeviceState> devs;
     std::vector<std::unique_ptr<Worker>> workers;     // workers[g-1] serves devs[g]
     std::vector<psa_shard> plan;                      // shard of the current batch per GPU
+    std::vector<psa_context*> lanes;                  // psa_search_many: one single-device child context per (device slot, lane)
+    std::vector<std::unique_ptr<Worker>> lane_workers; //   and a host thread for every lane but the first (which runs on the caller's)
     std::mutex err_mu;
     std::string err;
     // options
@@ -710,6 +713,15 @@ int psa_create(psa_context** out, const int* devices, int ndevices)
 void psa_destroy(psa_context* ctx)
 {
     if (!ctx) return;
+    for (auto& w : ctx->lane_workers) {
+        if (!w) continue;
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    ctx->lane_workers.clear();
+    for (psa_context* lane : ctx->lanes) psa_destroy(lane);
+    ctx->lanes.clear();
     for (auto& w : ctx->workers) {
         { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
         w->cv.notify_all();
@@ -1209,6 +1221,74 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, cons
                              int(&d - ctx->devs.data()), d.dev, d.st_prepare_ns * 1e-3, d.st_enqueue_ns * 1e-3, d.st_wait_ns * 1e-3);
     }
     return rc;
+}
+
+// Pipelined list of problems: lanes (single-device child contexts, each with its own stream, buffers and host thread)
+// take problems off a shared counter; see psa_b200.h.
+int psa_search_many(psa_context* ctx, psa_problem* problems, int32_t nproblems, int lanes_per_device)
+{
+    if (!ctx) return PSA_ERR_ARG;
+    if (nproblems < 0 || (nproblems > 0 && !problems) || lanes_per_device < 0 || lanes_per_device > 4)
+        return fail(ctx, PSA_ERR_ARG, "psa_search_many: bad argument");
+    if (nproblems == 0) return PSA_OK;
+    const int per_dev = lanes_per_device ? lanes_per_device : 2;
+    const int ndev = (int)ctx->devs.size();
+    const size_t want = (size_t)ndev * per_dev;
+    // lane l of device slot g is lanes[g * 4 + l]; created on first use, kept for the life of the context
+    if (ctx->lanes.size() < (size_t)ndev * 4) ctx->lanes.resize((size_t)ndev * 4, nullptr);
+    std::vector<psa_context*> use;
+    for (int l = 0; l < per_dev; l++)                                // lane-major: few problems spread over the GPUs first
+        for (int g = 0; g < ndev; g++) {
+            psa_context*& lane = ctx->lanes[(size_t)g * 4 + l];
+            if (!lane) {
+                const int dev = ctx->devs[g].dev;
+                const int rc = psa_create(&lane, &dev, 1);
+                if (rc) return fail(ctx, rc, "psa_search_many: cannot create a lane on cuda:%d", dev);
+            }
+            // the caller's knobs apply to every lane
+            lane->opt_engine = ctx->opt_engine; lane->opt_rank_planes = ctx->opt_rank_planes; lane->opt_scan_warps = ctx->opt_scan_warps;
+            lane->opt_fused_finish = ctx->opt_fused_finish; lane->opt_derive_rank = ctx->opt_derive_rank; lane->opt_pack_queries = ctx->opt_pack_queries;
+            lane->opt_zero_copy = ctx->opt_zero_copy; lane->opt_stream_queries = ctx->opt_stream_queries; lane->opt_slices = ctx->opt_slices;
+            lane->opt_sliced_keys = ctx->opt_sliced_keys; lane->opt_batch_mode = ctx->opt_batch_mode; lane->opt_stripe_mode = ctx->opt_stripe_mode;
+            lane->opt_single_launch = ctx->opt_single_launch;
+            use.push_back(lane);
+        }
+    const size_t nlanes = std::min(want, (size_t)nproblems);
+    std::atomic<int32_t> next{ 0 };
+    auto work = [&](psa_context* lane) {
+        for (;;) {
+            const int32_t k = next.fetch_add(1, std::memory_order_relaxed);
+            if (k >= nproblems) return;
+            psa_problem& p = problems[k];
+            p.status = psa_search_batch(lane, p.weights, p.is_max, p.seq1, p.len1, p.seq2s, p.q_off, p.nq, p.out);
+        }
+    };
+    // lane 0 runs here, the others on threads that stay with the context (waking one costs less than starting one)
+    if (ctx->lane_workers.size() < want) ctx->lane_workers.resize(want);
+    for (size_t l = 1; l < nlanes; l++) {
+        if (!ctx->lane_workers[l]) {
+            ctx->lane_workers[l].reset(new Worker());
+            ctx->lane_workers[l]->th = std::thread(worker_loop, ctx->lane_workers[l].get());
+        }
+        Worker& w = *ctx->lane_workers[l];
+        std::lock_guard<std::mutex> lk(w.mu);
+        psa_context* lane = use[l];
+        w.job = [&work, lane]() { work(lane); return 0; };
+        w.pending = true;
+        w.cv.notify_one();
+    }
+    work(use[0]);
+    for (size_t l = 1; l < nlanes; l++) {
+        Worker& w = *ctx->lane_workers[l];
+        std::unique_lock<std::mutex> lk(w.mu);
+        w.cv.wait(lk, [&w] { return !w.pending; });
+    }
+    for (int32_t k = 0; k < nproblems; k++)
+        if (problems[k].status != PSA_OK) {
+            // the message of the lane that failed is gone with the next problem it took: name the problem instead
+            return fail(ctx, problems[k].status, "psa_search_many: problem %d failed: %s", (int)k, psa_strerror(problems[k].status));
+        }
+    return PSA_OK;
 }
 
 int psa_search_range(psa_context* ctx, const double weights[4], int is_max, const char* seq1, int64_t len1,

@@ -676,6 +676,50 @@ def test_gated_timed_runs(psa, port, synth):
             assert all(same_answer(g, e) for g, e in zip(c.fetch(), exp))
 
 
+def test_search_many_pipelined(psa, port, synth):
+    """psa_search_many: a list of independent problems (different Seq1, weights, goals, batch shapes -- stripe mode, the
+    single-query launch, ragged batches, a re-scored order) pipelined over lanes; every problem's records equal what the
+    oracle gives for it alone.  One to four lanes on one device slot, two lanes on three slots, a failing problem in the list."""
+    rng = random.Random(77)
+    items = []
+    for k in range(14):
+        kind = k % 5
+        s1 = synth.letters(200 + k, rng.choice([700, 3000, 5000]))
+        if kind == 0:
+            qs = [bytes(synth.letters(300 + 31 * k + j, 200)) for j in range(rng.randint(2, 90))]      # equal lengths: stripe mode
+        elif kind == 1:
+            qs = [bytes(synth.letters(400 + k, rng.randint(64, 600)))]                                  # one query: k_single
+        elif kind == 2:
+            qs = [bytes(synth.letters(500 + 17 * k + j, rng.randint(1, 300))) for j in range(rng.randint(2, 40))]   # ragged
+        elif kind == 3:
+            qs = [bytes(synth.letters(600 + 13 * k + j, 64)) for j in range(400)]                        # many short queries
+        else:
+            qs = [bytes(synth.letters(700 + k + j, 150)) for j in range(5)]
+        w = [[1, 3, 4, 2], [1, 1, 1, 1], [1.5, 2.6, 0.1, 0.2], [5, 1, 2, 3]][k % 4]
+        items.append((w, bool(k & 1), bytes(s1), qs))
+    exp = [port.search_batch(w, mx, s1, qs) for (w, mx, s1, qs) in items]
+
+    def check(got):
+        for g_list, e_list in zip(got, exp):
+            assert len(g_list) == len(e_list)
+            assert all(same_answer(g, e) for g, e in zip(g_list, e_list))
+
+    with psa.Context(1) as c:
+        for lanes in (0, 1, 3, 4):
+            check(c.search_many(items, lanes=lanes))
+        assert c.search_many([], lanes=2) == []
+        bad = list(items)
+        bad[5] = (bad[5][0], bad[5][1], bad[5][2], [b"AB?D"])
+        with pytest.raises(psa.PsaError):
+            c.search_many(bad, lanes=2)
+        check(c.search_many(items, lanes=2))                               # the lanes recover
+        with pytest.raises(psa.PsaError):
+            c.search_many(items, lanes=5)
+    with psa.Context(devices=[0, 0, 0]) as c:
+        check(c.search_many(items, lanes=2))
+        check(c.search_many(items[:2], lanes=2))                           # fewer problems than lanes
+
+
 def test_random_batches(ctx, port):
     """Random batches through the default dispatch (long / packed / batch mode, fused or separate finish, exact or
     re-scored order, zero-copy or copied results): equal-length and ragged, tiny and multi-tile, five alphabets."""

@@ -11,15 +11,16 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
 psa = importlib.import_module("parallel-sequence-alignment_b200")
 synth = importlib.import_module("parallel-sequence-alignment_b200.synth")
 
 
 def main():
-    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c5"]
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c5", "c1", "c2"]
     with psa.Context(1) as c:
         for name in names:
-            wl = synth.workload(name)
+            wl = bench.make_workload(synth, name, 0)
             b = psa.Batch(wl.seq1, wl.queries, pinned=True)
             out = c.new_result_array(b.nq, pinned=True)
             wc = psa.c_weights(wl.weights)
