@@ -802,6 +802,7 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "stripe_queries_per_task")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.Q : 0; }
     if (!std::strcmp(name, "stripe_team_warps")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.T : 0; }
     if (!std::strcmp(name, "stripe_teams")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.teams : 0; }
+    if (!std::strcmp(name, "stripe_split")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.split : 0; }
     if (!std::strcmp(name, "stripe_lanes")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.S : 0; }
     if (!std::strcmp(name, "batch_mode")) { const DeviceState* d = first_active(); return ctx->batch_mode && !(d && d->stripe.ok) ? 1 : 0; }
     if (!std::strcmp(name, "slices")) { for (const DeviceState& d : ctx->devs) if (d.active) return d.single.ok ? d.single.slices : d.SG.slices; return 1; }

@@ -144,6 +144,8 @@ struct StripeGeom {
     size_t smem = 0;
     int threads = 0;     // block size
     int rank_planes_read = 0;   // rank bit planes in the window: 0 (none tracked, or the top rank is derived), 1 (uint32), 2 (uint2)
+    int split = 0;       // passes of a task that are cut in two along their steps (then T == passes + split: one unit per warp), so that
+                         //   the four schedulers of an SM carry equal shares of a task whose pass count is not a multiple of four
 };
 // threads of the one block per SM: 20 warps at <= 96 registers (28 warps at 72 registers measured no faster on short queries)
 __host__ __device__ constexpr int stripe_threads(int nb) { return nb <= 7 ? 640 : 640; }

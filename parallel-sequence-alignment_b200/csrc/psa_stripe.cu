@@ -357,6 +357,9 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
     uint32_t* s_ror_all = s_ro_all + size_t(SG.teams) * ro_team;                            // rank offsets (kRankPass)
     StripeSlot* s_slot_all = reinterpret_cast<StripeSlot*>(s_ror_all + (kRor ? size_t(SG.teams) * ro_team : 0));
     const int slots_team = SG.T * SG.Q;                                                     // [warp of the team][query of the task]
+    // split passes: the warp that counts the first part of the steps leaves its counter planes here for the warp that counts the rest
+    constexpr int kMergeWords = 3 * NB + 2;                                                 // A, B, C planes + two rank words
+    uint32_t* s_merge = reinterpret_cast<uint32_t*>(s_slot_all + size_t(SG.teams) * slots_team);   // [split pass][word][lane]
     const uint8_t* s_code = &T.code[0][0];                                                  // the pair table (in shared memory with T)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
@@ -690,7 +693,16 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
         Cand lbest = none;
         int lpass = -1;
         uint32_t lfloor = 0u;
-        for (int p = tw; p < passes; p += SG.T) {
+        // Units of work: whole passes, or -- for the last `split` passes of a task in a split plan -- the two parts of a pass
+        // (steps [0, gh) and [gh, steps)), each on a warp of its own: the first part's warp leaves its counters in shared
+        // memory and is done; the second part's warp adds them to its own and carries on as if it had counted every step.
+        const int split = SG.split, full = SG.passes - split;
+        const int gh = groups >= 8 ? groups / 2 + 1 : (groups + 1) / 2;        // the second part also runs the pass's epilogue
+        for (int u = tw; u < (split ? SG.T : passes); u += SG.T) {
+            int p = u, part = 0;                                    // part: 0 whole pass, 1 first steps, 2 the rest
+            if (split && u >= full) { p = full + ((u - full) >> 1); part = 1 + ((u - full) & 1); }
+            if (p >= passes) continue;                              // (a short last task: both parts skip)
+            const int g_begin = part == 2 ? gh : 0, g_end = part == 1 ? gh : groups;
             const int f = p * 32 + lane;
             const bool lane_on = f < lanes_task;
             const int j = lane_on ? f / S : 0, l = lane_on ? f - j * S : 0;        // idle lanes shadow lane 0 (addresses stay valid)
@@ -703,7 +715,7 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
             if constexpr (kRankPass && !kRank2) {
                 const uint32_t* ror = s_ror + j * SG.ro_stride;
                 const char* pr = reinterpret_cast<const char*>(s_rnk) + size_t(l) * 4;
-                for (int g = 0; g < groups; g++) {
+                for (int g = g_begin; g < g_end; g++) {
                     stripe_rank_group(racc[0], pr, ror + g * 32);
                     if (__all_sync(0xFFFFFFFFu, racc[0] == 0xFFFFFFFFu)) break;
                 }
@@ -712,9 +724,44 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
             A.clear(); B.clear(); C.clear();
             const char* pw = reinterpret_cast<const char*>(s_cls) + size_t(l) * 8;
             if constexpr (kRank2) {
-                for (int g = 0; g < groups; g++) stripe_class_rank_group<NUP>(A, B, C, racc, pw, ro + g * 32);
+                for (int g = g_begin; g < g_end; g++) stripe_class_rank_group<NUP>(A, B, C, racc, pw, ro + g * 32);
             } else {
-                for (int g = 0; g < groups; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+                for (int g = g_begin; g < g_end; g++) stripe_class_group<NUP>(A, B, C, pw, ro + g * 32);
+            }
+            if (part != 0) {
+                // named barrier 2 + j pairs the two warps of split pass j (barrier 1 is this team's; split plans have one team)
+                uint32_t* mg = s_merge + size_t(p - full) * kMergeWords * 32 + lane;
+                const int bar = 2 + (p - full);
+                if (part == 1) {
+#pragma unroll
+                    for (int k = 0; k < NB; k++) { mg[k * 32] = A.plane(k); mg[(NB + k) * 32] = B.plane(k); mg[(2 * NB + k) * 32] = C.plane(k); }
+                    mg[3 * NB * 32] = racc[0];
+                    if constexpr (K > 1) mg[(3 * NB + 1) * 32] = racc[1];
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, 64;" ::"r"(bar) : "memory");
+                    continue;                                       // nothing of this pass is left for this warp
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+                uint32_t a[NB], b[NB], c[NB], o[NB];
+#pragma unroll
+                for (int k = 0; k < NB; k++) { a[k] = A.plane(k); b[k] = B.plane(k); c[k] = C.plane(k); }
+#pragma unroll
+                for (int k = 0; k < NB; k++) o[k] = mg[k * 32];
+                sliced_add_scaled<NB, NB>(a, o, 1);
+#pragma unroll
+                for (int k = 0; k < NB; k++) o[k] = mg[(NB + k) * 32];
+                sliced_add_scaled<NB, NB>(b, o, 1);
+#pragma unroll
+                for (int k = 0; k < NB; k++) o[k] = mg[(2 * NB + k) * 32];
+                sliced_add_scaled<NB, NB>(c, o, 1);
+#pragma unroll
+                for (int k = 0; k < NB; k++) {
+                    if (k < 5) { A.low[k] = a[k]; B.low[k] = b[k]; C.low[k] = c[k]; }
+                    else { A.up[k - 5 < NUP ? k - 5 : 0] = a[k]; B.up[k - 5 < NUP ? k - 5 : 0] = b[k]; C.up[k - 5 < NUP ? k - 5 : 0] = c[k]; }
+                }
+                // rank words: "saturated outside the range" is in both parts' words, so OR is the union of what the steps met
+                racc[0] |= mg[3 * NB * 32];
+                if constexpr (K > 1) racc[1] |= mg[(3 * NB + 1) * 32];
             }
             if (DR) racc[0] |= derive_top_rank<NB, NUP>(T, A, B, C);
             PSA_TRACE_MARK(4);
@@ -764,7 +811,7 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
                 if (better(key, off, lbest.key, lbest.off)) { lbest.key = key; lbest.off = off; lpass = p; }
             }
             // ---- flush: lanes whose query ends with this pass hand their running best to the warp's slot of that query ----
-            const int pn = p + SG.T;
+            const int pn = split ? passes : p + SG.T;               // (split plans: one unit per warp, every lane leaves)
             const bool leaving = lane_on && (pn >= passes || (pn * 32 + lane) >= lanes_task || (pn * 32 + lane) / S != j);
             if (__any_sync(0xFFFFFFFFu, leaving)) {
                 for (int jj = jlo; jj <= jhi; jj++) {               // warp-uniform
@@ -826,6 +873,7 @@ size_t stripe_smem_bytes(const StripeGeom& g, int64_t len1, int rank_planes_read
     b += size_t(std::max<int64_t>(stripe_seq1_span(g), (len1 + 15) & ~int64_t(15)));
     b += size_t(g.teams) * g.Q * g.ro_stride * 4 * (rank_planes_read == 1 ? 2 : 1);
     b += size_t(g.teams) * g.T * g.Q * sizeof(StripeSlot);
+    b += size_t(g.split) * (3 * 10 + 2) * 32 * 4;                   // merge buffers of the split passes (NB <= 10)
     return b;
 }
 
@@ -883,11 +931,38 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, int rank_planes_r
             if (better_cost || tie) {
                 best_cost = have && tie ? std::min(best_cost, cost) : cost;
                 best_busy = busy;
-                g.Q = Q; g.passes = passes; g.T = Tw; g.teams = teams; g.ntasks = ntasks;
+                g.Q = Q; g.passes = passes; g.T = Tw; g.teams = teams; g.ntasks = ntasks; g.split = 0;
                 have = true;
             }
         }
+        // Split plans: ONE task per block in ONE round, a warp per pass -- and, where the pass count is not a multiple of four, the
+        // last `sp` passes cut in two along their steps, so that warp w % 4 = scheduler carries equal shares (config 3: 7 queries
+        // = 18 passes = 16 whole + 2 x 2 parts on 20 warps: 4.5 passes per scheduler on every SM, instead of 5 on the 68 SMs that
+        // hold four 5-pass tasks and 3.75 on the other 80).
+        static const int dbg_split = std::getenv("PSA_STRIPE_SPLIT") ? std::atoi(std::getenv("PSA_STRIPE_SPLIT")) : -1;   // experiments only
+        if (tasks_b == 1 && steps >= 256 && dbg_t <= 0)
+            for (int sp = 1; sp <= 3 && sp <= passes; sp++) {
+                if (dbg_split >= 0 && sp != dbg_split) continue;
+                const int Tw = passes + sp;
+                if (Tw > warps_max || Tw <= warps_max / 2 || Tw < 2) continue;      // one team, most of the block's warps
+                StripeGeom c = g;
+                c.Q = Q; c.passes = passes; c.T = Tw; c.teams = 1; c.ntasks = ntasks; c.split = sp;
+                if (stripe_smem_bytes(c, len1, rank_planes_read) > kStripeSmemMax) continue;
+                int load[4] = { 0, 0, 0, 0 };                                        // half passes per scheduler
+                for (int w = 0; w < Tw; w++) load[w & 3] += w < passes - sp ? 2 : 1;
+                const int worst = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+                const double pass_c = pass_groups_c + 1100.0;
+                const double util = double(Q) * double(S) / (32.0 * passes);
+                const double cost = std::max(0.5 * worst * pass_c, pass_c + 800.0) + 300.0 + (1.0 - util) * 0.5 * pass_c;   // + merging
+                if (!have || cost < best_cost * 0.99) {
+                    best_cost = cost;
+                    best_busy = Tw;
+                    g.Q = Q; g.passes = passes; g.T = Tw; g.teams = 1; g.ntasks = ntasks; g.split = sp;
+                    have = true;
+                }
+            }
     }
+    if (dbg_q > 0 || dbg_t > 0) { /* experiments: whatever the overrides left */ }
     if (!have) return g;
     // lanes that idle in the last pass of a task: below ~70 % the linear kernels' packing does better
     if (!force && double(g.Q) * double(S) / (32.0 * g.passes) < 0.70) return g;
