@@ -141,8 +141,10 @@ struct StripeSlot {
 // The finish step of one query by one warp (what finish_query_warp does for the linear kernels): sign counts, first
 // position carrying the best rank, replacement letter and score of the winning offset.  Seq1 symbols and the pair table
 // come from shared memory (the block staged both for the window), so the only global round trip is the query itself.
+//   ro / Wn : the query's per-step row offsets ((row * Wn + step) * 8, still in shared memory from the counting) -- the top-rank
+//             search reads the query's symbols out of them instead of going back to global memory
 __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const BatchPtrs& P, const uint8_t* s_seq1, const uint8_t* s_code,
-                                                    int q, int64_t qbeg, int len2, const StripeSlot& w)
+                                                    int q, int64_t qbeg, int len2, const StripeSlot& w, const uint32_t* ro, int Wn)
 {
     const int lane = threadIdx.x & 31;
     const Cand r{ w.key, w.off };
@@ -159,21 +161,17 @@ __device__ __forceinline__ void stripe_finish_query(const DeviceTable& T, const 
         // the FIRST position carrying that rank (strict compare in the reference, cpu_funcs.c:287-294) -- 32 positions per
         // round, normally found in the first round or two -- and the replacement letter there.
         const uint8_t* a = s_seq1 + r.off;
-        const uint8_t* b = P.seq2s + qbeg;
         const uint32_t want = uint32_t(T.nranks);
         int found = -1;
-        uint32_t found_c2 = 0;                                          // the query symbol at the position found (no second trip to global memory)
-        uint8_t nxt = lane < len2 ? b[lane] : uint8_t('A');
+        uint32_t found_c2 = 0;                                          // the query symbol at the position found
         for (int base = 0; base < len2 && found < 0; base += 32) {
-            const uint8_t cur = nxt;
-            if (base + 32 + lane < len2) nxt = b[base + 32 + lane];
             const int i = base + lane;
             bool hit = false;
             uint32_t c2 = 0;
             if (i < len2) {
                 uint32_t c1 = a[i];
-                c2 = symbol_of(cur);
-                if (c1 > 26u || c2 == 0xFFu) { c1 = 0; c2 = 0; }
+                c2 = ((ro[i] >> 3) - uint32_t(i)) / uint32_t(Wn);        // the row of step i = the query's symbol (a bad one was mapped to row 0)
+                if (c1 > 26u || c2 > 26u) { c1 = 0; c2 = 0; }
                 hit = (uint32_t(s_code[c2 * kRowPad + c1]) >> 2) == want;
             }
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
@@ -853,13 +851,13 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
         }
         // finish: one warp per query of the task -- best over the team's warps, then the record
         for (int jj = tw; jj < nqt; jj += SG.T) {
-            StripeSlot r = s_slot[jj];
-            for (int w = 1; w < SG.T; w++) {
-                const StripeSlot& o = s_slot[w * SG.Q + jj];
-                if (better(o.key, o.off, r.key, r.off)) r = o;
-            }
+            // best over the team's warps: lane w looks at warp w's slot (teams have at most 20 warps), one warp reduction
+            const Cand mine = lane < SG.T ? Cand{ s_slot[lane * SG.Q + jj].key, s_slot[lane * SG.Q + jj].off } : none;
+            const Cand wb = warp_best(mine);
+            const uint32_t own = __ballot_sync(0xFFFFFFFFu, lane < SG.T && mine.key == wb.key && mine.off == wb.off);
+            const StripeSlot r = s_slot[(own ? __ffs(int(own)) - 1 : 0) * SG.Q + jj];
             PSA_CHECK(q0 + jj < G.nq);
-            stripe_finish_query(T, P, s_seq1, s_code, q0 + jj, int64_t(q0 + jj) * len2, len2, r);
+            stripe_finish_query(T, P, s_seq1, s_code, q0 + jj, int64_t(q0 + jj) * len2, len2, r, s_ro + jj * SG.ro_stride, Wn);
         }
         PSA_TRACE_MARK(7);
         team_sync(team, team_threads);                              // next task's row offsets are in place, this task's slots are consumed
