@@ -6,7 +6,7 @@ set -u
 w=$1; k=$2; stem=$3; shift 3
 out=gpurun_out/profiles; mkdir -p $out
 for f in profiles/r0*_summary.json; do [ -f "$f" ] && [ ! -f $out/$(basename $f) ] && cp $f $out/; done
-B="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-others --no-strong $*"
+B="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-others --no-strong --opt gate_timed_runs=0 --opt stream_queries=0 $*"
 $B > gpurun_out/plain_$stem.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$stem.log; exit 1; }
 ncu --set full --import-source on --clock-control none -k regex:$k -s 3 -c 1 -f -o /tmp/$stem $B > gpurun_out/ncu_$stem.log 2>&1
 python tools/ncu_summary.py --out $out /tmp/$stem.ncu-rep $w >> gpurun_out/sum.log 2>&1
