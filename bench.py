@@ -363,7 +363,10 @@ def strong_scaling(psa, synth, torch, ngpus, steps, workloads=("c3", "c5", "c4")
             torch.cuda.synchronize(g)
 
     rec = {"n_gpus": ngpus, "how": "rank 0 alone: psa_create over devices 0..N-1, psa_search_batch on pinned host buffers, wall clock per call, "
-                                   "L2 of every GPU flushed between calls; t(1) from a 1-device context in the same process", "workloads": {}}
+                                   "L2 of every GPU flushed between calls; t(1) from a 1-device context in the same process.  A call is spread "
+                                   "over at most (its pair evaluations / 2.5e9) GPUs (`gpus_used`): a 40 us problem is not worth eight "
+                                   "shards' copies and launches; streams of such problems scale as `list_of_batches` (psa_search_many)",
+           "workloads": {}}
     ctxs = {1: psa.Context(devices=[0])}
     if ngpus > 1:
         ctxs[ngpus] = psa.Context(devices=list(range(ngpus)))
@@ -399,7 +402,7 @@ def strong_scaling(psa, synth, torch, ngpus, steps, workloads=("c3", "c5", "c4")
                 w[f"n{n}"] = {"e2e_ms": 1e3 * t / steps, "e2e_pair_evals_per_s": batch.pair_evals * steps / t,
                               "device_ms_max_over_gpus": dev / steps, "device_pair_evals_per_s": batch.pair_evals * steps / (dev * 1e-3),
                               "host_split_us": {k[5:-3]: v / steps * 1e-3 for k, v in split.items()},
-                              "launches_per_call": c.stat("kernel_launches"), "oracle_check": chk}
+                              "launches_per_call": c.stat("kernel_launches"), "gpus_used": c.stat("devices_used"), "oracle_check": chk}
             # The same workload as a LIST of independent batches through psa_search_many (2 lanes per GPU, a batch is never
             # split): what a stream of such batches gets out of the N GPUs of one process, end to end on host buffers.
             if name != "c4":

@@ -114,13 +114,15 @@ const char* psa_last_error(const psa_context* ctx);
                      while the kernel is already building its window; the kernel waits per task for the piece that holds the
                      task's queries | 0 one copy in front of the kernel
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns")
+     "min_split_work" a call is spread over at most (its pair evaluations / this value) of the context's GPUs, default 2.5e9
+                     (~80 us of kernel per GPU: a shard pays its own copies, launch and wake-up whatever its size) | 0 always all
      "gate_timed_runs" 1 psa_batch_run enqueues its events and launches behind a gate (a stream wait on a page-locked word) that
                      the host opens once everything is enqueued, so the reported device time holds no host launch latency;
                      the first run of a prepared batch is never gated (lazy kernel loading) | 0 (default) no gate */
 int psa_set_option(psa_context* ctx, const char* name, long long value);
 /* Facts about the last run: "kernel_launches", "tiles", "candidate_tiles" (32-offset words re-scored in reference
    order), "main_kernel_ns", "engine", "rank_planes", "scan_warps", "batch_mode", "slices", "packed_queries", "packed_warps", "exact",
-   "single_launch", "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", "streamed_chunks" (pieces the
+   "single_launch", "stripe_mode", "stripe_queries_per_task", "stripe_team_warps", "stripe_teams", "stripe_lanes", "devices_used" (GPUs the last call was spread over), "streamed_chunks" (pieces the
    last one-shot call streamed its queries in; 0 = one plain copy), and the host-side split of the
    last psa_search_batch in ns: "host_plan_ns", "host_prepare_ns", "host_enqueue_ns", "host_wait_ns", "host_total_ns".
    Unknown -> -1. */

@@ -111,6 +111,7 @@ struct psa_context {
     int opt_derive_rank = 1;   // 0: always read the top-rank bit from a rank plane
     int opt_pack_queries = 1;  // 0 never pack | 1 auto | 2..8 force that many queries per block (tests)
     int opt_zero_copy = 1;     // 1: result sets are written by the kernels straight into page-locked host memory (small ones; any size in stripe mode)
+    long long opt_min_split_work = 2500000000ll;   // a call is spread over at most work / this many GPUs (pair evaluations; 0: always over all)
     int opt_gate_timed_runs = 0; // 1: psa_batch_run enqueues its events and launches behind a host-released gate (device time only in the bracket)
     int opt_stream_queries = 1; // 1: one-shot stripe-mode batches copy their queries on a second stream while the kernel builds its window
     long long table_epoch = 0; // bumped whenever `table` is rebuilt
@@ -225,11 +226,16 @@ int pick_rank_planes(const psa_context* ctx)
 }
 
 // Run fn(device) for every GPU of the context: GPU 0 on the calling thread, the others on their worker threads.
+// Devices whose shard of the current plan is empty are not woken (waking a thread to find nothing costs a few microseconds).
 template <class F>
 int for_each_device(psa_context* ctx, F fn)
 {
     const int ndev = (int)ctx->devs.size();
+    auto idle = [ctx](int g) {
+        return g > 0 && (size_t)g < ctx->plan.size() && ctx->plan[g].q_begin == ctx->plan[g].q_end;
+    };
     for (int g = 1; g < ndev; g++) {
+        if (idle(g)) { ctx->devs[g].active = false; continue; }
         Worker& w = *ctx->workers[g - 1];
         std::lock_guard<std::mutex> lk(w.mu);
         w.job = [ctx, g, &fn]() { return fn(ctx->devs[g]); };
@@ -238,6 +244,7 @@ int for_each_device(psa_context* ctx, F fn)
     }
     int rc = fn(ctx->devs[0]);
     for (int g = 1; g < ndev; g++) {
+        if (idle(g)) continue;
         Worker& w = *ctx->workers[g - 1];
         std::unique_lock<std::mutex> lk(w.mu);
         w.cv.wait(lk, [&w] { return !w.pending; });
@@ -749,6 +756,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "zero_copy_results") && value >= 0 && value <= 1) { ctx->opt_zero_copy = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "stream_queries") && value >= 0 && value <= 1) { ctx->opt_stream_queries = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "gate_timed_runs") && value >= 0 && value <= 1) { ctx->opt_gate_timed_runs = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "min_split_work") && value >= 0) { ctx->opt_min_split_work = value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "slices") && value >= 0 && value <= 256) { ctx->opt_slices = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "sliced_keys") && value >= 0 && value <= 1) { ctx->opt_sliced_keys = (int)value; return PSA_OK; }
@@ -802,6 +810,7 @@ long long psa_get_stat(const psa_context* ctx, const char* name)
     if (!std::strcmp(name, "stripe_queries_per_task")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.Q : 0; }
     if (!std::strcmp(name, "stripe_team_warps")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.T : 0; }
     if (!std::strcmp(name, "stripe_teams")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.teams : 0; }
+    if (!std::strcmp(name, "devices_used")) { long long n = 0; for (const DeviceState& d : ctx->devs) n += d.active ? 1 : 0; return n; }
     if (!std::strcmp(name, "stripe_split")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.split : 0; }
     if (!std::strcmp(name, "stripe_lanes")) { const DeviceState* d = first_active(); return d && d->stripe.ok ? d->stripe.S : 0; }
     if (!std::strcmp(name, "batch_mode")) { const DeviceState* d = first_active(); return ctx->batch_mode && !(d && d->stripe.ok) ? 1 : 0; }
@@ -1027,13 +1036,24 @@ static int prepare_common(psa_context* ctx, const double* weights, int is_max, c
 
     const int64_t granule = ctx->engine == 2 ? ctx->scan_tile : kExactTile;
     ctx->plan.assign(ndev, psa_shard{ 0, 0, -1, -1 });
+    // A call is worth spreading over the GPUs only when each gets enough to do: a shard pays its own copies, launch and
+    // wake-up (~30 us) whatever its size, and eight host threads enqueue no faster than one.  Below `min_split_work` pair
+    // evaluations per GPU (2.5e9 = ~80 us of kernel) fewer GPUs take the call -- config 3 (1.3e9) and config 4 (2e9) run on
+    // one, config 5 (4.2e10) on all eight.  Streams of small problems scale through psa_search_many instead.
+    int use = ndev;
+    if (ndev > 1 && ctx->opt_min_split_work > 0) {
+        double work = 0.0;
+        if (ctx->uniform_len2 > 0) work = double(nq) * double(last >= 0 ? last - first : offsets_of(len1, max_len2)) * double(max_len2);
+        else for (int q = 0; q < nq; q++) work += double(offsets_of(len1, q_off[q + 1] - q_off[q])) * double(q_off[q + 1] - q_off[q]);
+        use = int(std::min<double>(ndev, std::max(1.0, std::floor(work / double(ctx->opt_min_split_work)))));
+    }
     if (nq > 1 && ctx->uniform_len2 > 0) {
         // lengths were validated above and are all equal: the balanced split is arithmetic (no second pass over q_off)
-        for (int g = 0; g < ndev; g++) {
-            ctx->plan[g].q_begin = int32_t(int64_t(nq) * g / ndev);
-            ctx->plan[g].q_end = int32_t(int64_t(nq) * (g + 1) / ndev);
+        for (int g = 0; g < use; g++) {
+            ctx->plan[g].q_begin = int32_t(int64_t(nq) * g / use);
+            ctx->plan[g].q_end = int32_t(int64_t(nq) * (g + 1) / use);
         }
-    } else if ((rc = psa_plan_shards(len1, q_off, nq, ndev, granule, first, last, ctx->plan.data())))
+    } else if ((rc = psa_plan_shards(len1, q_off, nq, use, granule, first, last, ctx->plan.data())))
         return fail(ctx, rc, "cannot partition the batch");
     int used = 0;
     for (int g = 0; g < ndev; g++) used += ctx->plan[g].q_begin != ctx->plan[g].q_end;

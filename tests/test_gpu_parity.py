@@ -228,6 +228,7 @@ def _multi_device_body(psa, port, synth, devices):
     eq = [synth.letters(170 + k, 200) for k in range(300)]                # equal lengths: packed / batch mode per device
     with psa.Context(devices=devices) as c:
         assert c.ngpus == len(devices)
+        c.set_option("min_split_work", 0)                                 # these problems are small: split them all the same
         for w, is_max in (([1, 3, 4, 2], False), ([2, 1.5, 1.1, 1.3], True), ([1, 1, 1, 1], True)):
             r = c.search(w, is_max, s1, s2)
             assert same_answer(r, port.search(w, is_max, s1, s2, nthreads=8)), (w, is_max)
@@ -837,6 +838,7 @@ def test_mutant_strings_on_the_device(psa, ctx, port, synth):
                 assert same_answer(r, e)
                 assert m == e.mutant(q.decode()) and sum(a != b for a, b in zip(m, q.decode())) <= 1
     with psa.Context(devices=[0, 0, 0]) as c:
+        c.set_option("min_split_work", 0)
         res, muts = c.search_batch_mutants([1, 3, 4, 2], False, s1, ragged)
         exp = port.search_batch([1, 3, 4, 2], False, s1, ragged)
         assert [m for m in muts] == [e.mutant(q.decode()) for q, e in zip(ragged, exp)]

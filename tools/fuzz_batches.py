@@ -33,6 +33,7 @@ def main():
     slots = int(os.environ.get("PSA_FUZZ_SLOTS", "0"))
     modes = {}
     with (psa.Context(devices=[0] * slots) if slots else psa.Context(ngpus=int(os.environ.get("PSA_FUZZ_GPUS", "1")))) as ctx:
+        ctx.set_option("min_split_work", 0)            # small problems: exercise the split over the device slots all the same
         for trial in range(trials):
             w = rng.choice(wsets)
             is_max = bool(rng.getrandbits(1))
