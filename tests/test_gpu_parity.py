@@ -721,6 +721,51 @@ def test_search_many_pipelined(psa, port, synth):
         check(c.search_many(items[:2], lanes=2))                           # fewer problems than lanes
 
 
+def test_stripe_split_plans_random(psa, ctx, port):
+    """Equal-length batches that are ONE wave of long queries take the split plans of stripe mode (one task per block, the
+    last passes of the task cut in two along their steps and merged through shared memory).  Shapes aimed at that regime
+    (about 148 x 17 warp passes of work) and random ones around it -- small alphabets plant ties by the thousand -- against
+    the oracle (every query of the small batches, a sample of the large ones) and, record for record, against the
+    linear-plane kernels (stripe mode off); the team size the plan reports is checked against passes + split."""
+    rng = random.Random(4242)
+    seen_split = 0
+    for trial in range(14):
+        aimed = trial < 8
+        len1 = rng.randint(700, 2800)
+        len2 = rng.randint(256, min(len1 - 1, 700))
+        noff = len1 - len2 + 1
+        lanes = (noff + 31) // 32
+        if aimed:
+            q_task = max(1, (rng.choice([15, 16, 17, 18, 19]) * 32) // lanes)
+            nq = max(2, 148 * q_task - rng.randint(0, 2 * q_task))
+        else:
+            nq = max(8, min(rng.randint(20, 420), int(1.1e8 // (noff * len2))))
+        alpha = rng.choice([ALPHA, ALPHA[:26], "ACDG", "AB", "NDEQKHRST", "A-"])
+        w = rng.choice([[1, 3, 4, 2], [1, 1, 1, 1], [5, 1, 2, 3], [10, 2, 3, 4], [2, 2, 1, 3]])
+        is_max = bool(rng.getrandbits(1))
+        s1 = "".join(rng.choice(alpha) for _ in range(len1))
+        pool = ["".join(rng.choice(alpha) for _ in range(len2)) for _ in range(min(nq, 64))]
+        qs = [pool[k % len(pool)] if k >= len(pool) and rng.random() < 0.5 else "".join(rng.choice(alpha) for _ in range(len2)) if k >= len(pool) else pool[k]
+              for k in range(nq)]
+        at = rng.randrange(noff)
+        qs[nq // 2] = s1[at: at + len2]                                   # a query cut out of Seq1: a planted best offset
+        _set_engine(ctx, 0)
+        got = ctx.search_batch(w, is_max, s1, qs)
+        mode, split, q_task, t_warps = ctx.stat("stripe_mode"), ctx.stat("stripe_split"), ctx.stat("stripe_queries_per_task"), ctx.stat("stripe_team_warps")
+        sample = list(range(nq)) if not aimed else sorted(set(rng.sample(range(nq), 40) + [0, nq // 2, nq - 1]))
+        exp = port.search_batch(w, is_max, s1, [qs[k] for k in sample])
+        assert all(same_answer(got[k], e) and got[k].counts == e.counts for k, e in zip(sample, exp)), (trial, len1, len2, nq, w, is_max, mode, split, q_task, t_warps)
+        if aimed or trial % 3 == 0:
+            ctx.set_option("stripe_mode", 0)
+            lin = ctx.search_batch(w, is_max, s1, qs)
+            ctx.set_option("stripe_mode", -1)
+            assert [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in lin] == [(a.offset, a.char_offset, a.ch, a.score, a.counts) for a in got], (trial, mode, split)
+        if mode:
+            seen_split += split > 0
+            assert split == 0 or t_warps == (q_task * lanes + 31) // 32 + split, (trial, split, q_task, t_warps)
+    assert seen_split >= 2, seen_split                                  # (pass counts that are multiples of four need no split)
+
+
 def test_random_batches(ctx, port):
     """Random batches through the default dispatch (long / packed / batch mode, fused or separate finish, exact or
     re-scored order, zero-copy or copied results): equal-length and ragged, tiny and multi-tile, five alphabets."""
