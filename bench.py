@@ -406,7 +406,7 @@ def strong_scaling(psa, synth, torch, ngpus, steps, workloads=("c3", "c5", "c4")
             # The same workload as a LIST of independent batches through psa_search_many (2 lanes per GPU, a batch is never
             # split): what a stream of such batches gets out of the N GPUs of one process, end to end on host buffers.
             if name != "c4":
-                per_gpu = {"c3": 48, "c5": 6}.get(name, 8)
+                per_gpu = {"c3": 48, "c5": 12}.get(name, 8)
                 distinct = {"c3": 16, "c5": 3}.get(name, 4)
                 wls = [wl] + [make_workload(synth, name, 0, variant=k) for k in range(1, distinct)]
                 built = [(wc, x.is_max, batch if k == 0 else psa.Batch(x.seq1, x.queries, pinned=True),

@@ -640,6 +640,8 @@ inline bool swapable(int is_max, double s_old, int off_old, double s_new, int of
     return s_new == s_old && off_new < off_old;
 }
 
+static_assert(sizeof(psa_problem) == 64 && offsetof(psa_problem, seq1) == 16 && offsetof(psa_problem, out) == 48 && offsetof(psa_problem, status) == 56,
+              "psa_problem is what the ctypes mirror (and any FFI binding) lays out");
 static_assert(sizeof(QueryRec) == sizeof(psa_result), "device record == public result");
 static_assert(offsetof(QueryRec, ch) == offsetof(psa_result, mutant) + offsetof(psa_mutant, ch), "ch");
 static_assert(offsetof(QueryRec, rank) == offsetof(psa_result, rank) && offsetof(QueryRec, score) == offsetof(psa_result, score) &&

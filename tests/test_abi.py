@@ -118,6 +118,14 @@ def test_record_layouts(psa):
     assert psa.abi_version() == 1
 
 
+def test_problem_list_layout_and_argument_checks(psa):
+    """psa_problem (psa_search_many) as the ctypes mirror lays it out == the static_assert in psa_engine.cu; a null
+    context is refused before anything touches a GPU."""
+    P = psa._CProblem
+    assert C.sizeof(P) == 64 and P.seq1.offset == 16 and P.out.offset == 48 and P.status.offset == 56
+    assert psa._lib.psa_search_many(None, None, 0, 0) == psa.PSA_ERR_ARG
+
+
 def test_layouts_agree_with_reference_build(psa, ref):
     assert ref.lib.ref_sizeof_program_data() == C.sizeof(psa.ProgramData)
     assert ref.lib.ref_sizeof_mutant() == C.sizeof(psa.Mutant)
