@@ -147,6 +147,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     } while (!done);
 }
 
+// The same for a warp that can afford to wait: one lane polls, with a pause between polls, so that a ring of waiting warps
+// does not keep the shared-memory pipe busy with barrier traffic that the one warp doing the real work has to queue behind.
+__device__ __forceinline__ void mbar_wait_patient(uint64_t* bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) {
+        for (;;) {
+            uint32_t done;
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            if (done) break;
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+}
+
 // bytes % 16 == 0, both addresses 16-byte aligned; completion is signalled on `bar` (complete_tx)
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
 {

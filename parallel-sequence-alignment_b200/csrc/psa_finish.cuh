@@ -181,13 +181,55 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                     double total = 0.0;
                     uint32_t best_rank = 0;
                     if (COOP && coop) __syncthreads();                 // the previous word is done with the ring and the rank slots
+                    // COOP, queries of up to 8192 symbols: the whole query and the whole Seq1 window under the word are staged ONCE,
+                    // by all eight warps together, into the per-warp staging arrays taken as one flat array each -- every load of
+                    // both is in flight at the same time (one trip to L2 instead of two per 1024-step chunk and warp), and the
+                    // producers then run through the query without a chunk boundary at which the consumer would starve.
+                    const bool flat = COOP && coop && len2 <= kFinishWarps * kFinishChunk;
+                    const int chunk = flat ? len2 : kFinishChunk;
+                    uint16_t* const flat_q = &s_q[0][0];
+                    uint8_t* const flat_win = &s_win[0][0];
+                    if (flat) {
+                        const uint8_t* qsrc = b;
+                        const int ft = int(threadIdx.x);
+                        if ((reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
+                            for (int i = ft * 16; i < len2; i += kFinishThreads * 16) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(qsrc + i);
+                                const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                                for (int t = 0; t < 16; t++) {
+                                    uint32_t c2 = symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3))));
+                                    if (c2 == 0xFFu) c2 = 0;           // flagged by the kernels before us
+                                    if (i + t < len2) flat_q[i + t] = uint16_t(c2 * kRowPad);
+                                }
+                            }
+                        } else {
+                            for (int i = ft; i < len2; i += kFinishThreads) {
+                                uint32_t c2 = symbol_of(qsrc[i]);
+                                if (c2 == 0xFFu) c2 = 0;
+                                flat_q[i] = uint16_t(c2 * kRowPad);
+                            }
+                        }
+                        for (int i = ft * 16; i < len2 + 31; i += kFinishThreads * 16) {
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (n0 + i < G.len1) v = *reinterpret_cast<const uint4*>(P.seq1 + n0 + i);      // n0 is a multiple of 32
+                            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                            for (int t = 0; t < 16; t++) {
+                                uint32_t c1 = (n0 + i + t) < G.len1 ? symbol_of(uint8_t(w4[t >> 2] >> (8 * (t & 3)))) : 0u;
+                                if (c1 == 0xFFu) c1 = 0;
+                                if (i + t < len2 + 31) flat_win[i + t] = uint8_t(c1);
+                            }
+                        }
+                        __syncthreads();
+                    }
                     if (COOP && coop && gwarp == 0) {
                         // ---- consumer: addends from the ring, adds in step order --------------------------------------
                         const double* ring = reinterpret_cast<const double*>(fin_dyn);
                         uint64_t* bars = reinterpret_cast<uint64_t*>(fin_dyn + kFinishRingBytes + kFinishRankBytes);      // full[8], empty[8]
                         int nblk = 0;
-                        for (int c0 = 0; c0 < len2; c0 += kFinishChunk)
-                            nblk += (((len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk) + kFinishRingSteps - 1) / kFinishRingSteps;
+                        for (int c0 = 0; c0 < len2; c0 += chunk)
+                            nblk += (((len2 - c0) < chunk ? (len2 - c0) : chunk) + kFinishRingSteps - 1) / kFinishRingSteps;
                         for (int kb = 0; kb < nblk; kb++) {
                             const int slot = coop_blk % kFinishRingSlots, use = coop_blk / kFinishRingSlots;
                             mbar_wait(bars + slot, uint32_t(use) & 1u);                  // produced?
@@ -202,12 +244,15 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                             coop_blk++;
                         }
                     } else
-                    for (int c0 = 0; c0 < len2; c0 += kFinishChunk) {
-                        const int cl = (len2 - c0) < kFinishChunk ? (len2 - c0) : kFinishChunk;
+                    for (int c0 = 0; c0 < len2; c0 += chunk) {
+                        const int cl = (len2 - c0) < chunk ? (len2 - c0) : chunk;
                         __syncwarp();
                         // symbols of this chunk, 16 bytes per lane per load (both device buffers carry 64 bytes of padding;
                         // the Seq1 window starts on a multiple of 32, the query start may be anywhere)
                         const uint8_t* qsrc = b + c0;
+                        if (flat) {
+                            // staged above, once, by the whole block
+                        } else
                         if ((reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
                             for (int i = lane * 16; i < cl; i += 512) {
                                 const uint4 v = *reinterpret_cast<const uint4*>(qsrc + i);
@@ -228,6 +273,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                             }
                         }
                         const int64_t p0 = n0 + c0;                    // multiple of 32
+                        if (!flat)
                         for (int i = lane * 16; i < cl + 31; i += 512) {
                             uint4 v = make_uint4(0u, 0u, 0u, 0u);
                             if (p0 + i < G.len1) v = *reinterpret_cast<const uint4*>(P.seq1 + p0 + i);
@@ -240,7 +286,8 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                             }
                         }
                         __syncwarp();
-                        const uint8_t* wv = &s_win[warp][lane];
+                        const uint8_t* wv = flat ? flat_win + lane : &s_win[warp][lane];
+                        const uint16_t* qv = flat ? flat_q : &s_q[warp][0];
                         // The sum must be the reference's: one rounding per step, in step order -- a chain of dependent
                         // double adds run by one warp, with nothing to hide latency behind.  Measured on B200
                         // (tools/probes/dadd_probe.cu): 8 cycles per step when each addend is a plain shared-memory load
@@ -255,13 +302,13 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                             for (int i0 = 0; i0 < cl; i0 += kFinishRingSteps, coop_blk++) {
                                 if (coop_blk % (kFinishWarps - 1) != gwarp - 1) continue;
                                 const int slot = coop_blk % kFinishRingSlots, use = coop_blk / kFinishRingSlots;
-                                if (use >= 1) mbar_wait(bars + kFinishRingSlots + slot, uint32_t(use - 1) & 1u);    // the slot's previous content is consumed
+                                if (use >= 1) mbar_wait_patient(bars + kFinishRingSlots + slot, uint32_t(use - 1) & 1u);    // the slot's previous content is consumed
                                 double* dst = ring + size_t(slot) * kFinishRingSteps * 32 + lane;
                                 if (i0 + kFinishRingSteps <= cl) {
                                     uint32_t idx[kFinishRingSteps];
                                     double w32[kFinishRingSteps];
 #pragma unroll
-                                    for (int u = 0; u < kFinishRingSteps; u++) idx[u] = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+                                    for (int u = 0; u < kFinishRingSteps; u++) idx[u] = uint32_t(qv[i0 + u]) + wv[i0 + u];
 #pragma unroll
                                     for (int u = 0; u < kFinishRingSteps; u++) {
                                         w32[u] = s_wtab[idx[u]];
@@ -273,7 +320,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                                     for (int u = 0; u < kFinishRingSteps; u++) {
                                         double wgt = 0.0;                             // steps past the end add +0.0: exact
                                         if (i0 + u < cl) {
-                                            const uint32_t idx = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+                                            const uint32_t idx = uint32_t(qv[i0 + u]) + wv[i0 + u];
                                             wgt = s_wtab[idx];
                                             best_rank = max(best_rank, uint32_t(s_code[idx]) >> 2);
                                         }
@@ -291,7 +338,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                                 uint32_t idx[32];
                                 double w32[32];
 #pragma unroll
-                                for (int u = 0; u < 32; u++) idx[u] = uint32_t(s_q[warp][i0 + u]) + wv[i0 + u];
+                                for (int u = 0; u < 32; u++) idx[u] = uint32_t(qv[i0 + u]) + wv[i0 + u];
 #pragma unroll
                                 for (int u = 0; u < 32; u++) {
                                     w32[u] = s_wtab[idx[u]];
@@ -301,7 +348,7 @@ __device__ __forceinline__ void finish_body(const DeviceTable& T, const BatchGeo
                                 for (int u = 0; u < 32; u++) total += w32[u];
                             } else {
                                 for (int i = i0; i < cl; i++) {
-                                    const uint32_t code = s_code[uint32_t(s_q[warp][i]) + wv[i]];
+                                    const uint32_t code = s_code[uint32_t(qv[i]) + wv[i]];
                                     total += s_w[code & 3u];
                                     best_rank = max(best_rank, code >> 2);
                                 }
