@@ -921,7 +921,10 @@ StripeGeom stripe_plan(int64_t len1, int64_t len2, int32_t nq, int rank_planes_r
             const double pass_c = pass_groups_c + (Tw == 1 ? 400.0 : 1100.0);
             const double task_c = 500.0 + (Tw > 1 ? 300.0 : 0.0);
             const double util = double(Q) * double(S) / (32.0 * passes);                 // lanes that hold offsets
-            const double spread = std::ceil(double(tasks_b) * passes / 4.0) * pass_c;    // warp w issues on scheduler w % 4
+            // warp w issues on scheduler w % 4: a team's passes go round its warps, hence round the schedulers -- but a one-warp
+            // team's task stays on one scheduler, so there whole tasks are what is dealt out (8 192 config-5 queries, a GPU's share
+            // of the batch on eight: 14 four-query tasks per SM put 4 on two schedulers and 3 on the others; 12 five-query tasks, 3 on each)
+            const double spread = Tw == 1 ? std::ceil(double(tasks_b) / 4.0) * passes * pass_c : std::ceil(double(tasks_b) * passes / 4.0) * pass_c;
             const double chain = double(rounds) * (ppw * pass_c * stretch + task_c);
             const double cost = std::max(spread, chain) + (1.0 - util) * 0.5 * pass_c;   // time of the busiest block = time of the launch
             const bool better_cost = !have || cost < best_cost * 0.99;
