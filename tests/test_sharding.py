@@ -151,3 +151,30 @@ def test_packing_plan(psa):
             assert q * lanes / (32 * w) >= 1.05 * lanes / (32 * ((lanes + 31) // 32))
     with pytest.raises(psa.PsaError):
         psa.plan_packing(10, 20, 5)
+
+
+def test_stripe_plans(psa):
+    """Stripe mode's launch shape (psa_plan_stripes, host arithmetic) for the shapes the design documents.
+    Config 3 is ONE wave: a split plan -- 7 queries = 553 lanes = 18 passes per block, 16 whole passes + 2 x 2 parts on 20
+    warps, 147 blocks.  Config 5 and anything with thousands of tasks: one-warp teams; there whole tasks are what a
+    scheduler is dealt, so a GPU's share of config 5 on eight GPUs takes smaller tasks than the whole batch does."""
+    p = psa.plan_stripes(3000, 500, 1024, 0)
+    assert (p["ok"], p["lanes"], p["queries_per_task"], p["passes"], p["team_warps"], p["teams"], p["blocks"]) == (1, 79, 7, 18, 20, 1, 147)
+    assert p["smem_bytes"] <= 224 * 1024
+    p = psa.plan_stripes(10000, 64, 65536, 2)
+    assert (p["ok"], p["lanes"], p["queries_per_task"], p["passes"], p["team_warps"], p["teams"], p["blocks"]) == (1, 311, 4, 39, 1, 20, 148)
+    p = psa.plan_stripes(3000, 500, 16384, 0)
+    assert (p["ok"], p["queries_per_task"], p["team_warps"], p["teams"]) == (1, 2, 1, 20)
+    p = psa.plan_stripes(10000, 64, 8192, 2)
+    assert p["ok"] == 1 and p["team_warps"] == 1 and p["queries_per_task"] < 4
+    # a window beyond shared memory, or queries longer than the counters take: not stripe mode
+    assert psa.plan_stripes(5000, 1000, 600, 2)["ok"] == 0
+    assert psa.plan_stripes(200000, 1500, 64, 0)["ok"] == 0
+    # any plan: teams x warps fit the block, lanes cover the offsets, a split plan has one team
+    for len1, len2, nq in ((700, 300, 37), (2100, 1000, 11), (330, 64, 5000), (4200, 200, 700), (1055, 32, 50), (3000, 300, 600), (2600, 640, 900)):
+        p = psa.plan_stripes(len1, len2, nq, 0)
+        if p["ok"]:
+            assert p["lanes"] * 32 >= len1 - len2 + 1 and p["team_warps"] * p["teams"] <= 20 and p["blocks"] <= 148
+            assert p["passes"] == (p["queries_per_task"] * p["lanes"] + 31) // 32
+            if p["team_warps"] > p["passes"]:
+                assert p["teams"] == 1 and p["team_warps"] - p["passes"] <= 3
