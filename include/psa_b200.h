@@ -114,6 +114,8 @@ const char* psa_last_error(const psa_context* ctx);
                      while the kernel is already building its window; the kernel waits per task for the piece that holds the
                      task's queries | 0 one copy in front of the kernel
      "kernel_events" 1 psa_batch_run also brackets the dominant kernel with CUDA events ("main_kernel_ns")
+     "gather_small"  1 a one-shot problem whose Seq1 and queries fit 32 KB (the gpu_run_program case) gathers both in a page-locked
+                     buffer and sends them up as ONE copy | 0 one copy per sequence
      "min_split_work" a call is spread over at most (its pair evaluations / this value) of the context's GPUs, default 2.5e9
                      (~80 us of kernel per GPU: a shard pays its own copies, launch and wake-up whatever its size) | 0 always all
      "gate_timed_runs" 1 psa_batch_run enqueues its events and launches behind a gate (a stream wait on a page-locked word) that

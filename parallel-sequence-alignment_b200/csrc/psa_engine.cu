@@ -65,6 +65,8 @@ struct DeviceState {
     int64_t plan_key[5] = { -1, -1, -1, -1, -1 };   // (len1, len2, nq, rank planes asked, forced) of the cached stripe plan:
     StripeGeom plan_cached{};                        //   the planner's search over (Q, T) is not repeated for a repeated batch shape
     PinBuf h_qoff, h_tile_start, h_out;
+    DevBuf inbuf;              // small one-shot problems: Seq1 and the queries in ONE device buffer, filled by ONE copy from h_in
+    PinBuf h_in;
     // slice of the current batch owned by this GPU
     int q_begin = 0, q_end = 0;
     BatchGeom G{};
@@ -113,6 +115,7 @@ struct psa_context {
     int opt_zero_copy = 1;     // 1: result sets are written by the kernels straight into page-locked host memory (small ones; any size in stripe mode)
     long long opt_min_split_work = 2500000000ll;   // a call is spread over at most work / this many GPUs (pair evaluations; 0: always over all)
     int opt_gate_timed_runs = 0; // 1: psa_batch_run enqueues its events and launches behind a host-released gate (device time only in the bracket)
+    int opt_gather_small = 1;   // 1: a small one-shot problem's Seq1 and queries are gathered on the host and go up as one copy
     int opt_stream_queries = 1; // 1: one-shot stripe-mode batches copy their queries on a second stream while the kernel builds its window
     long long table_epoch = 0; // bumped whenever `table` is rebuilt
     bool one_shot = false;     // the batch being prepared belongs to a prepare + run + fetch call (psa_search_batch / _range)
@@ -194,9 +197,9 @@ void release(DeviceState& d)
 {
     cudaSetDevice(d.dev);
     for (DevBuf* b : { &d.seq1, &d.seq2s, &d.qoff, &d.tile_start, &d.tiles, &d.out, &d.lane_keys, &d.partial, &d.code_table,
-                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync, &d.table, &d.ready })
+                       &d.cls_planes, &d.rank_planes, &d.mutants, &d.sync, &d.table, &d.ready, &d.inbuf })
         if (b->p) cudaFree(b->p);
-    for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out })
+    for (PinBuf* b : { &d.h_qoff, &d.h_tile_start, &d.h_out, &d.h_in })
         if (b->p) cudaFreeHost(b->p);
     if (d.h_err) cudaFreeHost(d.h_err);
     if (d.h_tags) cudaFreeHost(d.h_tags);
@@ -275,6 +278,7 @@ void worker_loop(Worker* w)
 // k_stripe -- launched right after the copies are enqueued -- builds its window while they are in flight and waits per task
 // for the piece that holds the task's queries (stream_wait, psa_kernels.cuh).  Everything the kernel waits for is enqueued
 // BEFORE the kernel is, so a failing copy can never leave a launched kernel waiting.
+constexpr int64_t kGatherMaxBytes = 32 * 1024;      // Seq1 + padding + queries up to this size go up as one copy (one-shot calls)
 constexpr int kStreamMaxChunks = 8;
 constexpr int64_t kStreamChunkBytes = 512 * 1024;
 constexpr int64_t kStreamMinBytes = 64 * 1024;
@@ -522,10 +526,29 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
             return rc;
     }
 
-    PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
+    // A small one-shot problem (the gpu_run_program case: a few KB of Seq1 and one query) goes up as ONE copy: both
+    // sequences are gathered in a page-locked buffer first (a host memcpy of a few KB costs less than a second copy's
+    // enqueue and its turn on the copy engine, ~2.5 us), and land in one device buffer.
+    const void* dev_seq1 = d.seq1.p;
+    const void* dev_seq2s = d.seq2s.p;
+    const int64_t gather_at = (len1 + 64 + 255) & ~int64_t(255);            // the queries' place behind Seq1 and its padding
+    const bool gathered = ctx->one_shot && ctx->opt_gather_small != 0 && gather_at + seq2_bytes <= kGatherMaxBytes;
+    if (gathered) {
+        if ((rc = ensure_dev(ctx, d.inbuf, (size_t)kGatherMaxBytes + 256))) return rc;
+        if ((rc = ensure_pin(ctx, d.h_in, (size_t)kGatherMaxBytes + 256))) return rc;
+        std::memcpy(d.h_in.p, seq1, (size_t)len1);
+        std::memcpy((char*)d.h_in.p + gather_at, seq2s + byte0, (size_t)seq2_bytes);
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.inbuf.p, d.h_in.p, (size_t)(gather_at + seq2_bytes), cudaMemcpyHostToDevice, d.stream));
+        dev_seq1 = d.inbuf.p;
+        dev_seq2s = (const char*)d.inbuf.p + gather_at;
+    } else
+        PSA_CUDA(ctx, cudaMemcpyAsync(d.seq1.p, seq1, (size_t)len1, cudaMemcpyHostToDevice, d.stream));
     d.streamed = false;
     d.st_chunks = 0;
     d.P.ready = nullptr; d.P.ready_tag = 0; d.P.ready_chunks = 0; d.P.ready_chunk_bytes = 128;
+    if (gathered) {
+        // (both sequences are on their way)
+    } else
     if (ctx->one_shot && d.stripe.ok && ctx->opt_stream_queries != 0 && seq2_bytes >= kStreamMinBytes) {
         if ((rc = enqueue_streamed_queries(ctx, d, seq2s + byte0, seq2_bytes))) return rc;
     } else
@@ -543,8 +566,8 @@ int prepare_device(psa_context* ctx, DeviceState& d, const char* seq1, int64_t l
     d.G.total_tiles = (int32_t)tiles;
     d.G.tiles_per_query = uniform > 0 ? (int32_t)uniform : 0;
     d.G.uniform_len2 = uniform_len ? (int32_t)ctx->uniform_len2 : 0;
-    d.P.seq1 = (const uint8_t*)d.seq1.p;
-    d.P.seq2s = (const uint8_t*)d.seq2s.p;
+    d.P.seq1 = (const uint8_t*)dev_seq1;
+    d.P.seq2s = (const uint8_t*)dev_seq2s;
     d.P.qoff = (const int64_t*)d.qoff.p;
     d.P.tile_start = (const int32_t*)d.tile_start.p;
     d.P.tiles = (TileRec*)d.tiles.p;
@@ -757,6 +780,7 @@ int psa_set_option(psa_context* ctx, const char* name, long long value)
     if (!std::strcmp(name, "pack_queries") && value >= 0 && value <= kPackMaxQ) { ctx->opt_pack_queries = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "zero_copy_results") && value >= 0 && value <= 1) { ctx->opt_zero_copy = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "stream_queries") && value >= 0 && value <= 1) { ctx->opt_stream_queries = (int)value; return PSA_OK; }
+    if (!std::strcmp(name, "gather_small") && value >= 0 && value <= 1) { ctx->opt_gather_small = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "gate_timed_runs") && value >= 0 && value <= 1) { ctx->opt_gate_timed_runs = (int)value; return PSA_OK; }
     if (!std::strcmp(name, "min_split_work") && value >= 0) { ctx->opt_min_split_work = value; return PSA_OK; }
     if (!std::strcmp(name, "kernel_events") && value >= 0 && value <= 1) { ctx->opt_kernel_events = (int)value; return PSA_OK; }
@@ -1272,6 +1296,7 @@ int psa_search_many(psa_context* ctx, psa_problem* problems, int32_t nproblems, 
             lane->opt_engine = ctx->opt_engine; lane->opt_rank_planes = ctx->opt_rank_planes; lane->opt_scan_warps = ctx->opt_scan_warps;
             lane->opt_fused_finish = ctx->opt_fused_finish; lane->opt_derive_rank = ctx->opt_derive_rank; lane->opt_pack_queries = ctx->opt_pack_queries;
             lane->opt_zero_copy = ctx->opt_zero_copy; lane->opt_stream_queries = ctx->opt_stream_queries; lane->opt_slices = ctx->opt_slices;
+            lane->opt_gather_small = ctx->opt_gather_small;
             lane->opt_sliced_keys = ctx->opt_sliced_keys; lane->opt_batch_mode = ctx->opt_batch_mode; lane->opt_stripe_mode = ctx->opt_stripe_mode;
             lane->opt_single_launch = ctx->opt_single_launch;
             use.push_back(lane);
