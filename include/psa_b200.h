@@ -165,6 +165,11 @@ int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* que
    passes per task, warps per team, teams per block, blocks, dynamic shared memory in bytes }.  Pure host arithmetic. */
 int psa_plan_stripes(int64_t len1, int64_t len2, int32_t nq, int rank_pass, int sm_count, int shape[8]);
 
+/* How a one-shot stripe-mode call streams `bytes` of queries to the device while its kernel is already running (option
+   "stream_queries"): *pieces copies of *piece_bytes each (a multiple of 128; the last one shorter), every one followed by a
+   flag the kernel waits for; *pieces == 0: the batch is too small to bother (one plain copy).  Pure host arithmetic. */
+int psa_plan_stream_pieces(int64_t bytes, int* pieces, int64_t* piece_bytes);
+
 /* Merge per-shard answers of ONE query given in ascending offset-range order, under the reference
    order: strictly better score wins, ties keep the earlier shard = lower offsets
    (MPI_MAXLOC/MINLOC on (score, rank), cpu_funcs.c:73-76; is_swapable cuda_funcs.cu:290-307). */

@@ -131,6 +131,7 @@ def _sig():
                                      C.POINTER(_CShard)]
     _lib.psa_merge_results.argtypes = [C.c_int, C.POINTER(_CResult), C.c_int, C.POINTER(_CResult)]
     _lib.psa_plan_packing.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib.psa_plan_stream_pieces.argtypes = [C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     _lib.psa_plan_stripes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_int)]
     batch = [C.c_void_p, dp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     _lib.psa_search_batch.argtypes = batch + [C.POINTER(_CResult)]
@@ -248,6 +249,15 @@ def plan_stripes(len1: int, len2: int, nq: int, rank_planes: int = 0, sm_count: 
     if rc:
         raise PsaError(rc, "psa_plan_stripes")
     return dict(zip(("ok", "lanes", "queries_per_task", "passes", "team_warps", "teams", "blocks", "smem_bytes"), list(shape)))
+
+
+def plan_stream_pieces(nbytes: int):
+    """(pieces, piece_bytes) a one-shot stripe-mode call streams `nbytes` of queries in (psa_plan_stream_pieces; host only)."""
+    n, b = C.c_int(0), C.c_int64(0)
+    rc = _lib.psa_plan_stream_pieces(nbytes, C.byref(n), C.byref(b))
+    if rc:
+        raise PsaError(rc)
+    return n.value, b.value
 
 
 def merge_results(is_max: bool, parts: Sequence[Result]) -> Result:

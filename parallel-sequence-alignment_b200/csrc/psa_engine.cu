@@ -348,9 +348,10 @@ int enqueue_streamed_queries(psa_context* ctx, DeviceState& d, const char* src, 
         d.ready_tag = 0;
     }
     const int32_t tag = ++d.ready_tag;
-    int64_t chunks = std::min<int64_t>(std::max<int64_t>(bytes / kStreamChunkBytes, 1), kStreamMaxChunks);
-    const int64_t cb = ((bytes + chunks - 1) / chunks + 127) & ~int64_t(127);
-    chunks = (bytes + cb - 1) / cb;
+    int pieces = 0;
+    int64_t cb = 0;
+    psa_plan_stream_pieces(bytes, &pieces, &cb);
+    const int64_t chunks = pieces;
     static bool memops_ok = true;                                            // cleared for good the first time the driver refuses one
     const WriteValue32Fn wv = memops_ok ? stream_write_value32() : nullptr;
     for (int64_t c = 0; c < chunks; c++) {
@@ -872,6 +873,18 @@ int psa_plan_packing(int64_t len1, int64_t len2, int32_t nq, int force, int* que
     }
     *queries_per_block = best_q;
     *warps = best_q ? best_w : 0;
+    return PSA_OK;
+}
+
+int psa_plan_stream_pieces(int64_t bytes, int* pieces, int64_t* piece_bytes)
+{
+    if (!pieces || !piece_bytes || bytes < 0) return PSA_ERR_ARG;
+    *pieces = 0; *piece_bytes = 0;
+    if (bytes < kStreamMinBytes) return PSA_OK;                             // one plain copy in front of the kernel
+    int64_t chunks = std::min<int64_t>(std::max<int64_t>(bytes / kStreamChunkBytes, 1), kStreamMaxChunks);
+    const int64_t cb = ((bytes + chunks - 1) / chunks + 127) & ~int64_t(127);
+    *pieces = int((bytes + cb - 1) / cb);
+    *piece_bytes = cb;
     return PSA_OK;
 }
 

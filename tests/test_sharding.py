@@ -178,3 +178,19 @@ def test_stripe_plans(psa):
             assert p["passes"] == (p["queries_per_task"] * p["lanes"] + 31) // 32
             if p["team_warps"] > p["passes"]:
                 assert p["teams"] == 1 and p["team_warps"] - p["passes"] <= 3
+
+
+def test_stream_piece_plan(psa):
+    """How a one-shot stripe-mode call cuts its query copy into pieces (psa_plan_stream_pieces, host arithmetic): nothing
+    below 64 KB, pieces of at least 512 KB, at most eight, every piece a multiple of 128 bytes (the kernel waits for the piece
+    that holds the END of the last 128-byte line it will touch), together exactly covering the bytes."""
+    assert psa.plan_stream_pieces(0) == (0, 0) and psa.plan_stream_pieces(65535) == (0, 0)
+    assert psa.plan_stream_pieces(512000) == (1, 512000)                  # config 3
+    assert psa.plan_stream_pieces(65536 * 64) == (8, 524288)              # config 5
+    assert psa.plan_stream_pieces(8192 * 64) == (1, 524288)               # a GPU's share of config 5 on eight
+    for nbytes in (65536, 100001, 1 << 20, (1 << 20) + 1, 3_000_000, 4_480_000, 50_000_000, 2_000_000_001):
+        n, b = psa.plan_stream_pieces(nbytes)
+        assert 1 <= n <= 8 and b % 128 == 0 and (n - 1) * b < nbytes <= n * b
+        assert n == 1 or b >= 512 * 1024 or n == 8
+    with pytest.raises(psa.PsaError):
+        psa.plan_stream_pieces(-1)
