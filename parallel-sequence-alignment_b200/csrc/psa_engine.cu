@@ -319,8 +319,10 @@ struct TimedGate {
     int32_t tag = 0;
     void close(DeviceState& d, bool enabled)
     {
-        static bool ok = true;                                               // cleared for good the first time the driver refuses
-        const WriteValue32Fn wait = enabled && ok ? stream_wait_value32() : nullptr;
+        // Never under a tool that is injected into the CUDA calls (Nsight Compute profiles a kernel INSIDE its launch call,
+        // i.e. before the host gets to open the gate: the profiled kernel would wait behind it for ever).
+        static bool ok = std::getenv("CUDA_INJECTION64_PATH") == nullptr && std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr;
+        const WriteValue32Fn wait = enabled && ok ? stream_wait_value32() : nullptr;   // (ok is also cleared the first time the driver refuses)
         if (!wait) return;
         if (d.gate_tag >= 0x7FFFFFF0) d.gate_tag = 0;
         const int32_t t = ++d.gate_tag;
