@@ -478,25 +478,33 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
             for (int r = 0; r < kPlaneRows; r++) dst[(size_t(r) * Wn + p) * wstep] = m[r];
         }
         __syncthreads();
-        constexpr int kRowGroups = 4, kRowsPer = kPlaneRows / kRowGroups;                   // 28 rows = 4 x 7
-        for (int task = tid; task < S * nkinds * kRowGroups; task += nthreads) {
-            const int rg = task % kRowGroups, ck = task / kRowGroups;
-            const int kind = ck / S, p = ck - kind * S;
+        // Plane kinds that sit side by side as uint2 entries -- the two class planes, and the two rank planes where there are
+        // two -- are shifted along together: one 8-byte store per entry, and the lanes of a warp take CONSECUTIVE columns of
+        // the same rows, so a store is 256 contiguous bytes (the 4-byte stores of one kind at a time were every other word of
+        // four scattered rows: two to three shared-memory wavefronts each, and twice as many of them).  Seven groups of four
+        // rows per column.
+        constexpr int kRowsPer = 4, kRowGroups = kPlaneRows / kRowsPer;                      // 28 rows = 7 x 4
+        constexpr int npairs = kRank2 ? 2 : 1;
+        for (int task = tid; task < S * npairs * kRowGroups; task += nthreads) {
+            const int p = task % S, rest = task / S;
+            const int rg = rest % kRowGroups, pair = rest / kRowGroups;
             if (p + S >= Wn) continue;                                                      // a column with a single word
-            const uint32_t* col = T.col[kind];
-            uint32_t* dst = kind < 2 ? reinterpret_cast<uint32_t*>(s_cls) + kind : reinterpret_cast<uint32_t*>(s_rnk) + (kRank2 ? kind - 2 : 0);
-            const int wstep = (kind < 2 || kRank2) ? 2 : 1;
+            const uint32_t* col0 = T.col[2 * pair];
+            const uint32_t* col1 = T.col[2 * pair + 1];
+            uint2* dst = reinterpret_cast<uint2*>(pair == 0 ? s_cls : s_rnk);
             const int r0 = rg * kRowsPer;
-            uint32_t m[kRowsPer];
+            uint2 m[kRowsPer];
 #pragma unroll
-            for (int r = 0; r < kRowsPer; r++) m[r] = dst[(size_t(r0 + r) * Wn + p) * wstep];
+            for (int r = 0; r < kRowsPer; r++) m[r] = dst[size_t(r0 + r) * Wn + p];
             // four words per round: the (dependent) symbol and column loads of all four are issued before the first shift
             for (int word = p + S; word < Wn; word += 4 * S) {
-                uint32_t c[4];
+                uint32_t c0[4], c1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int w = word + u * S;
-                    c[u] = w < Wn ? col[s_seq1[w + 31 * S]] >> r0 : 0u;                     // the position that enters at bit 31
+                    const uint32_t sym = w < Wn ? s_seq1[w + 31 * S] : 31u;                 // the position that enters at bit 31
+                    c0[u] = col0[sym] >> r0;
+                    c1[u] = col1[sym] >> r0;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -504,9 +512,31 @@ k_stripe(const BatchGeom G, const BatchPtrs P, const StripeGeom SG, const __grid
                     if (w < Wn) {
 #pragma unroll
                         for (int r = 0; r < kRowsPer; r++) {
-                            m[r] = __funnelshift_r(m[r], c[u] >> r, 1);
-                            dst[(size_t(r0 + r) * Wn + w) * wstep] = m[r];
+                            m[r].x = __funnelshift_r(m[r].x, c0[u] >> r, 1);
+                            m[r].y = __funnelshift_r(m[r].y, c1[u] >> r, 1);
+                            dst[size_t(r0 + r) * Wn + w] = m[r];
                         }
+                    }
+                }
+            }
+        }
+        if constexpr (kRor) {
+            // the one rank plane at a 4-byte pitch: on its own
+            for (int task = tid; task < S * kRowGroups; task += nthreads) {
+                const int p = task % S, rg = task / S;
+                if (p + S >= Wn) continue;
+                const uint32_t* col = T.col[2];
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_rnk);
+                const int r0 = rg * kRowsPer;
+                uint32_t m[kRowsPer];
+#pragma unroll
+                for (int r = 0; r < kRowsPer; r++) m[r] = dst[size_t(r0 + r) * Wn + p];
+                for (int word = p + S; word < Wn; word += S) {
+                    const uint32_t c = col[s_seq1[word + 31 * S]] >> r0;
+#pragma unroll
+                    for (int r = 0; r < kRowsPer; r++) {
+                        m[r] = __funnelshift_r(m[r], c >> r, 1);
+                        dst[size_t(r0 + r) * Wn + word] = m[r];
                     }
                 }
             }
