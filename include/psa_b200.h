@@ -189,7 +189,7 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max,
                      psa_result* out);
 
 /* Many independent problems in one call, pipelined: the stacked blocks of an input file, the per-Seq1 batches of a query
-   stream.  Every device slot of the context runs `lanes_per_device` lanes (1..4; 0 = the default, 2), each lane its own
+   stream.  Every device slot of the context runs `lanes_per_device` lanes (1..8; 0 = the default, 2), each lane its own
    stream, buffers and host thread; the lanes take problems off a shared counter, so the copies, launch and wake-up of one
    problem overlap the kernel of another and the GPUs stay busy between problems (one psa_search_batch at a time leaves a
    GPU idle for the ~30 us either side of a 40 us kernel).  A problem is never split: with N GPUs, N x lanes problems are

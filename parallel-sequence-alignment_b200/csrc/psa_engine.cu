@@ -279,6 +279,7 @@ void worker_loop(Worker* w)
 // for the piece that holds the task's queries (stream_wait, psa_kernels.cuh).  Everything the kernel waits for is enqueued
 // BEFORE the kernel is, so a failing copy can never leave a launched kernel waiting.
 constexpr int64_t kGatherMaxBytes = 32 * 1024;      // Seq1 + padding + queries up to this size go up as one copy (one-shot calls)
+constexpr int kMaxLanes = 8;                       // psa_search_many: lanes per device slot
 constexpr int kStreamMaxChunks = 8;
 constexpr int64_t kStreamChunkBytes = 512 * 1024;
 constexpr int64_t kStreamMinBytes = 64 * 1024;
@@ -1290,18 +1291,18 @@ int psa_search_batch(psa_context* ctx, const double weights[4], int is_max, cons
 int psa_search_many(psa_context* ctx, psa_problem* problems, int32_t nproblems, int lanes_per_device)
 {
     if (!ctx) return PSA_ERR_ARG;
-    if (nproblems < 0 || (nproblems > 0 && !problems) || lanes_per_device < 0 || lanes_per_device > 4)
+    if (nproblems < 0 || (nproblems > 0 && !problems) || lanes_per_device < 0 || lanes_per_device > kMaxLanes)
         return fail(ctx, PSA_ERR_ARG, "psa_search_many: bad argument");
     if (nproblems == 0) return PSA_OK;
     const int per_dev = lanes_per_device ? lanes_per_device : 2;
     const int ndev = (int)ctx->devs.size();
     const size_t want = (size_t)ndev * per_dev;
-    // lane l of device slot g is lanes[g * 4 + l]; created on first use, kept for the life of the context
-    if (ctx->lanes.size() < (size_t)ndev * 4) ctx->lanes.resize((size_t)ndev * 4, nullptr);
+    // lane l of device slot g is lanes[g * kMaxLanes + l]; created on first use, kept for the life of the context
+    if (ctx->lanes.size() < (size_t)ndev * kMaxLanes) ctx->lanes.resize((size_t)ndev * kMaxLanes, nullptr);
     std::vector<psa_context*> use;
     for (int l = 0; l < per_dev; l++)                                // lane-major: few problems spread over the GPUs first
         for (int g = 0; g < ndev; g++) {
-            psa_context*& lane = ctx->lanes[(size_t)g * 4 + l];
+            psa_context*& lane = ctx->lanes[(size_t)g * kMaxLanes + l];
             if (!lane) {
                 const int dev = ctx->devs[g].dev;
                 const int rc = psa_create(&lane, &dev, 1);

@@ -706,7 +706,7 @@ def test_search_many_pipelined(psa, port, synth):
             assert all(same_answer(g, e) for g, e in zip(g_list, e_list))
 
     with psa.Context(1) as c:
-        for lanes in (0, 1, 3, 4):
+        for lanes in (0, 1, 3, 8):
             check(c.search_many(items, lanes=lanes))
         assert c.search_many([], lanes=2) == []
         bad = list(items)
@@ -715,7 +715,7 @@ def test_search_many_pipelined(psa, port, synth):
             c.search_many(bad, lanes=2)
         check(c.search_many(items, lanes=2))                               # the lanes recover
         with pytest.raises(psa.PsaError):
-            c.search_many(items, lanes=5)
+            c.search_many(items, lanes=9)
     with psa.Context(devices=[0, 0, 0]) as c:
         check(c.search_many(items, lanes=2))
         check(c.search_many(items[:2], lanes=2))                           # fewer problems than lanes

@@ -42,7 +42,7 @@ def main():
             t_seq = time.perf_counter() - t0
             print(json.dumps({"workload": name, "gpus": ngpus, "problems": total, "how": "psa_search_batch, one call at a time",
                               "us_per_problem": round(t_seq / total * 1e6, 2), "pair_evals_per_s": pe / t_seq}), flush=True)
-            for lanes in (1, 2, 3, 4):
+            for lanes in (1, 2, 3, 4, 6, 8):
                 c.search_many_raw(arr, min(total, 16 * ngpus), lanes)
                 best = None
                 for _ in range(3):
