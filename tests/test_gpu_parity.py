@@ -766,6 +766,28 @@ def test_stripe_split_plans_random(psa, ctx, port):
     assert seen_split >= 2, seen_split                                  # (pass counts that are multiples of four need no split)
 
 
+def test_small_calls_stay_on_one_device(psa, port, synth):
+    """A call is spread over at most (its pair evaluations / min_split_work) device slots: by default a small batch runs on
+    one slot of a multi-slot context (idle slots are not even woken), a larger one on as many as its work pays for, and
+    min_split_work = 0 splits everything; same answers every time."""
+    wl = synth.workload("c3", nq=512)                                     # 6.4e8 pair evaluations
+    exp = port.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries[:48])
+    with psa.Context(devices=[0, 0, 0]) as c:
+        for knob, used in ((None, 1), (300_000_000, 2), (100_000_000, 3), (0, 3)):
+            if knob is not None:
+                c.set_option("min_split_work", knob)
+            got = c.search_batch(wl.weights, wl.is_max, wl.seq1, wl.queries)
+            assert c.stat("devices_used") == used, (knob, c.stat("devices_used"))
+            assert all(same_answer(g, e) for g, e in zip(got, exp))
+        long1 = synth.letters(9, 60_000)                                  # a single query: offset ranges over the three slots
+        e1 = port.search(wl.weights, wl.is_max, long1, wl.queries[0], nthreads=8)
+        r = c.search(wl.weights, wl.is_max, long1, wl.queries[0])
+        assert c.stat("devices_used") == 3 and same_answer(r, e1)
+        c.set_option("min_split_work", 2_500_000_000)
+        r = c.search(wl.weights, wl.is_max, long1, wl.queries[0])
+        assert c.stat("devices_used") == 1 and same_answer(r, e1)
+
+
 def test_random_batches(ctx, port):
     """Random batches through the default dispatch (long / packed / batch mode, fused or separate finish, exact or
     re-scored order, zero-copy or copied results): equal-length and ragged, tiny and multi-tile, five alphabets."""
