@@ -343,9 +343,21 @@ def quick_measure(psa, synth, ctx, name, flush_l2, steps):
         t0 = time.perf_counter()
         ctx.search_batch_raw(wc, wl.is_max, batch, out)
         e2e += time.perf_counter() - t0
+    # the same problem as a pipelined list (psa_search_many): 8 lanes for the single-query configs, 2 for the batches
+    lanes = 8 if batch.nq == 1 else 2
+    n_list = 128 if batch.nq == 1 else max(8, 2 * steps)
+    outs = [ctx.new_result_array(batch.nq, pinned=True) for _ in range(min(n_list, 16))]
+    plist = ctx.make_problem_list([(wc, wl.is_max, batch, outs[k % len(outs)]) for k in range(n_list)])
+    ctx.search_many_raw(plist, n_list, lanes)
+    flush_l2()
+    t0 = time.perf_counter()
+    ctx.search_many_raw(plist, n_list, lanes)
+    t_list = time.perf_counter() - t0
     return {"workload": workload_name(name, wl), "pair_evals": batch.pair_evals, "steps": steps,
             "value": batch.pair_evals * steps / (ms * 1e-3), "ms_per_step": ms / steps,
             "e2e": batch.pair_evals * steps / e2e, "e2e_ms_per_step": 1e3 * e2e / steps,
+            "e2e_list": {"value": batch.pair_evals * n_list / t_list, "ms_per_step": 1e3 * t_list / n_list, "problems": n_list, "lanes": lanes,
+                         "how": "the same problem n times as one psa_search_many list (every entry pays its own copies), wall clock around the list"},
             "kernel": kernel_name(ctx), "launches_per_step": ctx.stat("kernel_launches"),
             "slices": ctx.stat("slices"), "exact_integer_keys": bool(ctx.stat("exact"))}
 
